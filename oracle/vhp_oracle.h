@@ -1,0 +1,101 @@
+/*
+ * vhp_oracle.h -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * Plain-C restatement of the reference's visibility / planner hot path
+ * (IbrahimSquared/visibility-heuristic-path-planner, src/visibilityBasedSolver.cpp).
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may load this library.  The product (libvhp_b200.so) never
+ * links, loads or calls anything in oracle/.
+ *
+ * Parity status: PINNED -- checked bit-for-bit against the unmodified reference
+ * compiled from /root/reference (oracle/_ref, see oracle/Makefile and
+ * oracle/ref_harness.cpp) and against the golden fixtures in tests/golden/
+ * generated from that build by oracle/gen_golden.py.
+ *
+ * Build flags that define the floating-point contract: -O2 -ffp-contract=off
+ * (strict IEEE-754 binary64, one rounding per operation, no FMA contraction).
+ *
+ * All 2-D fields use the reference's Field<T> layout: index = x + y*nx
+ * (include/environment/field.h:26-29).  Occupancy "complement" convention:
+ * 1.0 = free, 0.0 = occupied (src/environment.cpp:198-209).
+ */
+#ifndef VHP_ORACLE_H
+#define VHP_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* cameFrom_ sentinel: Field<size_t> filled with 1e15 (visibilityBasedSolver.cpp:46) */
+#define VHP_ORACLE_NO_PARENT 1000000000000000ULL
+
+/* status codes of solve(), in the order the reference tests them (:89-116,:134-139) */
+enum {
+  VHP_ORACLE_OK = 0,
+  VHP_ORACLE_START_OOB = 1,
+  VHP_ORACLE_END_OOB = 2,
+  VHP_ORACLE_START_OCCUPIED = 3,
+  VHP_ORACLE_END_OCCUPIED = 4,
+  VHP_ORACLE_MAX_ITER = 5
+};
+
+/* computeVisibility(), visibilityBasedSolver.cpp:570-696.  `vis` is read-modify-
+ * write exactly like the member visibility_ (no reset; cells the sweep never
+ * visits keep their previous content). */
+void vhp_oracle_compute_visibility(const double *occ, int nx, int ny, int sx,
+                                   int sy, double *vis);
+
+/* One planner sweep = resetQueue() + updateVisibility() + heap_->top(),
+ * visibilityBasedSolver.cpp:65-71, 379-565, 130.
+ *   vis      : local visibility, zeroed first (visibility_.reset(), :386)
+ *   vg       : global visibility, max-merged (:417-418)
+ *   came     : parents, first-writer-wins (:419-423)
+ *   ls_xy    : light sources so far, (x,y) pairs, at least nb+1 entries valid
+ *   nb       : nb_of_sources_ (label written into `came`)
+ *   top_xyh  : out, heap top {x, y} and *top_h; returns number of pushes
+ *              (0 => heap empty, top undefined in the reference). */
+long vhp_oracle_update_visibility(const double *occ, int nx, int ny, int sx,
+                                  int sy, int ex, int ey, double thr,
+                                  double *vis, double *vg, uint64_t *came,
+                                  const int *ls_xy, uint64_t nb, int *top_xy,
+                                  double *top_h);
+
+/* solve(), visibilityBasedSolver.cpp:76-160 (start/end already in the internal
+ * frame, i.e. after the mode-2 flip of :83-86).  Buffers are (re)initialised
+ * like reset() (:42-60).  ls_xy needs room for max_iter+2 points.
+ * On OK, ls_xy[nb] = end (:141).  Returns a status code above. */
+int vhp_oracle_solve(const double *occ, int nx, int ny, int sx, int sy, int ex,
+                     int ey, double thr, long max_iter, double *vis, double *vg,
+                     uint64_t *came, int *ls_xy, long *nb_of_sources);
+
+/* reconstructPath(), visibilityBasedSolver.cpp:1183-1213.  Writes the path
+ * start->end into path_xy (capacity path_cap points), returns the number of
+ * points; *length = sum of eval_d segment lengths. */
+long vhp_oracle_reconstruct_path(const uint64_t *came, int nx, const int *ls_xy,
+                                 int ex, int ey, int *path_xy, long path_cap,
+                                 double *length);
+
+/* raycasting() for every target cell, visibilityBasedSolver.cpp:267-290 called
+ * as in benchmark() :228-232 (i outer over x, j inner over y).  `ray` is
+ * read-modify-write like visibilityRayCasting_ (initialised to 1.0 in reset()). */
+void vhp_oracle_raycast_all(const double *occ, int nx, int ny, int sx, int sy,
+                            double *ray);
+
+/* generateNewEnvironmentFromSettings(), src/environment.cpp:40-88: glibc
+ * srand(seed) + 4 rand() per obstacle.  occ is filled with 1.0 then rectangles
+ * of 0.0. */
+void vhp_oracle_generate_environment(double *occ, int nx, int ny,
+                                     long nb_of_obstacles, long min_w,
+                                     long max_w, long min_h, long max_h,
+                                     int seed);
+
+/* eval_d(), include/solver/visibilityBasedSolver.h:112-115 */
+double vhp_oracle_eval_d(int sx, int sy, int tx, int ty);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
