@@ -1,0 +1,246 @@
+/*
+ * vhp.h -- C-ABI of libvhp_b200.so: the B200-native (sm_100a) replacement for the
+ * hot path of IbrahimSquared/visibility-heuristic-path-planner:
+ *
+ *     visibilityBasedSolver::computeVisibility   src/visibilityBasedSolver.cpp:570-696
+ *     visibilityBasedSolver::updateVisibility    src/visibilityBasedSolver.cpp:379-565
+ *     visibilityBasedSolver::solve               src/visibilityBasedSolver.cpp:76-160
+ *     visibilityBasedSolver::reconstructPath     src/visibilityBasedSolver.cpp:1183-1213
+ *     visibilityBasedSolver::raycasting (+loops) src/visibilityBasedSolver.cpp:267-290,228-232
+ *
+ * The reference has no plugin / FFI layer: its surface is the C++ class
+ * vbs::visibilityBasedSolver (include/solver/visibilityBasedSolver.h:23-175), the
+ * config file (src/parser.cpp) and the .txt files it writes under ./output
+ * (src/visibilityBasedSolver.cpp:1022-1178).  This header is what a binding for
+ * that surface would call; include/vhp_solver.hpp is the C++ drop-in class built
+ * on it and INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types.
+ *  - 2-D fields use the reference's Field<T> layout: index = x + y*nx
+ *    (include/environment/field.h:26-29).  Batches are [item][y][x].
+ *  - occupancy ("occupancy complement" in the reference): uint8, 1 = free,
+ *    0 = occupied (the reference stores 1.0 / 0.0 doubles, src/environment.cpp:198-209).
+ *  - coordinates are (x, y) int32 pairs in the solver's internal frame (what
+ *    ls_ / lightSources_ hold, i.e. after the mode-2 y flip of solve() :83-86).
+ *  - all arithmetic is IEEE binary64 in the reference's operation order with one
+ *    rounding per operation (no FMA contraction); VHP_F32 only rounds the final
+ *    value once when it is stored.
+ *  - functions ending in _dev take DEVICE pointers and enqueue on the context's
+ *    stream without synchronising; the others take HOST pointers, copy in/out
+ *    and return when the result is in the host buffers.
+ *  - every entry point returns a vhp_status; negative = failure (message via
+ *    vhp_last_error).  There is no CPU fallback: without a CUDA device every
+ *    compute entry point fails with VHP_ERR_NO_DEVICE.
+ */
+#ifndef VHP_H
+#define VHP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VHP_ABI_VERSION 1
+
+typedef struct vhp_context vhp_context; /* one device + one stream + workspace */
+
+typedef enum vhp_status {
+  /* solve() outcomes, in the order the reference tests them (:89-116, :134-139) */
+  VHP_OK = 0,
+  VHP_START_OOB = 1,      /* "Start point is out of bounds." */
+  VHP_END_OOB = 2,        /* "End point is out of bounds." */
+  VHP_START_OCCUPIED = 3, /* "Start point is not valid (occupied)" */
+  VHP_END_OCCUPIED = 4,   /* "End point is not valid (occupied)" */
+  VHP_MAX_ITER = 5,       /* "Max iters hit. Solution could not be found. ..." */
+  /* library failures */
+  VHP_ERR_INVALID_ARG = -1,
+  VHP_ERR_NO_DEVICE = -2,
+  VHP_ERR_CUDA = -3,
+  VHP_ERR_IO = -4,
+  VHP_ERR_UNSUPPORTED = -5
+} vhp_status;
+
+typedef enum vhp_dtype {
+  VHP_F32 = 0, /* fp64 on chip, rounded once to fp32 at the store */
+  VHP_F64 = 1  /* bit-identical to the reference's Field<double> */
+} vhp_dtype;
+
+/* cameFrom_ "no parent" marker.  The reference keeps Field<size_t> filled with
+ * 1e15 (:46); this library stores int32 parents with -1 and widens to the
+ * reference's value only in vhp_export_came_from_u64 / cameFrom.txt. */
+#define VHP_NO_PARENT (-1)
+#define VHP_NO_PARENT_U64 1000000000000000ULL
+
+/* ---- library / context ------------------------------------------------------ */
+int vhp_abi_version(void);
+const char *vhp_version_string(void);
+int vhp_device_count(void);                  /* 0 when there is no usable GPU */
+
+/* `cuda_stream` is a cudaStream_t (as void*) to enqueue on, or NULL to let the
+ * context create its own non-blocking stream. */
+vhp_status vhp_context_create(int device, void *cuda_stream, vhp_context **out);
+void vhp_context_destroy(vhp_context *ctx);
+vhp_status vhp_context_synchronize(vhp_context *ctx);
+const char *vhp_last_error(const vhp_context *ctx); /* ctx may be NULL: global */
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t vhp_launch_count(const vhp_context *ctx);
+
+/* diagnostic: the sweep kernels compute c = i/k as RN(1/k) plus one correction
+ * step instead of an IEEE divide; this counts the (i,k), 0 <= i < k <= kmax, for
+ * which the two differ on this device (must be 0; kmax <= 16384). */
+vhp_status vhp_selftest_ratio(vhp_context *ctx, int kmax, int64_t *mismatches);
+
+/* ---- a1: batched stand-alone visibility sweep (computeVisibility) ------------
+ * npairs independent (map, source) pairs.  pair p uses map src_map[p] (NULL ->
+ * map 0 for every pair) and source (src_xy[2p], src_xy[2p+1]).
+ *   out[p][y][x] = visibility_ after computeVisibility() started from an all-zero
+ *   field: cells the reference never writes (column 0 / row 0 when the source is
+ *   not on them) are 0.
+ * A source outside the grid fails the call with VHP_ERR_INVALID_ARG; an occupied
+ * source gives an all-zero field like the reference (v = 1*occ = 0). */
+vhp_status vhp_visibility_batch(vhp_context *ctx, const uint8_t *occ, int nmaps,
+                                int nx, int ny, const int32_t *src_xy,
+                                const int32_t *src_map, int64_t npairs,
+                                vhp_dtype dtype, void *out);
+vhp_status vhp_visibility_batch_dev(vhp_context *ctx, const uint8_t *d_occ,
+                                    int nmaps, int nx, int ny,
+                                    const int32_t *d_src_xy,
+                                    const int32_t *d_src_map, int64_t npairs,
+                                    vhp_dtype dtype, void *d_out);
+/* Optional, for repeated _dev calls on the same maps: packs the maps into the
+ * bit-plane layout the sweep kernel reads (row-major and column-major bit maps)
+ * once, so later vhp_visibility_batch_dev calls with the same d_occ pointer,
+ * nmaps, nx, ny skip the packing pass.  Invalidate by calling it again. */
+vhp_status vhp_prepare_maps_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps,
+                                int nx, int ny);
+
+/* ---- a5: batched ray casting (raycasting + the all-targets loop) -------------
+ * out[p][y][x] = visibilityRayCasting_ after the loop of benchmark() :228-232 on
+ * a field initialised to 1.0 (reset() :45). */
+vhp_status vhp_raycast_batch(vhp_context *ctx, const uint8_t *occ, int nmaps,
+                             int nx, int ny, const int32_t *src_xy,
+                             const int32_t *src_map, int64_t npairs,
+                             vhp_dtype dtype, void *out);
+vhp_status vhp_raycast_batch_dev(vhp_context *ctx, const uint8_t *d_occ,
+                                 int nmaps, int nx, int ny,
+                                 const int32_t *d_src_xy,
+                                 const int32_t *d_src_map, int64_t npairs,
+                                 vhp_dtype dtype, void *d_out);
+
+/* ---- a2-a4: batched planner (solve + reconstructPath) ------------------------
+ * nprob independent problems; problem q uses map prob_map[q] (NULL -> map 0),
+ * start (se_xy[4q], se_xy[4q+1]) and end (se_xy[4q+2], se_xy[4q+3]).
+ * The whole loop of solve() (:127-140) runs on the device: sweep with fused
+ * max-merge / first-writer parents / arg-min of h in heap push order, next
+ * source selection, end-visible test and max_iter check, with no host round trip.
+ * Outputs (any pointer may be NULL to skip it):
+ *   status[q]        vhp_status of problem q (0..5)
+ *   nb_sources[q]    nb_of_sources_ when solve() returned
+ *   light_sources    [q][ls_cap][2] int32: lightSources_[0..nb] (entry nb = end on
+ *                    VHP_OK, :141); ls_cap must be >= max_iter + 2
+ *   path_len[q]      reconstructPath() length (0 unless VHP_OK)
+ *   path_n[q], path  [q][ls_cap][2] int32 start->end points
+ *   vg               [q][ny][x] global visibility (dtype), came [q][ny][nx] int32
+ *                    parents (VHP_NO_PARENT where the reference holds 1e15),
+ *   vis              [q][ny][nx] local visibility of the last sweep (dtype) */
+typedef struct vhp_planner_out {
+  int32_t *status;
+  int32_t *nb_sources;
+  int32_t *light_sources;
+  double *path_len;
+  int32_t *path_n;
+  int32_t *path;
+  void *vg;
+  int32_t *came;
+  void *vis;
+} vhp_planner_out;
+
+vhp_status vhp_planner_batch(vhp_context *ctx, const uint8_t *occ, int nmaps,
+                             int nx, int ny, const int32_t *se_xy,
+                             const int32_t *prob_map, int64_t nprob,
+                             double threshold, int32_t max_iter, int32_t ls_cap,
+                             vhp_dtype dtype, const vhp_planner_out *out);
+vhp_status vhp_planner_batch_dev(vhp_context *ctx, const uint8_t *d_occ,
+                                 int nmaps, int nx, int ny,
+                                 const int32_t *d_se_xy,
+                                 const int32_t *d_prob_map, int64_t nprob,
+                                 double threshold, int32_t max_iter,
+                                 int32_t ls_cap, vhp_dtype dtype,
+                                 const vhp_planner_out *d_out);
+
+/* widen int32 parents to the reference's Field<size_t> content (host arrays) */
+void vhp_export_came_from_u64(const int32_t *came, int64_t n, uint64_t *out);
+
+/* ---- host-side boundary: config, environment, files ---------------------------
+ * struct Config of include/parser/parser.h:11-37, same fields and defaults. */
+typedef struct vhp_config {
+  int32_t mode;             /* 1 random environment, 2 image */
+  int64_t ncols, nrows;     /* nx, ny */
+  int64_t nb_of_obstacles;
+  int64_t min_width, max_width, min_height, max_height;
+  int32_t random_seed;      /* bool */
+  int32_t seed_value;
+  char image_path[1024];
+  int32_t start_x, start_y, end_x, end_y;
+  int64_t max_iter;
+  double visibility_threshold;
+  float light_strength;     /* parsed, unused (reference: lightStrength_ = 1.0) */
+  int32_t timer, save_results, save_local_visibility, save_came_from,
+      save_light_sources, save_global_visibility, save_visibility_field, silent;
+  int32_t ball_radius;
+} vhp_config;
+
+void vhp_config_default(vhp_config *cfg);
+/* ConfigParser::parse (src/parser.cpp:12-338): same keys, validation, messages
+ * and stdout echo.  Returns VHP_OK or VHP_ERR_IO / VHP_ERR_INVALID_ARG where the
+ * reference returns false. */
+vhp_status vhp_config_parse(const char *filename, vhp_config *cfg);
+
+/* environment::generateNewEnvironmentFromSettings (src/environment.cpp:40-88),
+ * glibc srand/rand stream, into occ[ny][nx] (uint8).  Returns the seed used. */
+vhp_status vhp_environment_generate(const vhp_config *cfg, uint8_t *occ,
+                                    int64_t *seed_used);
+/* environment::loadImage (src/environment.cpp:183-214): red channel == 255 ->
+ * free.  Reads PNG (8-bit gray/RGB/RGBA/palette, non-interlaced) and binary
+ * PGM/PPM.  First call with occ == NULL to get nx, ny. */
+vhp_status vhp_environment_load_image(const char *filename, uint8_t *occ,
+                                      int *nx, int *ny);
+
+/* Solver handle: the drop-in for one vbs::visibilityBasedSolver instance. */
+typedef struct vhp_solver vhp_solver;
+/* ctor (:13-37).  occ is copied (uint8 [ny][nx]). */
+vhp_status vhp_solver_create(vhp_context *ctx, const vhp_config *cfg,
+                             const uint8_t *occ, int nx, int ny,
+                             vhp_solver **out);
+void vhp_solver_destroy(vhp_solver *s);
+/* solve() (:76-160): same stdout lines (unless silent), same ./output files. */
+vhp_status vhp_solver_solve(vhp_solver *s);
+/* standAloneVisibility() (:165-189) and benchmark() (:194-262), benchmarkSeries()
+ * (:295-374; n_sizes <= 60 limits the series, 0 = all 60). */
+vhp_status vhp_solver_stand_alone_visibility(vhp_solver *s);
+vhp_status vhp_solver_benchmark(vhp_solver *s);
+vhp_status vhp_solver_benchmark_series(vhp_solver *s, int n_sizes);
+/* results of the last solve()/benchmark() (host copies, fp64 like the reference) */
+typedef enum vhp_field {
+  VHP_FIELD_VISIBILITY = 0,        /* visibility_           double[ny][nx] */
+  VHP_FIELD_VISIBILITY_GLOBAL = 1, /* visibility_global_    double[ny][nx] */
+  VHP_FIELD_CAME_FROM = 2,         /* cameFrom_             int32 [ny][nx] */
+  VHP_FIELD_RAYCASTING = 3,        /* visibilityRayCasting_ double[ny][nx] */
+  VHP_FIELD_OCCUPANCY = 4          /* occupancyComplement_  uint8 [ny][nx] */
+} vhp_field;
+vhp_status vhp_solver_get_field(const vhp_solver *s, vhp_field which, void *dst);
+int64_t vhp_solver_nb_of_sources(const vhp_solver *s);
+/* lightSources_[0..nb] and the reconstructed path; return the number of points */
+int64_t vhp_solver_light_sources(const vhp_solver *s, int32_t *xy, int64_t cap);
+int64_t vhp_solver_path(const vhp_solver *s, int32_t *xy, int64_t cap,
+                        double *length);
+/* saveResults() (:1022-1178) into `dir` ("./output" in the reference) */
+vhp_status vhp_solver_save_results(const vhp_solver *s, const char *dir);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VHP_H */

@@ -1,0 +1,150 @@
+"""K1 (visibility sweep) and K4 (ray casting) on the GPU, through the C-ABI,
+against the CPU oracle and the golden vectors.  Bit-exact in fp64; VHP_F32 output
+must equal the oracle's fp64 value rounded once to fp32."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, rect_map
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def vhp():
+    import visibility_heuristic_path_planner_b200 as m
+    return m
+
+
+@pytest.fixture(scope="module", params=["front", "naive"])
+def ctx(request, vhp):
+    os.environ["VHP_SWEEP_IMPL"] = request.param
+    c = vhp.Context(0)
+    os.environ.pop("VHP_SWEEP_IMPL")
+    yield c
+    c.close()
+
+
+def oracle_batch(oracle, occ, srcs):
+    return np.stack([oracle.compute_visibility(occ, sx, sy) for sx, sy in srcs])
+
+
+def test_ratio_exact_exhaustive(vhp):
+    c = vhp.Context(0)
+    assert c.selftest_ratio(4096) == 0
+    assert c.selftest_ratio(16384) == 0
+    c.close()
+
+
+def test_golden_sweeps(ctx, vhp):
+    g = load_golden("sweep.npz")
+    for k, (nx, ny, nobs, seed, sx, sy) in enumerate(g["cases"]):
+        occ = g[f"occ_{k}"]
+        out = ctx.visibility_batch(occ, [(sx, sy)], dtype=vhp.F64)[0]
+        assert np.array_equal(out, g[f"vis_{k}"]), (k, nx, ny, sx, sy)
+        out32 = ctx.visibility_batch(occ, [(sx, sy)], dtype=vhp.F32)[0]
+        assert np.array_equal(out32, g[f"vis_{k}"].astype(np.float32)), k
+    assert np.array_equal(ctx.visibility_batch(g["kat_diag_occ"], [(2, 2)])[0], g["kat_diag_vis"])
+    occ = np.ones((12, 10)); occ[5, 4] = 0
+    assert not ctx.visibility_batch(occ, [(4, 5)]).any()          # occupied source
+    seed, x, y = map(int, g["kat_flip"])
+    # strict-IEEE threshold decision (the -Ofast reference build flips this cell)
+    from oracle_py import Oracle
+    occ = Oracle().generate_environment(101, 101, 10, 10, 20, 10, 20, seed)
+    out = ctx.visibility_batch(occ, [(50, 50)])[0]
+    assert np.array_equal(out, g["kat_flip_vis"]) and out[y, x] == g["kat_flip_vals"][0]
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 9), (9, 1), (2, 2), (3, 5), (31, 33), (64, 64),
+                                   (127, 129), (130, 61), (257, 255), (256, 256), (300, 200),
+                                   (513, 40), (40, 517)])
+def test_random_maps_all_source_positions(ctx, vhp, oracle, shape):
+    nx, ny = shape
+    g = np.random.default_rng(nx * 1000 + ny)
+    occ = rect_map(nx, ny, (nx * ny) // 400, nx + ny, 1, 9)
+    srcs = [(0, 0), (nx - 1, 0), (0, ny - 1), (nx - 1, ny - 1), (nx // 2, ny // 2)]
+    srcs += [(int(g.integers(0, nx)), int(g.integers(0, ny))) for _ in range(11)]
+    ref = oracle_batch(oracle, occ, srcs)
+    out = ctx.visibility_batch(occ, srcs, dtype=vhp.F64)
+    bad = [(s, np.argwhere(o != r)[:3].tolist()) for s, o, r in zip(srcs, out, ref)
+           if not np.array_equal(o, r)]
+    assert not bad, bad[:3]
+    out32 = ctx.visibility_batch(occ, srcs, dtype=vhp.F32)
+    assert np.array_equal(out32, ref.astype(np.float32))
+
+
+def test_multi_map_batch(ctx, vhp, oracle):
+    nx, ny, nmaps = 96, 80, 7
+    maps = np.stack([rect_map(nx, ny, 10, 50 + m, 2, 12) for m in range(nmaps)])
+    g = np.random.default_rng(5)
+    src_map = g.integers(0, nmaps, 40).astype(np.int32)
+    srcs = np.stack([g.integers(0, nx, 40), g.integers(0, ny, 40)], axis=1).astype(np.int32)
+    out = ctx.visibility_batch(maps, srcs, src_map=src_map)
+    for p in range(40):
+        assert np.array_equal(out[p], oracle.compute_visibility(maps[src_map[p]], *srcs[p])), p
+
+
+def test_shipped_1000_config(ctx, vhp, oracle):
+    """config/settings.config of the reference (1000x1000, 15 obstacles, seed 1)."""
+    g = load_golden("shipped1000.npz")
+    occ = oracle.generate_environment(1000, 1000, 15, 100, 200, 100, 200, 1)
+    out = ctx.visibility_batch(occ, [(50, 50)], dtype=vhp.F64)[0]
+    s64, s32, sbin = g["seed1_cv_sha"]
+    assert sha(out) == s64
+    assert sha((out >= 0.25).astype(np.uint8)) == sbin      # thresholded visibility bit-exact
+    out32 = ctx.visibility_batch(occ, [(50, 50)], dtype=vhp.F32)[0]
+    assert sha(out32) == s32
+    empty = ctx.visibility_batch(np.ones((1000, 1000)), [(500, 500)])[0]
+    assert sha(empty) == g["empty_cv_sha"][0]
+
+
+def test_1000_random_sources_vs_oracle(ctx, vhp, oracle):
+    occ = oracle.generate_environment(1000, 1000, 15, 100, 200, 100, 200, 3)
+    g = np.random.default_rng(11)
+    srcs = [(int(g.integers(0, 1000)), int(g.integers(0, 1000))) for _ in range(6)]
+    srcs += [(0, 999), (999, 0), (3, 4), (996, 997)]
+    out = ctx.visibility_batch(occ, srcs, dtype=vhp.F64)
+    for s, o in zip(srcs, out):
+        assert np.array_equal(o, oracle.compute_visibility(occ, *s)), s
+
+
+def test_front_equals_naive_full_size(vhp):
+    """Size-independent property at BASELINE size: the tuned kernel and the simple
+    kernel agree bit-for-bit on a 64-source 1000x1000 batch."""
+    from oracle_py import Oracle
+    occ = Oracle().generate_environment(1000, 1000, 40, 20, 120, 20, 120, 9)
+    g = np.random.default_rng(3)
+    srcs = np.stack([g.integers(0, 1000, 64), g.integers(0, 1000, 64)], axis=1)
+    os.environ["VHP_SWEEP_IMPL"] = "naive"
+    a = vhp.Context(0)
+    os.environ.pop("VHP_SWEEP_IMPL")
+    b = vhp.Context(0)
+    ra = a.visibility_batch(occ, srcs, dtype=vhp.F64)
+    rb = b.visibility_batch(occ, srcs, dtype=vhp.F64)
+    assert np.array_equal(ra, rb)
+    assert ra.min() >= 0.0 and ra.max() <= 1.0
+    a.close(); b.close()
+
+
+def test_out_of_grid_source_is_an_error(ctx, vhp):
+    with pytest.raises(vhp.VhpError) as e:
+        ctx.visibility_batch(np.ones((8, 8)), [(8, 0)])
+    assert e.value.status == -1
+
+
+def test_raycast_vs_oracle(ctx, vhp, oracle):
+    g = load_golden("sweep.npz")
+    for k, (nx, ny, nobs, seed, sx, sy) in enumerate(g["cases"]):
+        out = ctx.raycast_batch(g[f"occ_{k}"], [(sx, sy)], dtype=vhp.F64)[0]
+        assert np.array_equal(out, g[f"ray_{k}"]), k
+    occ = rect_map(200, 150, 40, 8, 3, 15)
+    srcs = [(0, 0), (199, 149), (100, 75), (17, 140)]
+    out = ctx.raycast_batch(occ, srcs, dtype=vhp.F32)
+    for s, o in zip(srcs, out):
+        assert np.array_equal(o, oracle.raycast_all(occ, *s).astype(np.float32)), s

@@ -1,0 +1,225 @@
+"""visibility_heuristic_path_planner_b200 -- ctypes binding of libvhp_b200.so.
+
+The product is the C-ABI in include/vhp.h (CUDA kernels for sm_100a + C++ host
+boundary).  This module is only the thin Python view of it used by tests/ and
+bench.py: numpy arrays go through the host-buffer entry points, torch CUDA
+tensors through the *_dev entry points (pointers via .data_ptr(), the context
+enqueues on torch's current stream).
+
+There is no CPU fallback: `Context()` raises when the library is missing or no
+sm_100 device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "lib", "libvhp_b200.so")
+
+F32, F64 = 0, 1
+NO_PARENT = -1
+STATUS_NAMES = {0: "OK", 1: "START_OOB", 2: "END_OOB", 3: "START_OCCUPIED",
+                4: "END_OCCUPIED", 5: "MAX_ITER", -1: "ERR_INVALID_ARG",
+                -2: "ERR_NO_DEVICE", -3: "ERR_CUDA", -4: "ERR_IO", -5: "ERR_UNSUPPORTED"}
+
+
+class VhpError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {msg}")
+        self.status = status
+
+
+class PlannerOut(C.Structure):
+    _fields_ = [("status", C.c_void_p), ("nb_sources", C.c_void_p),
+                ("light_sources", C.c_void_p), ("path_len", C.c_void_p),
+                ("path_n", C.c_void_p), ("path", C.c_void_p), ("vg", C.c_void_p),
+                ("came", C.c_void_p), ("vis", C.c_void_p)]
+
+
+class Config(C.Structure):
+    """struct vhp_config (mirror of the reference's struct Config)."""
+    _fields_ = [("mode", C.c_int32), ("ncols", C.c_int64), ("nrows", C.c_int64),
+                ("nb_of_obstacles", C.c_int64), ("min_width", C.c_int64),
+                ("max_width", C.c_int64), ("min_height", C.c_int64),
+                ("max_height", C.c_int64), ("random_seed", C.c_int32),
+                ("seed_value", C.c_int32), ("image_path", C.c_char * 1024),
+                ("start_x", C.c_int32), ("start_y", C.c_int32), ("end_x", C.c_int32),
+                ("end_y", C.c_int32), ("max_iter", C.c_int64),
+                ("visibility_threshold", C.c_double), ("light_strength", C.c_float),
+                ("timer", C.c_int32), ("save_results", C.c_int32),
+                ("save_local_visibility", C.c_int32), ("save_came_from", C.c_int32),
+                ("save_light_sources", C.c_int32), ("save_global_visibility", C.c_int32),
+                ("save_visibility_field", C.c_int32), ("silent", C.c_int32),
+                ("ball_radius", C.c_int32)]
+
+
+_lib = None
+
+
+def load_library(build_if_missing: bool = True):
+    """dlopen libvhp_b200.so (building it in-tree first if it is absent)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise FileNotFoundError(LIB_PATH)
+        from .build import build
+        build()
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    lib.vhp_abi_version.restype = C.c_int
+    lib.vhp_version_string.restype = C.c_char_p
+    lib.vhp_device_count.restype = C.c_int
+    lib.vhp_context_create.argtypes = [i32, vp, C.POINTER(vp)]
+    lib.vhp_context_destroy.argtypes = [vp]
+    lib.vhp_context_destroy.restype = None
+    lib.vhp_context_synchronize.argtypes = [vp]
+    lib.vhp_last_error.argtypes = [vp]
+    lib.vhp_last_error.restype = C.c_char_p
+    lib.vhp_launch_count.argtypes = [vp]
+    lib.vhp_launch_count.restype = i64
+    batch = [vp, vp, i32, i32, i32, vp, vp, i64, i32, vp]
+    for name in ("vhp_visibility_batch", "vhp_visibility_batch_dev", "vhp_raycast_batch",
+                 "vhp_raycast_batch_dev"):
+        getattr(lib, name).argtypes = batch
+    lib.vhp_prepare_maps_dev.argtypes = [vp, vp, i32, i32, i32]
+    plan = [vp, vp, i32, i32, i32, vp, vp, i64, C.c_double, C.c_int32, C.c_int32, i32,
+            C.POINTER(PlannerOut)]
+    lib.vhp_planner_batch.argtypes = plan
+    lib.vhp_planner_batch_dev.argtypes = plan
+    lib.vhp_selftest_ratio.argtypes = [vp, i32, C.POINTER(i64)]
+    lib.vhp_export_came_from_u64.argtypes = [vp, i64, vp]
+    lib.vhp_export_came_from_u64.restype = None
+    _lib = lib
+    return lib
+
+
+def _np_ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _occ_u8(occ):
+    """(ny, nx) or (nmaps, ny, nx) -> contiguous uint8 (1 free / 0 occupied)."""
+    occ = np.asarray(occ)
+    if occ.ndim == 2:
+        occ = occ[None]
+    return np.ascontiguousarray(occ != 0, dtype=np.uint8)
+
+
+class Context:
+    """One device + stream + workspace (vhp_context)."""
+
+    def __init__(self, device: int = 0, stream=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        st = self.lib.vhp_context_create(int(device), stream, C.byref(h))
+        if st != 0:
+            raise VhpError(st, self.lib.vhp_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vhp_context_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st < 0:
+            raise VhpError(st, self.lib.vhp_last_error(self.h).decode())
+        return st
+
+    def synchronize(self):
+        self._check(self.lib.vhp_context_synchronize(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.vhp_launch_count(self.h))
+
+    def selftest_ratio(self, kmax: int) -> int:
+        bad = C.c_int64(-1)
+        self._check(self.lib.vhp_selftest_ratio(self.h, int(kmax), C.byref(bad)))
+        return bad.value
+
+    # ---- host (numpy) entry points ------------------------------------------
+    def _batch_host(self, fn, occ, src_xy, src_map, dtype):
+        occ = _occ_u8(occ)
+        nmaps, ny, nx = occ.shape
+        xy = np.ascontiguousarray(src_xy, dtype=np.int32).reshape(-1, 2)
+        n = xy.shape[0]
+        mp = None if src_map is None else np.ascontiguousarray(src_map, dtype=np.int32)
+        out = np.empty((n, ny, nx), dtype=np.float32 if dtype == F32 else np.float64)
+        self._check(fn(self.h, _np_ptr(occ), nmaps, nx, ny, _np_ptr(xy), _np_ptr(mp), n,
+                       dtype, _np_ptr(out)))
+        return out
+
+    def visibility_batch(self, occ, src_xy, src_map=None, dtype=F64):
+        """computeVisibility for every (map, source) pair -> (npairs, ny, nx)."""
+        return self._batch_host(self.lib.vhp_visibility_batch, occ, src_xy, src_map, dtype)
+
+    def raycast_batch(self, occ, src_xy, src_map=None, dtype=F64):
+        return self._batch_host(self.lib.vhp_raycast_batch, occ, src_xy, src_map, dtype)
+
+    def planner_batch(self, occ, start_end, prob_map=None, threshold=0.5, max_iter=100,
+                      dtype=F64, fields=True):
+        """solve() + reconstructPath() for every problem.  Returns a dict of numpy
+        arrays (status, nb_sources, light_sources, path_len, path_n, path[, vg,
+        came, vis])."""
+        occ = _occ_u8(occ)
+        nmaps, ny, nx = occ.shape
+        se = np.ascontiguousarray(start_end, dtype=np.int32).reshape(-1, 4)
+        n = se.shape[0]
+        mp = None if prob_map is None else np.ascontiguousarray(prob_map, dtype=np.int32)
+        cap = int(max_iter) + 2
+        ft = np.float32 if dtype == F32 else np.float64
+        r = dict(status=np.zeros(n, np.int32), nb_sources=np.zeros(n, np.int32),
+                 light_sources=np.zeros((n, cap, 2), np.int32), path_len=np.zeros(n),
+                 path_n=np.zeros(n, np.int32), path=np.zeros((n, cap, 2), np.int32))
+        if fields:
+            r.update(vg=np.zeros((n, ny, nx), ft), came=np.zeros((n, ny, nx), np.int32),
+                     vis=np.zeros((n, ny, nx), ft))
+        po = PlannerOut(*[_np_ptr(r.get(k)) for k in
+                          ("status", "nb_sources", "light_sources", "path_len", "path_n",
+                           "path", "vg", "came", "vis")])
+        self._check(self.lib.vhp_planner_batch(self.h, _np_ptr(occ), nmaps, nx, ny,
+                                               _np_ptr(se), _np_ptr(mp), n, float(threshold),
+                                               int(max_iter), cap, dtype, C.byref(po)))
+        return r
+
+    # ---- device (torch) entry points ----------------------------------------
+    def visibility_batch_dev(self, occ_t, src_xy_t, out_t, src_map_t=None):
+        """occ_t uint8 (nmaps, ny, nx), src_xy_t int32 (n, 2), out_t float32/64
+        (n, ny, nx); all CUDA tensors, contiguous.  Asynchronous."""
+        nmaps, ny, nx = occ_t.shape
+        dtype = F32 if out_t.element_size() == 4 else F64
+        self._check(self.lib.vhp_visibility_batch_dev(
+            self.h, occ_t.data_ptr(), nmaps, nx, ny, src_xy_t.data_ptr(),
+            None if src_map_t is None else src_map_t.data_ptr(), src_xy_t.shape[0], dtype,
+            out_t.data_ptr()))
+
+    def raycast_batch_dev(self, occ_t, src_xy_t, out_t, src_map_t=None):
+        nmaps, ny, nx = occ_t.shape
+        dtype = F32 if out_t.element_size() == 4 else F64
+        self._check(self.lib.vhp_raycast_batch_dev(
+            self.h, occ_t.data_ptr(), nmaps, nx, ny, src_xy_t.data_ptr(),
+            None if src_map_t is None else src_map_t.data_ptr(), src_xy_t.shape[0], dtype,
+            out_t.data_ptr()))
+
+    def prepare_maps_dev(self, occ_t):
+        nmaps, ny, nx = occ_t.shape
+        self._check(self.lib.vhp_prepare_maps_dev(self.h, occ_t.data_ptr(), nmaps, nx, ny))
+
+
+def torch_context(device: int, stream) -> Context:
+    """Context that enqueues on the given torch.cuda.Stream (time it with events
+    recorded on that stream)."""
+    return Context(device, C.c_void_p(stream.cuda_stream))

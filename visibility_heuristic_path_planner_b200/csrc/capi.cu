@@ -1,0 +1,399 @@
+// capi.cu -- extern "C" entry points of include/vhp.h: context management and the
+// batched sweep / ray-casting / planner calls.  Plain pointers in, status out.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "vhp_internal.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+vhp_status fail(vhp_context *ctx, vhp_status st, const std::string &msg) {
+  g_last_error = msg;
+  if (ctx) ctx->last_error = msg;
+  return st;
+}
+
+vhp_status cuda_fail(vhp_context *ctx, cudaError_t e, const char *what) {
+  return fail(ctx, VHP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define VHP_CUDA(ctx, call)                                   \
+  do {                                                        \
+    cudaError_t e_ = (call);                                  \
+    if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);  \
+  } while (0)
+
+vhp_status ensure(vhp_context *ctx, VhpDevBuf &b, size_t bytes) {
+  if (bytes <= b.cap) return VHP_OK;
+  if (b.p) {
+    VHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    VHP_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    VHP_CUDA(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  VHP_CUDA(ctx, cudaMalloc(&b.p, bytes));
+  b.cap = bytes;
+  return VHP_OK;
+}
+
+vhp_status ensure_rcp(vhp_context *ctx, int len) {
+  if (len <= ctx->rcp_len) return VHP_OK;
+  len = std::max(len, 4096 + 8);
+  if (ctx->rcp_table) {
+    VHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    VHP_CUDA(ctx, cudaFree(ctx->rcp_table));
+    ctx->rcp_table = nullptr;
+  }
+  VHP_CUDA(ctx, cudaMalloc(&ctx->rcp_table, (size_t)len * sizeof(double)));
+  VHP_CUDA(ctx, vhp_launch_rcp_table(ctx->rcp_table, len, ctx->stream, &ctx->launches));
+  ctx->rcp_len = len;
+  return VHP_OK;
+}
+
+// (re)build the bit planes for d_occ unless they are cached for this pointer
+vhp_status pack_maps(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx, int ny,
+                     bool force) {
+  if (!force && ctx->packed_sticky && ctx->packed_src == d_occ &&
+      ctx->packed_nmaps == nmaps && ctx->packed_nx == nx && ctx->packed_ny == ny)
+    return VHP_OK;
+  ctx->packed_sticky = false;
+  const int wpr = vhp_words_padded(nx), wpc = vhp_words_padded(ny);
+  const size_t row_plane = (size_t)ny * wpr, col_plane = (size_t)nx * wpc;
+  const size_t bytes = (size_t)nmaps * (row_plane + col_plane) * sizeof(uint32_t);
+  if (bytes > ctx->packed_bytes) {
+    if (ctx->packed_buf) {
+      VHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      VHP_CUDA(ctx, cudaFree(ctx->packed_buf));
+      ctx->packed_buf = nullptr;
+    }
+    VHP_CUDA(ctx, cudaMalloc(&ctx->packed_buf, bytes));
+    ctx->packed_bytes = bytes;
+  }
+  uint32_t *rowbits = ctx->packed_buf;
+  uint32_t *colbits = ctx->packed_buf + (size_t)nmaps * row_plane;
+  VHP_CUDA(ctx, vhp_launch_pack_maps(d_occ, nmaps, nx, ny, rowbits, colbits, wpr, wpc,
+                                     ctx->stream, &ctx->launches));
+  ctx->packed.rowbits = rowbits;
+  ctx->packed.colbits = colbits;
+  ctx->packed.wpr = wpr;
+  ctx->packed.wpc = wpc;
+  ctx->packed.row_plane = row_plane;
+  ctx->packed.col_plane = col_plane;
+  ctx->packed_src = d_occ;
+  ctx->packed_nmaps = nmaps;
+  ctx->packed_nx = nx;
+  ctx->packed_ny = ny;
+  return VHP_OK;
+}
+
+vhp_status check_common(vhp_context *ctx, const void *occ, int nmaps, int nx, int ny,
+                        const void *xy, int64_t n, int dtype, const void *out) {
+  if (!ctx) return fail(nullptr, VHP_ERR_INVALID_ARG, "null context");
+  if (!occ || !xy || !out) return fail(ctx, VHP_ERR_INVALID_ARG, "null buffer");
+  if (nmaps < 1 || nx < 1 || ny < 1 || n < 0)
+    return fail(ctx, VHP_ERR_INVALID_ARG, "bad sizes");
+  if ((int64_t)nx * ny > (int64_t)1 << 30 || nx > 16384 || ny > 16384)
+    return fail(ctx, VHP_ERR_UNSUPPORTED, "grid larger than 16384 x 16384 is not supported");
+  if (dtype != VHP_F32 && dtype != VHP_F64) return fail(ctx, VHP_ERR_INVALID_ARG, "bad dtype");
+  return VHP_OK;
+}
+
+// host-side validation of (x, y[, map]) items
+vhp_status check_points(vhp_context *ctx, const int32_t *xy, int per_item, const int32_t *maps,
+                        int64_t n, int nmaps, int nx, int ny, const char *what) {
+  for (int64_t i = 0; i < n; ++i) {
+    if (maps && (maps[i] < 0 || maps[i] >= nmaps))
+      return fail(ctx, VHP_ERR_INVALID_ARG, std::string(what) + ": map index out of range");
+    if (per_item == 2) {
+      const int x = xy[2 * i], y = xy[2 * i + 1];
+      if (x < 0 || x >= nx || y < 0 || y >= ny)
+        return fail(ctx, VHP_ERR_INVALID_ARG,
+                    std::string(what) + ": source outside the grid at item " + std::to_string(i));
+    }
+  }
+  return VHP_OK;
+}
+
+vhp_status check_device_error(vhp_context *ctx) {
+  int flag = 0;
+  VHP_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+  VHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (flag) {
+    VHP_CUDA(ctx, cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+    return fail(ctx, VHP_ERR_INVALID_ARG, "a source / start / end point lies outside the grid");
+  }
+  return VHP_OK;
+}
+
+enum class Op { Sweep, Raycast };
+
+vhp_status run_dev(vhp_context *ctx, Op op, const uint8_t *d_occ, int nmaps, int nx, int ny,
+                   const int32_t *d_xy, const int32_t *d_map, int64_t n, vhp_dtype dtype,
+                   void *d_out) {
+  if (n == 0) return VHP_OK;
+  if (op == Op::Raycast) {
+    VHP_CUDA(ctx, vhp_launch_raycast(d_occ, nx, ny, d_xy, d_map, n, dtype, d_out, ctx->d_err,
+                                     ctx->stream, &ctx->launches));
+    return VHP_OK;
+  }
+  const size_t esz = dtype == VHP_F32 ? 4 : 8;
+  const bool aligned = ((uintptr_t)d_out % 16) == 0 && ((size_t)nx * ny * esz) % 16 == 0;
+  const int n_max = std::max(nx, ny);
+  const bool front_fits = vhp_sweep_front_supported(nx, ny) && n_max <= 128 * 26;
+  if (ctx->sweep_impl == 0 && front_fits && aligned) {
+    vhp_status st = ensure_rcp(ctx, n_max + 8);
+    if (st != VHP_OK) return st;
+    st = pack_maps(ctx, d_occ, nmaps, nx, ny, false);
+    if (st != VHP_OK) return st;
+    VHP_CUDA(ctx, vhp_launch_sweep_front(ctx->packed, nx, ny, d_xy, d_map, n, dtype, d_out,
+                                         ctx->rcp_table, ctx->d_err, ctx->stream,
+                                         &ctx->launches));
+    return VHP_OK;
+  }
+  // reference kernel: chunk so that the scratch fronts stay small
+  const int64_t chunk = 4096;
+  vhp_status st = ensure(ctx, ctx->b_scratch, vhp_sweep_naive_scratch_bytes(nx, ny, std::min(n, chunk)));
+  if (st != VHP_OK) return st;
+  for (int64_t p0 = 0; p0 < n; p0 += chunk) {
+    const int64_t np = std::min(chunk, n - p0);
+    VHP_CUDA(ctx, vhp_launch_sweep_naive(d_occ, nx, ny, d_xy + 2 * p0, d_map ? d_map + p0 : nullptr,
+                                         np, dtype, (char *)d_out + (size_t)p0 * nx * ny * esz,
+                                         (double *)ctx->b_scratch.p, ctx->d_err, ctx->stream,
+                                         &ctx->launches));
+  }
+  return VHP_OK;
+}
+
+// host buffers: upload, run in chunks, overlap the D2H of chunk c with the
+// kernel of chunk c+1 (two device buffers, copy stream)
+vhp_status run_host(vhp_context *ctx, Op op, const uint8_t *occ, int nmaps, int nx, int ny,
+                    const int32_t *xy, const int32_t *maps, int64_t n, vhp_dtype dtype,
+                    void *out) {
+  vhp_status st = check_common(ctx, occ, nmaps, nx, ny, xy, n, dtype, out);
+  if (st != VHP_OK) return st;
+  st = check_points(ctx, xy, 2, maps, n, nmaps, nx, ny,
+                    op == Op::Sweep ? "vhp_visibility_batch" : "vhp_raycast_batch");
+  if (st != VHP_OK) return st;
+  if (n == 0) return VHP_OK;
+  VHP_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t cells = (size_t)nx * ny, esz = dtype == VHP_F32 ? 4 : 8;
+  const size_t occ_bytes = (size_t)nmaps * cells;
+  if ((st = ensure(ctx, ctx->b_occ, occ_bytes)) != VHP_OK) return st;
+  if ((st = ensure(ctx, ctx->b_src, (size_t)n * 2 * sizeof(int32_t))) != VHP_OK) return st;
+  if (maps && (st = ensure(ctx, ctx->b_map, (size_t)n * sizeof(int32_t))) != VHP_OK) return st;
+  VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_occ.p, occ, occ_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_src.p, xy, (size_t)n * 2 * sizeof(int32_t),
+                                cudaMemcpyHostToDevice, ctx->stream));
+  if (maps)
+    VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_map.p, maps, (size_t)n * sizeof(int32_t),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+  ctx->packed_src = nullptr; // b_occ content changed
+  ctx->packed_sticky = false;
+  if (op == Op::Sweep && ctx->sweep_impl == 0) { // pack once for all chunks
+    if ((st = pack_maps(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, true)) != VHP_OK)
+      return st;
+    ctx->packed_sticky = true;
+  }
+  const size_t chunk_bytes_target = (size_t)1 << 30;
+  int64_t chunk = std::max<int64_t>(1, (int64_t)(chunk_bytes_target / (cells * esz)));
+  chunk = std::min(chunk, n);
+  const size_t buf_bytes = (size_t)chunk * cells * esz;
+  if ((st = ensure(ctx, ctx->b_out[0], buf_bytes)) != VHP_OK) return st;
+  if (n > chunk && (st = ensure(ctx, ctx->b_out[1], buf_bytes)) != VHP_OK) return st;
+  // pin the caller's buffer for full-rate async copies (ignore "already pinned")
+  const size_t out_bytes = (size_t)n * cells * esz;
+  const bool registered =
+      cudaHostRegister(out, out_bytes, cudaHostRegisterDefault) == cudaSuccess;
+  (void)cudaGetLastError();
+  const int32_t *d_xy = (const int32_t *)ctx->b_src.p;
+  const int32_t *d_map = maps ? (const int32_t *)ctx->b_map.p : nullptr;
+  vhp_status result = VHP_OK;
+  int it = 0;
+  for (int64_t p0 = 0; p0 < n && result == VHP_OK; p0 += chunk, ++it) {
+    const int b = it & 1;
+    const int64_t np = std::min(chunk, n - p0);
+    if (it >= 2) { // the copy that last read this buffer must be done
+      cudaError_t e = cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0);
+      if (e != cudaSuccess) { result = cuda_fail(ctx, e, "cudaStreamWaitEvent"); break; }
+    }
+    result = run_dev(ctx, op, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, d_xy + 2 * p0,
+                     d_map ? d_map + p0 : nullptr, np, dtype, ctx->b_out[b].p);
+    if (result != VHP_OK) break;
+    cudaEventRecord(ctx->ev_done[b], ctx->stream);
+    cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0);
+    cudaError_t e = cudaMemcpyAsync((char *)out + (size_t)p0 * cells * esz, ctx->b_out[b].p,
+                                    (size_t)np * cells * esz, cudaMemcpyDeviceToHost,
+                                    ctx->copy_stream);
+    if (e != cudaSuccess) { result = cuda_fail(ctx, e, "cudaMemcpyAsync D2H"); break; }
+    cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream);
+  }
+  cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream);
+  cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+  if (registered) cudaHostUnregister(out);
+  ctx->packed_sticky = false;
+  ctx->packed_src = nullptr;
+  if (result != VHP_OK) return result;
+  if (e1 != cudaSuccess) return cuda_fail(ctx, e1, "sync copy stream");
+  if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "sync stream");
+  return check_device_error(ctx);
+}
+
+} // namespace
+
+extern "C" {
+
+int vhp_abi_version(void) { return VHP_ABI_VERSION; }
+
+const char *vhp_version_string(void) {
+  return "vhp_b200 0.1 (sm_100a; visibility sweep / planner / ray casting)";
+}
+
+int vhp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char *vhp_last_error(const vhp_context *ctx) {
+  return ctx ? ctx->last_error.c_str() : g_last_error.c_str();
+}
+
+int64_t vhp_launch_count(const vhp_context *ctx) { return ctx ? ctx->launches : 0; }
+
+vhp_status vhp_context_create(int device, void *cuda_stream, vhp_context **out) {
+  if (!out) return fail(nullptr, VHP_ERR_INVALID_ARG, "null out pointer");
+  *out = nullptr;
+  const int n = vhp_device_count();
+  if (n == 0) return fail(nullptr, VHP_ERR_NO_DEVICE, "no CUDA device available (no CPU fallback)");
+  if (device < 0 || device >= n) return fail(nullptr, VHP_ERR_INVALID_ARG, "bad device index");
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+  if (prop.major != 10)
+    return fail(nullptr, VHP_ERR_NO_DEVICE,
+                "device is not sm_100 (this library ships sm_100a code only)");
+  vhp_context *ctx = new vhp_context();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  VHP_CUDA(nullptr, cudaSetDevice(device));
+  if (cuda_stream) {
+    ctx->stream = (cudaStream_t)cuda_stream;
+  } else {
+    VHP_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->owns_stream = true;
+  }
+  VHP_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    VHP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+    VHP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+  }
+  VHP_CUDA(nullptr, cudaMalloc(&ctx->d_err, sizeof(int)));
+  VHP_CUDA(nullptr, cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+  const char *impl = std::getenv("VHP_SWEEP_IMPL");
+  ctx->sweep_impl = (impl && std::strcmp(impl, "naive") == 0) ? 1 : 0;
+  *out = ctx;
+  return VHP_OK;
+}
+
+void vhp_context_destroy(vhp_context *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->copy_stream);
+  VhpDevBuf *bufs[] = {&ctx->b_occ, &ctx->b_src, &ctx->b_map, &ctx->b_out[0], &ctx->b_out[1],
+                       &ctx->b_scratch, &ctx->b_planner, &ctx->b_misc};
+  for (VhpDevBuf *b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (ctx->packed_buf) cudaFree(ctx->packed_buf);
+  if (ctx->rcp_table) cudaFree(ctx->rcp_table);
+  if (ctx->d_err) cudaFree(ctx->d_err);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+    if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+  }
+  cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+vhp_status vhp_context_synchronize(vhp_context *ctx) {
+  if (!ctx) return fail(nullptr, VHP_ERR_INVALID_ARG, "null context");
+  return check_device_error(ctx);
+}
+
+vhp_status vhp_prepare_maps_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx,
+                                int ny) {
+  if (!ctx || !d_occ || nmaps < 1 || nx < 1 || ny < 1)
+    return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_prepare_maps_dev: bad argument");
+  VHP_CUDA(ctx, cudaSetDevice(ctx->device));
+  vhp_status st = pack_maps(ctx, d_occ, nmaps, nx, ny, true);
+  if (st == VHP_OK) ctx->packed_sticky = true;
+  return st;
+}
+
+vhp_status vhp_visibility_batch_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx,
+                                    int ny, const int32_t *d_src_xy, const int32_t *d_src_map,
+                                    int64_t npairs, vhp_dtype dtype, void *d_out) {
+  vhp_status st = check_common(ctx, d_occ, nmaps, nx, ny, d_src_xy, npairs, dtype, d_out);
+  if (st != VHP_OK) return st;
+  VHP_CUDA(ctx, cudaSetDevice(ctx->device));
+  return run_dev(ctx, Op::Sweep, d_occ, nmaps, nx, ny, d_src_xy, d_src_map, npairs, dtype, d_out);
+}
+
+vhp_status vhp_visibility_batch(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx, int ny,
+                                const int32_t *src_xy, const int32_t *src_map, int64_t npairs,
+                                vhp_dtype dtype, void *out) {
+  return run_host(ctx, Op::Sweep, occ, nmaps, nx, ny, src_xy, src_map, npairs, dtype, out);
+}
+
+vhp_status vhp_raycast_batch_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx,
+                                 int ny, const int32_t *d_src_xy, const int32_t *d_src_map,
+                                 int64_t npairs, vhp_dtype dtype, void *d_out) {
+  vhp_status st = check_common(ctx, d_occ, nmaps, nx, ny, d_src_xy, npairs, dtype, d_out);
+  if (st != VHP_OK) return st;
+  VHP_CUDA(ctx, cudaSetDevice(ctx->device));
+  return run_dev(ctx, Op::Raycast, d_occ, nmaps, nx, ny, d_src_xy, d_src_map, npairs, dtype,
+                 d_out);
+}
+
+vhp_status vhp_raycast_batch(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx, int ny,
+                             const int32_t *src_xy, const int32_t *src_map, int64_t npairs,
+                             vhp_dtype dtype, void *out) {
+  return run_host(ctx, Op::Raycast, occ, nmaps, nx, ny, src_xy, src_map, npairs, dtype, out);
+}
+
+vhp_status vhp_selftest_ratio(vhp_context *ctx, int kmax, int64_t *mismatches) {
+  if (!ctx || !mismatches || kmax < 1 || kmax > 16384)
+    return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_selftest_ratio: bad argument");
+  VHP_CUDA(ctx, cudaSetDevice(ctx->device));
+  vhp_status st = ensure_rcp(ctx, kmax + 8);
+  if (st != VHP_OK) return st;
+  if ((st = ensure(ctx, ctx->b_misc, 64)) != VHP_OK) return st;
+  VHP_CUDA(ctx, cudaMemsetAsync(ctx->b_misc.p, 0, 8, ctx->stream));
+  VHP_CUDA(ctx, vhp_launch_ratio_selftest(ctx->rcp_table, kmax,
+                                          (unsigned long long *)ctx->b_misc.p, ctx->stream,
+                                          &ctx->launches));
+  unsigned long long bad = 0;
+  VHP_CUDA(ctx, cudaMemcpyAsync(&bad, ctx->b_misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *mismatches = (int64_t)bad;
+  return VHP_OK;
+}
+
+void vhp_export_came_from_u64(const int32_t *came, int64_t n, uint64_t *out) {
+  for (int64_t i = 0; i < n; ++i)
+    out[i] = came[i] < 0 ? VHP_NO_PARENT_U64 : (uint64_t)came[i];
+}
+
+} // extern "C"

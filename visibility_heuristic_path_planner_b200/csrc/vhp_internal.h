@@ -1,0 +1,112 @@
+// vhp_internal.h -- shared declarations between the C-ABI layer and the kernels.
+#ifndef VHP_INTERNAL_H
+#define VHP_INTERNAL_H
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "vhp.h"
+
+// Packed occupancy planes of one batch of maps (built by vhp_pack_maps):
+//   rowbits[m][y][wx]  bit (x & 31) of word x>>5 = occupancy(x, y)   (row-major)
+//   colbits[m][x][wy]  bit (y & 31) of word y>>5 = occupancy(x, y)   (column-major)
+// Row pitch is padded (+1 word, rounded up to 4 words) so that a lookahead read
+// one word past the last data word stays inside the row.
+struct VhpPackedMaps {
+  const uint32_t *rowbits = nullptr;
+  const uint32_t *colbits = nullptr;
+  int wpr = 0;            // words per row of rowbits
+  int wpc = 0;            // words per column of colbits
+  size_t row_plane = 0;   // words per map in rowbits (= ny * wpr)
+  size_t col_plane = 0;   // words per map in colbits (= nx * wpc)
+};
+
+// grow-only device buffer
+struct VhpDevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct vhp_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr; // D2H of the host-buffer entry points
+  bool owns_stream = false;
+  int sm_count = 0;
+  int64_t launches = 0;
+  std::string last_error;
+  // device-side error word (bit 0: a source / start / end outside the grid)
+  int *d_err = nullptr;
+  // workspace buffers (grown on demand, reused across calls)
+  VhpDevBuf b_occ, b_src, b_map, b_out[2], b_scratch, b_planner, b_misc;
+  cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  // cached packed maps for _dev calls (vhp_prepare_maps_dev)
+  const uint8_t *packed_src = nullptr;
+  bool packed_sticky = false; // set by vhp_prepare_maps_dev: reuse planes for this pointer
+  int packed_nmaps = 0, packed_nx = 0, packed_ny = 0;
+  uint32_t *packed_buf = nullptr;
+  size_t packed_bytes = 0;
+  VhpPackedMaps packed;
+  // 1/k table for the sweep kernels (exact __drcp_rn), device resident
+  double *rcp_table = nullptr;
+  int rcp_len = 0;
+  // which K1 implementation vhp_visibility_batch* uses (env VHP_SWEEP_IMPL):
+  // 0 = front kernel (default), 1 = naive reference kernel
+  int sweep_impl = 0;
+};
+
+// ---- kernel launchers (all enqueue on `st`, return cudaGetLastError()) --------
+// Each launcher returns the number of kernel launches it made through *launches.
+
+cudaError_t vhp_launch_pack_maps(const uint8_t *d_occ, int nmaps, int nx, int ny,
+                                 uint32_t *d_rowbits, uint32_t *d_colbits, int wpr,
+                                 int wpc, cudaStream_t st, int64_t *launches);
+
+cudaError_t vhp_launch_rcp_table(double *d_table, int len, cudaStream_t st,
+                                 int64_t *launches);
+
+cudaError_t vhp_launch_ratio_selftest(const double *d_rcp, int kmax,
+                                      unsigned long long *d_mismatches, cudaStream_t st,
+                                      int64_t *launches);
+
+// K1, straightforward L-front kernel (one CTA per (pair, quadrant), fronts in
+// shared/global memory).  Correctness anchor for the tuned kernel.
+cudaError_t vhp_launch_sweep_naive(const uint8_t *d_occ, int nx, int ny,
+                                   const int32_t *d_src_xy, const int32_t *d_src_map,
+                                   int64_t npairs, vhp_dtype dtype, void *d_out,
+                                   double *d_scratch, int *d_err, cudaStream_t st,
+                                   int64_t *launches);
+size_t vhp_sweep_naive_scratch_bytes(int nx, int ny, int64_t npairs);
+
+// K1, tuned front kernel (absolute-coordinate ownership, bit-plane occupancy,
+// register-resident fp64 fronts, sector-staged column stores).
+bool vhp_sweep_front_supported(int nx, int ny);
+cudaError_t vhp_launch_sweep_front(const VhpPackedMaps &maps, int nx, int ny,
+                                   const int32_t *d_src_xy, const int32_t *d_src_map,
+                                   int64_t npairs, vhp_dtype dtype, void *d_out,
+                                   const double *d_rcp, int *d_err, cudaStream_t st,
+                                   int64_t *launches);
+
+// K4 ray casting
+cudaError_t vhp_launch_raycast(const uint8_t *d_occ, int nx, int ny,
+                               const int32_t *d_src_xy, const int32_t *d_src_map,
+                               int64_t npairs, vhp_dtype dtype, void *d_out,
+                               int *d_err, cudaStream_t st, int64_t *launches);
+
+// K2/K3/K5 planner
+struct VhpPlannerWork; // opaque, defined in kernels_planner.cu
+size_t vhp_planner_workspace_bytes(int nx, int ny, int64_t nprob, int32_t ls_cap,
+                                   vhp_dtype dtype, const vhp_planner_out *out);
+cudaError_t vhp_launch_planner(const uint8_t *d_occ, int nmaps, int nx, int ny,
+                               const int32_t *d_se_xy, const int32_t *d_prob_map,
+                               int64_t nprob, double threshold, int32_t max_iter,
+                               int32_t ls_cap, vhp_dtype dtype,
+                               const vhp_planner_out *d_out, void *d_ws,
+                               size_t ws_bytes, cudaStream_t st, int64_t *launches);
+
+// helpers
+static inline int vhp_words_padded(int n) { return (((n + 31) >> 5) + 1 + 3) & ~3; }
+
+#endif
