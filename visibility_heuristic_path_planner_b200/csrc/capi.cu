@@ -51,7 +51,7 @@ vhp_status ensure_rcp(vhp_context *ctx, int len) {
     VHP_CUDA(ctx, cudaFree(ctx->rcp_table));
     ctx->rcp_table = nullptr;
   }
-  VHP_CUDA(ctx, cudaMalloc(&ctx->rcp_table, (size_t)len * sizeof(double)));
+  VHP_CUDA(ctx, cudaMalloc(&ctx->rcp_table, (size_t)len * 2 * sizeof(double)));
   VHP_CUDA(ctx, vhp_launch_rcp_table(ctx->rcp_table, len, ctx->stream, &ctx->launches));
   ctx->rcp_len = len;
   return VHP_OK;
@@ -147,15 +147,21 @@ vhp_status run_dev(vhp_context *ctx, Op op, const uint8_t *d_occ, int nmaps, int
   const size_t esz = dtype == VHP_F32 ? 4 : 8;
   const bool aligned = ((uintptr_t)d_out % 16) == 0 && ((size_t)nx * ny * esz) % 16 == 0;
   const int n_max = std::max(nx, ny);
-  const bool front_fits = vhp_sweep_front_supported(nx, ny) && n_max <= 128 * 26;
-  if (ctx->sweep_impl == 0 && front_fits && aligned) {
+  const bool front_fits = vhp_sweep_front_supported(nx, ny);
+  const bool ring_fits = vhp_sweep_ring_supported(nx, ny);
+  if (ctx->sweep_impl != 1 && (front_fits || ring_fits) && aligned) {
     vhp_status st = ensure_rcp(ctx, n_max + 8);
     if (st != VHP_OK) return st;
     st = pack_maps(ctx, d_occ, nmaps, nx, ny, false);
     if (st != VHP_OK) return st;
-    VHP_CUDA(ctx, vhp_launch_sweep_front(ctx->packed, nx, ny, d_xy, d_map, n, dtype, d_out,
-                                         ctx->rcp_table, ctx->d_err, ctx->stream,
-                                         &ctx->launches));
+    if (ring_fits && (ctx->sweep_impl == 3 || (ctx->sweep_impl == 0 && !front_fits)))
+      VHP_CUDA(ctx, vhp_launch_sweep_ring(ctx->packed, nx, ny, d_xy, d_map, n, dtype, d_out,
+                                          ctx->rcp_table, ctx->d_err, ctx->stream,
+                                          &ctx->launches));
+    else
+      VHP_CUDA(ctx, vhp_launch_sweep_front(ctx->packed, nx, ny, d_xy, d_map, n, dtype, d_out,
+                                           ctx->rcp_table, ctx->d_err, ctx->stream,
+                                           &ctx->launches));
     return VHP_OK;
   }
   // reference kernel: chunk so that the scratch fronts stay small
@@ -197,7 +203,7 @@ vhp_status run_host(vhp_context *ctx, Op op, const uint8_t *occ, int nmaps, int 
                                   cudaMemcpyHostToDevice, ctx->stream));
   ctx->packed_src = nullptr; // b_occ content changed
   ctx->packed_sticky = false;
-  if (op == Op::Sweep && ctx->sweep_impl == 0) { // pack once for all chunks
+  if (op == Op::Sweep && ctx->sweep_impl != 1) { // pack once for all chunks
     if ((st = pack_maps(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, true)) != VHP_OK)
       return st;
     ctx->packed_sticky = true;
@@ -301,7 +307,10 @@ vhp_status vhp_context_create(int device, void *cuda_stream, vhp_context **out) 
   VHP_CUDA(nullptr, cudaMalloc(&ctx->d_err, sizeof(int)));
   VHP_CUDA(nullptr, cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
   const char *impl = std::getenv("VHP_SWEEP_IMPL");
-  ctx->sweep_impl = (impl && std::strcmp(impl, "naive") == 0) ? 1 : 0;
+  ctx->sweep_impl = 0;
+  if (impl && std::strcmp(impl, "naive") == 0) ctx->sweep_impl = 1;
+  if (impl && std::strcmp(impl, "front") == 0) ctx->sweep_impl = 2;
+  if (impl && std::strcmp(impl, "ring") == 0) ctx->sweep_impl = 3;
   *out = ctx;
   return VHP_OK;
 }

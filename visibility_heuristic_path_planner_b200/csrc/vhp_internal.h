@@ -53,7 +53,8 @@ struct vhp_context {
   double *rcp_table = nullptr;
   int rcp_len = 0;
   // which K1 implementation vhp_visibility_batch* uses (env VHP_SWEEP_IMPL):
-  // 0 = front kernel (default), 1 = naive reference kernel
+  // 0 = auto (front kernel where it fits), 1 = naive reference kernel, 2 = front
+  // kernel (every thread serves all four fronts), 3 = ring kernel (one front per warp)
   int sweep_impl = 0;
 };
 
@@ -88,6 +89,14 @@ cudaError_t vhp_launch_sweep_front(const VhpPackedMaps &maps, int nx, int ny,
                                    int64_t npairs, vhp_dtype dtype, void *d_out,
                                    const double *d_rcp, int *d_err, cudaStream_t st,
                                    int64_t *launches);
+
+// K1, front-specialised warps (grids up to 1024 x 1024): the default sweep kernel.
+bool vhp_sweep_ring_supported(int nx, int ny);
+cudaError_t vhp_launch_sweep_ring(const VhpPackedMaps &maps, int nx, int ny,
+                                  const int32_t *d_src_xy, const int32_t *d_src_map,
+                                  int64_t npairs, vhp_dtype dtype, void *d_out,
+                                  const double *d_rcp, int *d_err, cudaStream_t st,
+                                  int64_t *launches);
 
 // K4 ray casting
 cudaError_t vhp_launch_raycast(const uint8_t *d_occ, int nx, int ny,
