@@ -252,6 +252,58 @@ vhp_status run_host(vhp_context *ctx, Op op, const uint8_t *occ, int nmaps, int 
   return check_device_error(ctx);
 }
 
+// ---- planner ------------------------------------------------------------------
+// device pointers in `o` (any may be null).  Fields the caller did not ask for in
+// fp64 live in the context workspace, so large batches run in chunks.
+vhp_status planner_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx, int ny,
+                       const int32_t *d_se, const int32_t *d_pmap, int64_t nprob, double thr,
+                       int32_t max_iter, int32_t ls_cap, vhp_dtype dtype, const vhp_planner_out &o) {
+  if (nprob == 0) return VHP_OK;
+  if (!vhp_planner_supported(nx, ny))
+    return fail(ctx, VHP_ERR_UNSUPPORTED, "planner: grid too large for the single-CTA kernel");
+  if (ls_cap < max_iter + 2 || max_iter < 0)
+    return fail(ctx, VHP_ERR_INVALID_ARG, "planner: ls_cap must be >= max_iter + 2");
+  vhp_status st = ensure_rcp(ctx, std::max(nx, ny) + 8);
+  if (st != VHP_OK) return st;
+  if ((st = pack_maps(ctx, d_occ, nmaps, nx, ny, false)) != VHP_OK) return st;
+  const size_t cells = (size_t)nx * ny;
+  const bool vis_user = dtype == VHP_F64 && o.vis, vg_user = dtype == VHP_F64 && o.vg;
+  const size_t per_prob = (vis_user ? 0 : 8 * cells) + (vg_user ? 0 : 8 * cells) +
+                          (o.came ? 0 : 4 * cells);
+  const size_t small_pp = 4 + 4 + 8 + 4 + 2 * (size_t)ls_cap * 8 + 32;
+  int64_t chunk = nprob;
+  const size_t ws_limit = (size_t)8 << 30;
+  if (per_prob) chunk = std::max<int64_t>(1, std::min<int64_t>(nprob, (int64_t)(ws_limit / per_prob)));
+  const size_t field_bytes = (size_t)chunk * per_prob;
+  const size_t small_bytes = (size_t)nprob * small_pp;
+  if ((st = ensure(ctx, ctx->b_planner, field_bytes + small_bytes + 256)) != VHP_OK) return st;
+  char *w = (char *)ctx->b_planner.p;
+  auto take = [&](size_t bytes) { char *r = w; w += (bytes + 15) & ~(size_t)15; return r; };
+  double *ws_vis = vis_user ? nullptr : (double *)take(8 * cells * chunk);
+  double *ws_vg = vg_user ? nullptr : (double *)take(8 * cells * chunk);
+  int32_t *ws_came = o.came ? nullptr : (int32_t *)take(4 * cells * chunk);
+  int32_t *status = o.status ? o.status : (int32_t *)take(4 * nprob);
+  int32_t *nb = o.nb_sources ? o.nb_sources : (int32_t *)take(4 * nprob);
+  int32_t *ls = o.light_sources ? o.light_sources : (int32_t *)take(8 * (size_t)ls_cap * nprob);
+  double *plen = o.path_len ? o.path_len : (double *)take(8 * nprob);
+  int32_t *pn = o.path_n ? o.path_n : (int32_t *)take(4 * nprob);
+  int32_t *path = o.path ? o.path : (int32_t *)take(8 * (size_t)ls_cap * nprob);
+  for (int64_t q0 = 0; q0 < nprob; q0 += chunk) {
+    const int64_t n = std::min(chunk, nprob - q0);
+    double *vis = vis_user ? (double *)o.vis + q0 * cells : ws_vis;
+    double *vg = vg_user ? (double *)o.vg + q0 * cells : ws_vg;
+    int32_t *came = o.came ? o.came + q0 * cells : ws_came;
+    float *vg32 = (dtype == VHP_F32 && o.vg) ? (float *)o.vg + q0 * cells : nullptr;
+    float *vis32 = (dtype == VHP_F32 && o.vis) ? (float *)o.vis + q0 * cells : nullptr;
+    VHP_CUDA(ctx, vhp_launch_planner(ctx->packed, nx, ny, d_se + 4 * q0, d_pmap ? d_pmap + q0 : nullptr,
+                                     n, thr, max_iter, ls_cap, ctx->rcp_table, vis, vg, came,
+                                     status + q0, nb + q0, ls + 2 * (size_t)ls_cap * q0, plen + q0,
+                                     pn + q0, path + 2 * (size_t)ls_cap * q0, vg32, vis32,
+                                     ctx->d_err, ctx->stream, &ctx->launches));
+  }
+  return VHP_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -398,6 +450,92 @@ vhp_status vhp_selftest_ratio(vhp_context *ctx, int kmax, int64_t *mismatches) {
   VHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   *mismatches = (int64_t)bad;
   return VHP_OK;
+}
+
+vhp_status vhp_planner_batch_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx,
+                                 int ny, const int32_t *d_se_xy, const int32_t *d_prob_map,
+                                 int64_t nprob, double threshold, int32_t max_iter,
+                                 int32_t ls_cap, vhp_dtype dtype, const vhp_planner_out *d_out) {
+  static const vhp_planner_out none = {};
+  vhp_status st = check_common(ctx, d_occ, nmaps, nx, ny, d_se_xy, nprob, dtype, ctx);
+  if (st != VHP_OK) return st;
+  VHP_CUDA(ctx, cudaSetDevice(ctx->device));
+  return planner_dev(ctx, d_occ, nmaps, nx, ny, d_se_xy, d_prob_map, nprob, threshold, max_iter,
+                     ls_cap, dtype, d_out ? *d_out : none);
+}
+
+vhp_status vhp_planner_batch(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx, int ny,
+                             const int32_t *se_xy, const int32_t *prob_map, int64_t nprob,
+                             double threshold, int32_t max_iter, int32_t ls_cap, vhp_dtype dtype,
+                             const vhp_planner_out *out) {
+  static const vhp_planner_out none = {};
+  const vhp_planner_out &h = out ? *out : none;
+  vhp_status st = check_common(ctx, occ, nmaps, nx, ny, se_xy, nprob, dtype, ctx);
+  if (st != VHP_OK) return st;
+  if (prob_map)
+    if ((st = check_points(ctx, nullptr, 0, prob_map, nprob, nmaps, nx, ny, "vhp_planner_batch")) != VHP_OK)
+      return st;
+  if (nprob == 0) return VHP_OK;
+  VHP_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t cells = (size_t)nx * ny, esz = dtype == VHP_F32 ? 4 : 8;
+  if ((st = ensure(ctx, ctx->b_occ, (size_t)nmaps * cells)) != VHP_OK) return st;
+  if ((st = ensure(ctx, ctx->b_src, (size_t)nprob * 16)) != VHP_OK) return st;
+  if (prob_map && (st = ensure(ctx, ctx->b_map, (size_t)nprob * 4)) != VHP_OK) return st;
+  VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_occ.p, occ, (size_t)nmaps * cells, cudaMemcpyHostToDevice, ctx->stream));
+  VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_src.p, se_xy, (size_t)nprob * 16, cudaMemcpyHostToDevice, ctx->stream));
+  if (prob_map)
+    VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_map.p, prob_map, (size_t)nprob * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->packed_src = nullptr;
+  ctx->packed_sticky = false;
+  if ((st = pack_maps(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, true)) != VHP_OK) return st;
+  ctx->packed_sticky = true;
+  // device staging for the requested outputs, a chunk of problems at a time
+  const size_t per_prob = (h.vis ? esz * cells : 0) + (h.vg ? esz * cells : 0) + (h.came ? 4 * cells : 0) +
+                          4 + 4 + 8 + 4 + 2 * (size_t)ls_cap * 8 + 64;
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(nprob, (int64_t)(((size_t)2 << 30) / per_prob)));
+  vhp_status result = VHP_OK;
+  if ((st = ensure(ctx, ctx->b_out[0], (size_t)chunk * per_prob + 256)) != VHP_OK) result = st;
+  for (int64_t q0 = 0; q0 < nprob && result == VHP_OK; q0 += chunk) {
+    const int64_t n = std::min(chunk, nprob - q0);
+    char *w = (char *)ctx->b_out[0].p;
+    auto take = [&](size_t bytes) { char *r = w; w += (bytes + 15) & ~(size_t)15; return r; };
+    vhp_planner_out d = {};
+    d.vis = h.vis ? take(esz * cells * n) : nullptr;
+    d.vg = h.vg ? take(esz * cells * n) : nullptr;
+    d.came = h.came ? (int32_t *)take(4 * cells * n) : nullptr;
+    d.status = (int32_t *)take(4 * n);
+    d.nb_sources = (int32_t *)take(4 * n);
+    d.light_sources = (int32_t *)take(8 * (size_t)ls_cap * n);
+    d.path_len = (double *)take(8 * n);
+    d.path_n = (int32_t *)take(4 * n);
+    d.path = (int32_t *)take(8 * (size_t)ls_cap * n);
+    result = planner_dev(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny,
+                         (const int32_t *)ctx->b_src.p + 4 * q0,
+                         prob_map ? (const int32_t *)ctx->b_map.p + q0 : nullptr, n, threshold,
+                         max_iter, ls_cap, dtype, d);
+    if (result != VHP_OK) break;
+    auto back = [&](void *dst, const void *src, size_t bytes) {
+      if (dst && result == VHP_OK) {
+        cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) result = cuda_fail(ctx, e, "planner D2H");
+      }
+    };
+    back(h.vis ? (char *)h.vis + q0 * cells * esz : nullptr, d.vis, esz * cells * n);
+    back(h.vg ? (char *)h.vg + q0 * cells * esz : nullptr, d.vg, esz * cells * n);
+    back(h.came ? h.came + q0 * cells : nullptr, d.came, 4 * cells * n);
+    back(h.status ? h.status + q0 : nullptr, d.status, 4 * n);
+    back(h.nb_sources ? h.nb_sources + q0 : nullptr, d.nb_sources, 4 * n);
+    back(h.light_sources ? h.light_sources + 2 * (size_t)ls_cap * q0 : nullptr, d.light_sources, 8 * (size_t)ls_cap * n);
+    back(h.path_len ? h.path_len + q0 : nullptr, d.path_len, 8 * n);
+    back(h.path_n ? h.path_n + q0 : nullptr, d.path_n, 4 * n);
+    back(h.path ? h.path + 2 * (size_t)ls_cap * q0 : nullptr, d.path, 8 * (size_t)ls_cap * n);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess && result == VHP_OK) result = cuda_fail(ctx, e, "planner sync");
+  }
+  ctx->packed_sticky = false;
+  ctx->packed_src = nullptr;
+  if (result != VHP_OK) return result;
+  return check_device_error(ctx);
 }
 
 void vhp_export_came_from_u64(const int32_t *came, int64_t n, uint64_t *out) {

@@ -104,16 +104,17 @@ cudaError_t vhp_launch_raycast(const uint8_t *d_occ, int nx, int ny,
                                int64_t npairs, vhp_dtype dtype, void *d_out,
                                int *d_err, cudaStream_t st, int64_t *launches);
 
-// K2/K3/K5 planner
-struct VhpPlannerWork; // opaque, defined in kernels_planner.cu
-size_t vhp_planner_workspace_bytes(int nx, int ny, int64_t nprob, int32_t ls_cap,
-                                   vhp_dtype dtype, const vhp_planner_out *out);
-cudaError_t vhp_launch_planner(const uint8_t *d_occ, int nmaps, int nx, int ny,
-                               const int32_t *d_se_xy, const int32_t *d_prob_map,
-                               int64_t nprob, double threshold, int32_t max_iter,
-                               int32_t ls_cap, vhp_dtype dtype,
-                               const vhp_planner_out *d_out, void *d_ws,
-                               size_t ws_bytes, cudaStream_t st, int64_t *launches);
+// K2/K3/K5 planner: one persistent CTA per problem (sweep + fused epilogue +
+// arg-min + next-source selection + path reconstruction, no host round trip).
+// Working fields are fp64; vg32/vis32 are optional fp32 exports.
+bool vhp_planner_supported(int nx, int ny);
+cudaError_t vhp_launch_planner(const VhpPackedMaps &maps, int nx, int ny, const int32_t *d_se_xy,
+                               const int32_t *d_prob_map, int64_t nprob, double threshold,
+                               int32_t max_iter, int32_t ls_cap, const double *d_rcp,
+                               double *d_vis, double *d_vg, int32_t *d_came, int32_t *d_status,
+                               int32_t *d_nb, int32_t *d_ls, double *d_path_len, int32_t *d_path_n,
+                               int32_t *d_path, float *d_vg32, float *d_vis32, int *d_err,
+                               cudaStream_t st, int64_t *launches);
 
 // helpers
 static inline int vhp_words_padded(int n) { return (((n + 31) >> 5) + 1 + 3) & ~3; }
