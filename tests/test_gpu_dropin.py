@@ -1,0 +1,148 @@
+"""Drop-in surface on the GPU: the solver handle / CLI write the same ./output/*.txt
+as the reference executable (oracle/_ref/ref_cli_strict, prebuilt where the
+reference checkout exists) and print the same result lines."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+pytestmark = pytest.mark.gpu
+CLI = os.path.join(ROOT, "visibility_heuristic_path_planner_b200", "bin", "visibility_heuristic_planner")
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "ref_cli_strict")
+
+CONFIG = """mode={mode}
+ncols={n}
+nrows={n}
+nb_of_obstacles=10
+minWidth=10
+maxWidth=20
+minHeight=10
+maxHeight=20
+randomSeed=0
+seedValue={seed}
+imagePath={image}
+start={{{sx},{sy}}}
+end={{{ex},{ey}}}
+max_iter=250
+visibilityThreshold={thr}
+lightStrength=1
+timer=1
+saveResults=1
+saveCameFrom=1
+saveLightSources=1
+saveGlobalVisibility=1
+saveLocalVisibility=1
+saveVisibilityField=1
+silent=0
+ballRadius=5
+"""
+
+
+def run(exe, workdir, cfg):
+    os.makedirs(os.path.join(workdir, "config"), exist_ok=True)
+    with open(os.path.join(workdir, "config", "settings.config"), "w") as f:
+        f.write(cfg)
+    p = subprocess.run([exe], cwd=workdir, capture_output=True, text=True, timeout=600)
+    return p.returncode, p.stdout
+
+
+FILES = ["cameFrom.txt", "lightSources.txt", "VisibilityMap.txt", "LocalVisibilityMap.txt", "visibilityField.txt"]
+
+
+@pytest.mark.parametrize("seed,thr", [(2, 0.25), (3, 0.25), (5, 0.5)])
+def test_cli_outputs_match_reference_executable(tmp_path, seed, thr):
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref/ref_cli_strict not prebuilt")
+    cfg = CONFIG.format(mode=1, n=101, seed=seed, image="none", sx=5, sy=5, ex=95, ey=95, thr=thr)
+    a, b = str(tmp_path / "ours"), str(tmp_path / "ref")
+    rc_a, out_a = run(CLI, a, cfg)
+    rc_b, out_b = run(REF_CLI, b, cfg)
+    assert rc_a == 0 and rc_b == 0, (out_a[-500:], out_b[-500:])
+    for f in FILES:
+        assert open(os.path.join(a, "output", f), "rb").read() == open(os.path.join(b, "output", f), "rb").read(), f
+    for pat in (r"Path length: (\S+)", r"Density of the occupancy grid: (\S+)"):
+        assert re.search(pat, out_a).group(1) == re.search(pat, out_b).group(1)
+    assert "Visibility computation time in us:" in out_a and "Raycasting computation time in us:" in out_a
+
+
+def test_cli_error_messages(tmp_path):
+    cfg = CONFIG.format(mode=1, n=101, seed=1, image="none", sx=5, sy=5, ex=95, ey=95, thr=0.25)
+    rc, out = run(CLI, str(tmp_path / "occ"), cfg)
+    assert rc == 0 and "End point is not valid (occupied)" in out   # seed 1 (golden)
+    cfg = CONFIG.format(mode=1, n=101, seed=2, image="none", sx=500, sy=5, ex=95, ey=95, thr=0.25)
+    rc, out = run(CLI, str(tmp_path / "oob"), cfg)
+    assert "Start point is out of bounds." in out
+
+
+def test_cli_image_mode_maze5(tmp_path):
+    """BASELINE config 3 through the CLI: mode 2, bottom-left start/end, thr 0.2."""
+    from PIL import Image
+    g = load_golden("maze5.npz")
+    ny, nx = map(int, g["shape"])
+    occ = np.unpackbits(g["occ_bits"])[: ny * nx].reshape(ny, nx)
+    img = np.zeros((ny, nx, 4), dtype=np.uint8)
+    img[..., 0] = np.where(occ, 255, 0); img[..., 3] = 255
+    png = str(tmp_path / "maze_5.png")
+    Image.fromarray(img, "RGBA").save(png)
+    cfg = CONFIG.format(mode=2, n=100, seed=1, image=png, sx=118, sy=317, ex=123, ey=10, thr=0.2)
+    work = str(tmp_path / "maze")
+    rc, out = run(CLI, work, cfg)
+    assert rc == 0, out[-800:]
+    assert "Loaded image of dimensions 242x322 successfully" in out
+    assert "Path length: 1341.71" in out
+    ls = np.loadtxt(os.path.join(work, "output", "lightSources.txt"), dtype=int)
+    assert len(ls) == 112 and tuple(ls[0]) == (118, 317)          # written back in the config frame
+    ref_ls = g["thr020_ls"][:112].copy(); ref_ls[:, 1] = ny - 1 - ref_ls[:, 1]
+    assert np.array_equal(ls, ref_ls)
+    came = np.loadtxt(os.path.join(work, "output", "cameFrom.txt"), dtype=np.uint64)
+    assert came.shape == (ny, nx) and came.max() == 10**15
+
+
+def test_solver_handle_fields(tmp_path):
+    """vhp_solver_* through ctypes: fields, light sources and path of a solve."""
+    import ctypes as C
+    import visibility_heuristic_path_planner_b200 as vhp
+    from oracle_py import Oracle
+    lib = vhp.load_library()
+    ora = Oracle()
+    occ = ora.generate_environment(101, 101, 10, 10, 20, 10, 20, 4)
+    ref = ora.solve(occ, (5, 5), (95, 95), 0.25, 100)
+    cfg = vhp.Config()
+    lib.vhp_config_default(C.byref(cfg))
+    cfg.ncols = cfg.nrows = 101
+    cfg.start_x, cfg.start_y, cfg.end_x, cfg.end_y = 5, 5, 95, 95
+    cfg.visibility_threshold, cfg.max_iter, cfg.silent, cfg.save_results = 0.25, 100, 1, 0
+    for k in ("save_came_from", "save_light_sources", "save_global_visibility", "save_local_visibility",
+              "save_visibility_field"):
+        setattr(cfg, k, 0)
+    ctx = vhp.Context(0)
+    h = C.c_void_p()
+    occ8 = np.ascontiguousarray(occ != 0, dtype=np.uint8)
+    lib.vhp_solver_create.argtypes = [C.c_void_p, C.POINTER(vhp.Config), C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    assert lib.vhp_solver_create(ctx.h, C.byref(cfg), occ8.ctypes.data, 101, 101, C.byref(h)) == 0
+    cwd = os.getcwd(); os.chdir(tmp_path)
+    try:
+        lib.vhp_solver_solve.argtypes = [C.c_void_p]
+        assert lib.vhp_solver_solve(h) == 0
+    finally:
+        os.chdir(cwd)
+    lib.vhp_solver_get_field.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    vg = np.zeros((101, 101)); came = np.zeros((101, 101), np.int32)
+    lib.vhp_solver_get_field(h, 1, vg.ctypes.data); lib.vhp_solver_get_field(h, 2, came.ctypes.data)
+    assert np.array_equal(vg, ref["vg"])
+    u = came.astype(np.int64); u[u < 0] = 10**15
+    assert np.array_equal(u.astype(np.uint64), ref["came"])
+    lib.vhp_solver_nb_of_sources.argtypes = [C.c_void_p]; lib.vhp_solver_nb_of_sources.restype = C.c_int64
+    assert lib.vhp_solver_nb_of_sources(h) == ref["nb_of_sources"]
+    lib.vhp_solver_path.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_double)]
+    lib.vhp_solver_path.restype = C.c_int64
+    xy = np.zeros((64, 2), np.int32); ln = C.c_double(0)
+    n = lib.vhp_solver_path(h, xy.ctypes.data, 64, C.byref(ln))
+    assert np.array_equal(xy[:n], ref["path"]) and ln.value == ref["path_length"]
+    lib.vhp_solver_destroy.argtypes = [C.c_void_p]
+    lib.vhp_solver_destroy(h)
+    ctx.close()
