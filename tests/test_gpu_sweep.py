@@ -22,7 +22,7 @@ def vhp():
     return m
 
 
-@pytest.fixture(scope="module", params=["auto", "ring", "naive"])
+@pytest.fixture(scope="module", params=["auto", "octant", "ring", "naive"])
 def ctx(request, vhp):
     os.environ["VHP_SWEEP_IMPL"] = request.param
     c = vhp.Context(0)

@@ -57,6 +57,49 @@ vhp_status ensure_rcp(vhp_context *ctx, int len) {
   return VHP_OK;
 }
 
+vhp_status ensure_rcp2(vhp_context *ctx, int len) {
+  if (len <= ctx->rcp2_len) return VHP_OK;
+  len = std::max(len, 4096 + 8);
+  if (ctx->rcp2_table) {
+    VHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    VHP_CUDA(ctx, cudaFree(ctx->rcp2_table));
+    ctx->rcp2_table = nullptr;
+  }
+  VHP_CUDA(ctx, cudaMalloc(&ctx->rcp2_table, (size_t)len * 2 * sizeof(double)));
+  VHP_CUDA(ctx, vhp_launch_rcp2_table(ctx->rcp2_table, len, ctx->stream, &ctx->launches));
+  ctx->rcp2_len = len;
+  return VHP_OK;
+}
+
+// bit planes of the octant kernel, cached like pack_maps (same sticky flag)
+vhp_status pack_oct(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx, int ny,
+                    bool force) {
+  if (!force && ctx->packed_sticky && ctx->oct_src == d_occ && ctx->oct_nmaps == nmaps &&
+      ctx->oct_nx == nx && ctx->oct_ny == ny)
+    return VHP_OK;
+  const int wp = vhp_oct_words_per_line(nx, ny);
+  const size_t row_plane = (size_t)ny * wp, col_plane = (size_t)nx * wp;
+  const size_t bytes = (size_t)nmaps * 2 * (row_plane + col_plane) * sizeof(uint32_t);
+  if (bytes > ctx->oct_bytes) {
+    if (ctx->oct_buf) {
+      VHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      VHP_CUDA(ctx, cudaFree(ctx->oct_buf));
+      ctx->oct_buf = nullptr;
+    }
+    VHP_CUDA(ctx, cudaMalloc(&ctx->oct_buf, bytes));
+    ctx->oct_bytes = bytes;
+  }
+  uint32_t *row_f = ctx->oct_buf, *row_r = row_f + (size_t)nmaps * row_plane;
+  uint32_t *col_f = row_r + (size_t)nmaps * row_plane, *col_r = col_f + (size_t)nmaps * col_plane;
+  VHP_CUDA(ctx, vhp_launch_pack_oct(d_occ, nmaps, nx, ny, row_f, row_r, col_f, col_r, ctx->stream,
+                                    &ctx->launches));
+  ctx->oct.row_f = row_f; ctx->oct.row_r = row_r;
+  ctx->oct.col_f = col_f; ctx->oct.col_r = col_r;
+  ctx->oct.row_plane = row_plane; ctx->oct.col_plane = col_plane;
+  ctx->oct_src = d_occ; ctx->oct_nmaps = nmaps; ctx->oct_nx = nx; ctx->oct_ny = ny;
+  return VHP_OK;
+}
+
 // (re)build the bit planes for d_occ unless they are cached for this pointer
 vhp_status pack_maps(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx, int ny,
                      bool force) {
@@ -149,6 +192,16 @@ vhp_status run_dev(vhp_context *ctx, Op op, const uint8_t *d_occ, int nmaps, int
   const int n_max = std::max(nx, ny);
   const bool front_fits = vhp_sweep_front_supported(nx, ny);
   const bool ring_fits = vhp_sweep_ring_supported(nx, ny);
+  const bool oct_fits = vhp_sweep_octant_supported(nx, ny);
+  if (ctx->sweep_impl == 4 && oct_fits && aligned) {
+    vhp_status st = ensure_rcp2(ctx, n_max + 8);
+    if (st != VHP_OK) return st;
+    if ((st = pack_oct(ctx, d_occ, nmaps, nx, ny, false)) != VHP_OK) return st;
+    VHP_CUDA(ctx, vhp_launch_sweep_octant(ctx->oct, d_occ, nx, ny, d_xy, d_map, n, dtype, d_out,
+                                          ctx->rcp2_table, ctx->d_err, ctx->stream,
+                                          &ctx->launches));
+    return VHP_OK;
+  }
   if (ctx->sweep_impl != 1 && (front_fits || ring_fits) && aligned) {
     vhp_status st = ensure_rcp(ctx, n_max + 8);
     if (st != VHP_OK) return st;
@@ -203,9 +256,15 @@ vhp_status run_host(vhp_context *ctx, Op op, const uint8_t *occ, int nmaps, int 
                                   cudaMemcpyHostToDevice, ctx->stream));
   ctx->packed_src = nullptr; // b_occ content changed
   ctx->packed_sticky = false;
+  ctx->oct_src = nullptr;
   if (op == Op::Sweep && ctx->sweep_impl != 1) { // pack once for all chunks
-    if ((st = pack_maps(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, true)) != VHP_OK)
-      return st;
+    const bool use_oct = ctx->sweep_impl == 4 &&
+                         vhp_sweep_octant_supported(nx, ny);
+    if (use_oct)
+      st = pack_oct(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, true);
+    else
+      st = pack_maps(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, true);
+    if (st != VHP_OK) return st;
     ctx->packed_sticky = true;
   }
   const size_t chunk_bytes_target = (size_t)1 << 30;
@@ -246,6 +305,7 @@ vhp_status run_host(vhp_context *ctx, Op op, const uint8_t *occ, int nmaps, int 
   if (registered) cudaHostUnregister(out);
   ctx->packed_sticky = false;
   ctx->packed_src = nullptr;
+  ctx->oct_src = nullptr;
   if (result != VHP_OK) return result;
   if (e1 != cudaSuccess) return cuda_fail(ctx, e1, "sync copy stream");
   if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "sync stream");
@@ -363,6 +423,7 @@ vhp_status vhp_context_create(int device, void *cuda_stream, vhp_context **out) 
   if (impl && std::strcmp(impl, "naive") == 0) ctx->sweep_impl = 1;
   if (impl && std::strcmp(impl, "front") == 0) ctx->sweep_impl = 2;
   if (impl && std::strcmp(impl, "ring") == 0) ctx->sweep_impl = 3;
+  if (impl && std::strcmp(impl, "octant") == 0) ctx->sweep_impl = 4;
   *out = ctx;
   return VHP_OK;
 }
@@ -377,7 +438,9 @@ void vhp_context_destroy(vhp_context *ctx) {
   for (VhpDevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->packed_buf) cudaFree(ctx->packed_buf);
+  if (ctx->oct_buf) cudaFree(ctx->oct_buf);
   if (ctx->rcp_table) cudaFree(ctx->rcp_table);
+  if (ctx->rcp2_table) cudaFree(ctx->rcp2_table);
   if (ctx->d_err) cudaFree(ctx->d_err);
   for (int i = 0; i < 2; ++i) {
     if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
@@ -399,6 +462,8 @@ vhp_status vhp_prepare_maps_dev(vhp_context *ctx, const uint8_t *d_occ, int nmap
     return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_prepare_maps_dev: bad argument");
   VHP_CUDA(ctx, cudaSetDevice(ctx->device));
   vhp_status st = pack_maps(ctx, d_occ, nmaps, nx, ny, true);
+  if (st == VHP_OK && vhp_sweep_octant_supported(nx, ny))
+    st = pack_oct(ctx, d_occ, nmaps, nx, ny, true);
   if (st == VHP_OK) ctx->packed_sticky = true;
   return st;
 }
@@ -445,6 +510,10 @@ vhp_status vhp_selftest_ratio(vhp_context *ctx, int kmax, int64_t *mismatches) {
   VHP_CUDA(ctx, vhp_launch_ratio_selftest(ctx->rcp_table, kmax,
                                           (unsigned long long *)ctx->b_misc.p, ctx->stream,
                                           &ctx->launches));
+  if ((st = ensure_rcp2(ctx, kmax + 8)) != VHP_OK) return st;
+  VHP_CUDA(ctx, vhp_launch_ratio2_selftest(ctx->rcp2_table, kmax,
+                                           (unsigned long long *)ctx->b_misc.p, ctx->stream,
+                                           &ctx->launches));
   unsigned long long bad = 0;
   VHP_CUDA(ctx, cudaMemcpyAsync(&bad, ctx->b_misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
   VHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

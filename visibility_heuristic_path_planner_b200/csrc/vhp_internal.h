@@ -23,6 +23,14 @@ struct VhpPackedMaps {
   size_t col_plane = 0;   // words per map in colbits (= nx * wpc)
 };
 
+// Bit planes of the octant sweep kernel (built by vhp_launch_pack_oct): forward and
+// mirrored, row and column major, 4*NS words per line, never-written border baked
+// in as occupied (see kernels_sweep_octant.cu).
+struct VhpOctPlanes {
+  const uint32_t *row_f = nullptr, *row_r = nullptr, *col_f = nullptr, *col_r = nullptr;
+  size_t row_plane = 0, col_plane = 0; // words per map
+};
+
 // grow-only device buffer
 struct VhpDevBuf {
   void *p = nullptr;
@@ -52,9 +60,19 @@ struct vhp_context {
   // 1/k table for the sweep kernels (exact __drcp_rn), device resident
   double *rcp_table = nullptr;
   int rcp_len = 0;
+  // double-double 1/k table {rh, rl} of the octant kernel
+  double *rcp2_table = nullptr;
+  int rcp2_len = 0;
+  // octant-kernel bit planes (cached like `packed`)
+  const uint8_t *oct_src = nullptr;
+  int oct_nmaps = 0, oct_nx = 0, oct_ny = 0;
+  uint32_t *oct_buf = nullptr;
+  size_t oct_bytes = 0;
+  VhpOctPlanes oct;
   // which K1 implementation vhp_visibility_batch* uses (env VHP_SWEEP_IMPL):
-  // 0 = auto (front kernel where it fits), 1 = naive reference kernel, 2 = front
-  // kernel (every thread serves all four fronts), 3 = ring kernel (one front per warp)
+  // 0 = auto (octant kernel where it fits), 1 = naive reference kernel, 2 = front
+  // kernel (every thread serves all four fronts), 3 = ring kernel (one front per
+  // warp, block barrier per ring), 4 = octant kernel (one octant per warp, no barriers)
   int sweep_impl = 0;
 };
 
@@ -97,6 +115,22 @@ cudaError_t vhp_launch_sweep_ring(const VhpPackedMaps &maps, int nx, int ny,
                                   int64_t npairs, vhp_dtype dtype, void *d_out,
                                   const double *d_rcp, int *d_err, cudaStream_t st,
                                   int64_t *launches);
+
+// K1, one warp per octant, no block barriers (grids up to 1021 x 1021): the default.
+bool vhp_sweep_octant_supported(int nx, int ny);
+int vhp_oct_words_per_line(int nx, int ny);
+cudaError_t vhp_launch_pack_oct(const uint8_t *d_occ, int nmaps, int nx, int ny, uint32_t *row_f,
+                                uint32_t *row_r, uint32_t *col_f, uint32_t *col_r,
+                                cudaStream_t st, int64_t *launches);
+cudaError_t vhp_launch_rcp2_table(double *d_table, int len, cudaStream_t st, int64_t *launches);
+cudaError_t vhp_launch_ratio2_selftest(const double *d_rcp2, int kmax,
+                                       unsigned long long *d_mismatches, cudaStream_t st,
+                                       int64_t *launches);
+cudaError_t vhp_launch_sweep_octant(const VhpOctPlanes &pl, const uint8_t *d_occ, int nx, int ny,
+                                    const int32_t *d_src_xy, const int32_t *d_src_map,
+                                    int64_t npairs, vhp_dtype dtype, void *d_out,
+                                    const double *d_rcp2, int *d_err, cudaStream_t st,
+                                    int64_t *launches);
 
 // K4 ray casting
 cudaError_t vhp_launch_raycast(const uint8_t *d_occ, int nx, int ny,
