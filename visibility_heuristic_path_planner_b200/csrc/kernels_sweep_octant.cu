@@ -42,8 +42,10 @@
 
 namespace {
 
+#ifndef VHP_OCT_MINB
+#define VHP_OCT_MINB (NS >= 8 ? 12 : 16)
+#endif
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kRing = 32;                       // diagonal hand-off slots per quadrant
 constexpr unsigned long long kEmpty = ~0ull;    // a NaN pattern no visibility value has
 
 struct OctArgs {
@@ -73,12 +75,13 @@ __device__ __forceinline__ void st_slot(uint32_t a, unsigned long long v) {
 
 // one ring of one slice for the thread's 4 offsets; `mask` = occupancy & activity
 // bits.  Descending e keeps F[e-1] at its previous-ring value.
+template <int OFF>
 __device__ __forceinline__ void slice_update(double (&F)[4], const double nb, const uint32_t mask,
                                              const double fd0, const double rh, const double rl) {
 #pragma unroll
   for (int e = 3; e >= 0; --e) {
     const double b = e ? F[e > 0 ? e - 1 : 0] : nb;
-    const double fd = __dadd_rn(fd0, (double)e);
+    const double fd = __dadd_rn(fd0, (double)(OFF + e));
     const double c = __fma_rn(fd, rh, __dmul_rn(fd, rl));
     const double v = lerp_rn(F[e], b, c);
     F[e] = ((mask >> e) & 1u) ? v : 0.0;
@@ -145,21 +148,31 @@ struct Oct {
   int phi;        // alignment shift: d = D - phi
   int base;       // plane coordinate of D = 0
   int nsl;        // slices that hold grid cells
-  int n_ac, n_al; // grid size across / along
 };
 
 // ---------------------------------------------------------------------------------
 // One octant, all rings.  ISROW: front runs along x (rows sy +- k); otherwise along y.
+//
+// Register layout: F[j] is the slice j places below the edge slice (the slice that
+// holds the newest offset); when the edge moves into the next slice the array is
+// renamed (F[j+1] = F[j]) so the edge code exists once (j == 0) and the interior
+// slices are one fall-through chain entered at j = me.
 // ---------------------------------------------------------------------------------
+// 4 ones (fp32) / 2 ones (fp64) per 16-byte store
+template <typename OutT> __device__ __forceinline__ void stg16_ones(OutT *p) {
+  if constexpr (sizeof(OutT) == 4) stg16(p, 1.0f, 1.0f, 1.0f, 1.0f);
+  else { stg16(p, 1.0, 1.0); stg16(p + 2, 1.0, 1.0); }
+}
+
 template <typename OutT, int NS, bool VEC, bool ISROW>
 __device__ __forceinline__ void octant_sweep(const OctArgs &p, const Oct &g, const int sx,
-                                             const int sy, const double s0,
-                                             const uint32_t *__restrict__ plane,
-                                             OutT *__restrict__ out, const uint32_t ring,
+                                             const double s0, const uint32_t *__restrict__ plane,
+                                             OutT *__restrict__ out, const uint32_t diag,
                                              const uint32_t stage) {
-  constexpr int S = 32 / (int)sizeof(OutT);      // rings per sector
-  constexpr int WP = 4 * NS;                     // plane words per line
-  constexpr uint32_t kSlotBytes = sizeof(OutT) == 4 ? 512u : 1024u; // one (slice, ring) row of slots
+  constexpr int S = 4;                            // rings parked per flush (columns)
+  constexpr int WP = 4 * NS;                      // plane words per line
+  constexpr uint32_t kSlotBytes = sizeof(OutT) == 4 ? 512u : 1024u; // one ring of one slice
+  constexpr uint32_t kSliceBytes = S * kSlotBytes;
   const int lane = threadIdx.x & 31;
   const int nx = p.nx;
   const int K = g.K, phi = g.phi, Dlim = g.Dlim, dir = g.dir_ac;
@@ -167,9 +180,9 @@ __device__ __forceinline__ void octant_sweep(const OctArgs &p, const Oct &g, con
 
   // occupancy nibble of slice m = bits of plane coordinate base + 128m + 4l .. +3
   const int nbl = (g.base >> 2) + lane;
-  const int src_lane0 = nbl >> 3;
   const int nshift = (nbl & 7) * 4;
-  const double fd_lane = (double)(4 * lane - phi);
+  int src_top = nbl >> 3;                         // + 4*me
+  double fd_top = (double)(4 * lane - phi);       // + 128*me
 
   // store-eligible elements per slice (4 bits each): 0 <= d <= Dlim, and the axis
   // d == 0 belongs to the "+" octant
@@ -181,23 +194,50 @@ __device__ __forceinline__ void octant_sweep(const OctArgs &p, const Oct &g, con
       const int d = 128 * m + 4 * lane + e - phi;
       if (d >= (g.rev ? 1 : 0) && d <= Dlim) sm |= 1u << (4 * m + e);
     }
+  uint32_t smr = sm & 0xFu;                       // nibble j = slice me - j
 
   double F[NS][4];
 #pragma unroll
-  for (int m = 0; m < NS; ++m)
+  for (int j = 0; j < NS; ++j)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) F[m][e] = (m == 0 && lane == 0 && e == phi) ? s0 : 0.0;
+    for (int e = 0; e < 4; ++e) F[j][e] = (j == 0 && lane == 0 && e == phi) ? s0 : 0.0;
 
   // real coordinate along the front of element e = 0 of slice 0
   const int al0 = g.rev ? (128 * NS - 1) - (g.base + 4 * lane) : g.base + 4 * lane;
-  // row octants: pointer to (al0, current row); column octants: row pointer of al0
-  OutT *rp = ISROW ? out + ((ptrdiff_t)(g.s_ac + dir) * nx + al0) : out + (ptrdiff_t)al0 * nx;
+  // rows: (al0, source row); columns: row of al0
+  OutT *const org = ISROW ? out + ((ptrdiff_t)g.s_ac * nx + al0) : out + (ptrdiff_t)al0 * nx;
+  // rows: pointer to (element 0 of the edge slice, current row); columns: row of that element
+  OutT *ptop = ISROW ? org + (ptrdiff_t)dir * nx : org;
   const ptrdiff_t rstep = ISROW ? (ptrdiff_t)dir * nx : 0;
+  const uint32_t slot0 = stage + 16u * (uint32_t)lane;
+  uint32_t slot_lane = slot0;                     // + me * kSliceBytes
 
   const uint32_t *pl = plane + (ptrdiff_t)(g.s_ac + dir) * WP + lane;
   uint32_t wnext = (lane < WP) ? __ldg(pl) : 0u;
   int t = g.s_ac;
-  int blk_lo = 1; // first ring parked in the current sector block (columns)
+  int me_cur = 0;
+  int blk_lo = 1;   // first ring parked in the current block (columns)
+  int avail = 0;    // rows: diagonal entries known to be published
+  // last diagonal entry that is handed over: the row octant reads entries 1..min(Ky-1, Ex)
+  const int jlast = ISROW ? min(K - 1, Dlim) : min(Dlim - 1, K);
+  // "lit" mode: every cell of the front so far is exactly 1.0 (no obstacle met yet), so a
+  // ring whose occupancy bits are all set reproduces 1.0 everywhere: a - c*(a - b) with
+  // a == b == 1 is exactly 1.  The front registers are only materialised when it ends.
+  bool lit = s0 == 1.0;
+  const int sp = g.base + phi; // plane coordinate of the source
+
+#define VHP_SLICE(j)                                                                         \
+  {                                                                                          \
+    const double r_ = rot_up(F[j][3], lane);                                                 \
+    const double nb_ = lane ? r_ : rprev;                                                    \
+    rprev = r_;                                                                              \
+    const uint32_t nib_ = __shfl_sync(kFull, wcur, src_top - 4 * (j)) >> nshift;             \
+    slice_update<-128 * (j)>(F[j], nb_, nib_, fd_top, rh, rl);                               \
+    if (ISROW)                                                                               \
+      row_store<OutT, VEC>(ptop - estep * (128 * (j)), estep, F[j], (smr >> (4 * (j))) & 0xFu); \
+    else                                                                                     \
+      col_park<OutT>(slot - (uint32_t)(j) * kSliceBytes, F[j]);                              \
+  }
 
 #pragma unroll 1
   for (int k = 1; k <= K; ++k) {
@@ -205,229 +245,305 @@ __device__ __forceinline__ void octant_sweep(const OctArgs &p, const Oct &g, con
     const uint32_t wcur = wnext;
     pl += dir * WP;
     if (k < K && lane < WP) wnext = __ldg(pl);
-    const double2 rr = __ldg(p.rtab + k);
-    const double rh = rr.x, rl = rr.y;
 
     // edge slice: rows -> slice of the last interpolated offset d = k-1;
     // columns -> slice of the diagonal cell d = k
     const int dstar = ISROW ? k - 1 + phi : k + phi;
     const bool has_edge = ISROW ? (k - 1 <= Dlim) : (k <= Dlim);
-    const int me = dstar >> 7;
-    const int ni = has_edge ? me : g.nsl;
+    const int me = has_edge ? dstar >> 7 : g.nsl - 1; // top slice of this ring
 
     double dval = 0.0;
     if (ISROW && has_edge && k >= 2) { // diagonal cell of ring k-1 from the column octant
-      const uint32_t a = ring + 8u * (uint32_t)((k - 1) & (kRing - 1));
-      unsigned long long raw = ld_slot(a);
-      while (raw == kEmpty) {
-        __nanosleep(40);
-        raw = ld_slot(a);
+      if (k - 1 > avail) {             // wait in batches: the producer publishes in order
+        const int target = min(k + 6, jlast);
+        const uint32_t a = diag + 8u * (uint32_t)target;
+        unsigned ns = 256;
+        while (ld_slot(a) == kEmpty) {
+          __nanosleep(ns);
+          ns = min(2 * ns, 4096u);
+        }
+        avail = target;
       }
-      __syncwarp();
-      if (lane == 0) st_slot(a, kEmpty);
+      const uint32_t a = diag + 8u * (uint32_t)(k - 1);
+      unsigned long long raw = ld_slot(a);
+      while (raw == kEmpty) raw = ld_slot(a);
       dval = __longlong_as_double((long long)raw);
     }
 
-    double rprev = 0.0;
-    uint32_t slot = stage + (uint32_t)(t & (S - 1)) * kSlotBytes + 16u * (uint32_t)lane;
-    // ---- interior slices -------------------------------------------------------
-#pragma unroll
-    for (int m = 0; m < NS; ++m) {
-      if (m < ni) {
-        const double r = rot_up(F[m][3], lane);
-        const double nb = lane ? r : rprev;
-        rprev = r;
-        const uint32_t nib = __shfl_sync(kFull, wcur, src_lane0 + 4 * m) >> nshift;
-        slice_update(F[m], nb, nib, __dadd_rn(fd_lane, (double)(128 * m)), rh, rl);
-        if (ISROW)
-          row_store<OutT, VEC>(rp + estep * (128 * m), estep, F[m], (sm >> (4 * m)) & 0xFu);
-        else
-          col_park<OutT>(slot + (uint32_t)m * (S * kSlotBytes), F[m]);
-      }
-    }
-    // ---- edge slice ------------------------------------------------------------
-    if (has_edge) {
-#pragma unroll
-      for (int m = 0; m < NS; ++m) {
-        if (m == me) {
-          const double r = rot_up(F[m][3], lane);
-          const double nb = lane ? r : rprev;
-          const uint32_t nib = __shfl_sync(kFull, wcur, src_lane0 + 4 * m) >> nshift;
-          const int r0 = dstar - 128 * m - 4 * lane;
-          if (ISROW) {
-            // offsets d <= k-1 are interpolated; d == k-1 starts from the diagonal cell
-            const uint32_t wedge = r0 >= 3 ? 0xFu : (r0 < 0 ? 0u : (2u << r0) - 1u);
-            if (k >= 2) {
+    bool general = true;
+    if (lit) {
+      // all occupancy bits of the active offsets 0..dmax set?  (lane j holds plane word j)
+      const int dmax = min(ISROW ? k - 1 : k, Dlim);
+      const int lo = max(sp - 32 * lane, 0), hi = min(sp + dmax - 32 * lane, 31);
+      const uint32_t need = lo <= hi ? ((2u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
+      bool ok = (wcur & need) == need;
+      if (ISROW && has_edge && k >= 2) ok = ok && dval == 1.0;
+      if (__all_sync(kFull, ok)) {
+        general = false;
+        const int r0 = dstar - 128 * me - 4 * lane;
+        if (ISROW) {
+          OutT *q = org + (ptrdiff_t)(dir * k) * nx;
+          const uint32_t wedge = !has_edge || r0 >= 3 ? 0xFu : (r0 < 0 ? 0u : (2u << r0) - 1u);
+#pragma unroll 1
+          for (int m = 0; m <= me; ++m, q += estep * 128) {
+            uint32_t msk = (sm >> (4 * m)) & 0xFu;
+            if (m == me) msk &= wedge;
+            if (VEC && msk == 0xFu) {
+              stg16_ones<OutT>(estep > 0 ? q : q - 3);
+            } else if (msk) {
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                if (e == r0) F[m][e] = dval;
+                if ((msk >> e) & 1u) __stcs(q + e * estep, (OutT)1);
             }
-            slice_update(F[m], nb, nib & wedge, __dadd_rn(fd_lane, (double)(128 * m)), rh, rl);
-            row_store<OutT, VEC>(rp + estep * (128 * m), estep, F[m], (sm >> (4 * m)) & wedge);
-          } else {
-            // offsets d <= k-1 are interpolated, d == k is the diagonal cell
-            const uint32_t wedge = r0 >= 4 ? 0xFu : (r0 <= 0 ? 0u : (1u << r0) - 1u);
-            slice_update(F[m], nb, nib & wedge, __dadd_rn(fd_lane, (double)(128 * m)), rh, rl);
-            double pz = 0.0;
-            if ((dstar & 3) == 0) { // the diagonal offset is some lane's e == 0
-              const double pr = rot_up(F[m][3], lane);
-              const double p0 = __shfl_sync(kFull, F[m > 0 ? m - 1 : 0][3], 31);
-              pz = lane ? pr : p0;
+          }
+        } else {
+          uint32_t a = slot0 + (uint32_t)(t & (S - 1)) * kSlotBytes;
+#pragma unroll 1
+          for (int m = 0; m <= me; ++m, a += kSliceBytes) {
+            if constexpr (sizeof(OutT) == 4) {
+              asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(a), "f"(1.0f) : "memory");
+            } else {
+              asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(a), "d"(1.0) : "memory");
+              asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(a + 512u), "d"(1.0) : "memory");
             }
-            if ((unsigned)r0 < 4u) {
-              const double pv = r0 == 0 ? pz : (r0 == 1 ? F[m][0] : (r0 == 2 ? F[m][1] : F[m][2]));
-              const double dk = ((nib >> r0) & 1u) ? pv : 0.0;
+          }
+          if (has_edge && k <= jlast && r0 >= 0 && r0 < 4)
+            asm volatile("st.relaxed.cluster.shared::cluster.u64 [%0], %1;" ::"r"(diag + 8u * (uint32_t)k),
+                         "l"(__double_as_longlong(1.0)) : "memory");
+        }
+      } else {
+        // leave lit mode: build the front as it stands after ring k-1 (offsets 0..dprev are
+        // 1.0, everything else 0) in the renamed layout the general code expects
+        lit = false;
+        const int dsp = ISROW ? k - 2 + phi : k - 1 + phi;             // dstar of ring k-1
+        const bool edge_prev = ISROW ? (k - 2 <= Dlim) : (k - 1 <= Dlim);
+        me_cur = edge_prev ? max(dsp, 0) >> 7 : g.nsl - 1;
+        const int dprev = ISROW ? max(min(k - 2, Dlim), 0) : min(k - 1, Dlim);
+        smr = 0;
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (e == r0) F[m][e] = dk;
-              // hand the diagonal cell to the row octant of this quadrant
-              const uint32_t a = ring + 8u * (uint32_t)(k & (kRing - 1));
-              while (ld_slot(a) != kEmpty) __nanosleep(40);
-              st_slot(a, (unsigned long long)__double_as_longlong(dk));
-            }
-            col_park<OutT>(slot + (uint32_t)m * (S * kSlotBytes), F[m]);
+        for (int j = 0; j < NS; ++j) {
+          const int m = me_cur - j;
+          if (m >= 0) smr |= ((sm >> (4 * m)) & 0xFu) << (4 * j);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int d = 128 * m + 4 * lane + e - phi;
+            F[j][e] = (m >= 0 && d >= 0 && d <= dprev) ? 1.0 : 0.0;
           }
         }
+        src_top = (nbl >> 3) + 4 * me_cur;
+        fd_top = (double)(4 * lane - phi + 128 * me_cur);
+        ptop = ISROW ? org + (ptrdiff_t)(dir * k) * nx + estep * 128 * me_cur
+                     : org + (ptrdiff_t)(estep * 128 * me_cur) * nx;
+        slot_lane = slot0 + (uint32_t)me_cur * kSliceBytes;
       }
     }
-    if (ISROW) {
-      rp += rstep;
-    } else {
-      // ---- flush the sector block when it is complete --------------------------
+
+    if (general) {
+      const double2 rr = __ldg(p.rtab + k);
+      const double rh = rr.x, rl = rr.y;
+      if (has_edge && me != me_cur) { // the edge enters the next slice: rename
+#pragma unroll
+        for (int j = NS - 1; j > 0; --j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) F[j][e] = F[j - 1][e];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) F[0][e] = 0.0;
+        ++me_cur;
+        smr = (smr << 4) | ((sm >> (4 * me_cur)) & 0xFu);
+        src_top += 4;
+        fd_top = __dadd_rn(fd_top, 128.0);
+        ptop += estep * 128 * (ISROW ? 1 : nx);
+        slot_lane += kSliceBytes;
+      }
+
+      double rprev = 0.0;
+      const uint32_t slot = slot_lane + (uint32_t)(t & (S - 1)) * kSlotBytes;
+      // ---- interior slices, ascending offsets (fall-through chain) ---------------
+      switch (me_cur) {
+        case 7: if (NS > 7) VHP_SLICE(NS > 7 ? 7 : 0)
+        case 6: if (NS > 6) VHP_SLICE(NS > 6 ? 6 : 0)
+        case 5: if (NS > 5) VHP_SLICE(NS > 5 ? 5 : 0)
+        case 4: if (NS > 4) VHP_SLICE(NS > 4 ? 4 : 0)
+        case 3: if (NS > 3) VHP_SLICE(NS > 3 ? 3 : 0)
+        case 2: if (NS > 2) VHP_SLICE(NS > 2 ? 2 : 0)
+        case 1: if (NS > 1) VHP_SLICE(NS > 1 ? 1 : 0)
+        default: break;
+      }
+      if (!has_edge) {
+        VHP_SLICE(0)
+      } else {
+        // ---- edge slice ----------------------------------------------------------
+        const double r = rot_up(F[0][3], lane);
+        const double nb = lane ? r : rprev;
+        const uint32_t nib = __shfl_sync(kFull, wcur, src_top) >> nshift;
+        const int r0 = dstar - 128 * me_cur - 4 * lane;
+        if (ISROW) {
+          // offsets d <= k-1 are interpolated; d == k-1 starts from the diagonal cell
+          const uint32_t wedge = r0 >= 3 ? 0xFu : (r0 < 0 ? 0u : (2u << r0) - 1u);
+          if (k >= 2) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (e == r0) F[0][e] = dval;
+          }
+          slice_update<0>(F[0], nb, nib & wedge, fd_top, rh, rl);
+          row_store<OutT, VEC>(ptop, estep, F[0], smr & wedge);
+        } else {
+          // offsets d <= k-1 are interpolated, d == k is the diagonal cell
+          const uint32_t wedge = r0 >= 4 ? 0xFu : (r0 <= 0 ? 0u : (1u << r0) - 1u);
+          slice_update<0>(F[0], nb, nib & wedge, fd_top, rh, rl);
+          double pz = 0.0;
+          if ((dstar & 3) == 0) { // the diagonal offset is some lane's e == 0
+            const double pr = rot_up(F[0][3], lane);
+            const double p0 = __shfl_sync(kFull, F[NS > 1 ? 1 : 0][3], 31);
+            pz = lane ? pr : p0;
+          }
+          if ((unsigned)r0 < 4u) {
+            const double pv = r0 == 0 ? pz : (r0 == 1 ? F[0][0] : (r0 == 2 ? F[0][1] : F[0][2]));
+            const double dk = ((nib >> r0) & 1u) ? pv : 0.0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (e == r0) F[0][e] = dk;
+            // hand the diagonal cell to the row octant of this quadrant (its shared memory)
+            if (k <= jlast)
+              asm volatile("st.relaxed.cluster.shared::cluster.u64 [%0], %1;" ::"r"(diag + 8u * (uint32_t)k),
+                           "l"(__double_as_longlong(dk)) : "memory");
+          }
+          col_park<OutT>(slot, F[0]);
+        }
+      }
+      if (ISROW) ptop += rstep;
+    }
+    if (!ISROW) {
+      // ---- flush the parked block when it is complete ----------------------------
       const int kk = t & (S - 1);
       const bool last = (dir > 0 ? kk == S - 1 : kk == 0) || k == K;
       if (last) {
-        __syncwarp();
         const int xb = t & ~(S - 1);
-        // ring of slot j: kj = dir * (xb + j - sx); parked rings are blk_lo..k
-        const int mtop = has_edge ? me : g.nsl - 1;
         const bool full = (k - blk_lo + 1) == S;
-        const int kmin = blk_lo; // earliest ring in the block: offsets d <= kmin are in every ring
-#pragma unroll
-        for (int m = 0; m < NS; ++m) {
-          if (m <= mtop) {
-            const uint32_t sl = stage + (uint32_t)m * (S * kSlotBytes) + 16u * (uint32_t)lane;
-            const uint32_t smm = (sm >> (4 * m)) & 0xFu;
-            const int d0 = 128 * m + 4 * lane - phi;
-            OutT *q = rp + (ptrdiff_t)(estep * 128 * m) * nx + xb;
-            if (VEC && full && smm == 0xFu && d0 + 3 <= kmin) {
-              if constexpr (sizeof(OutT) == 4) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  float4 v[4];
-#pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w)
-                                 : "r"(sl + (uint32_t)(4 * h + j) * kSlotBytes));
-                  stg16(q + 4 * h, v[0].x, v[1].x, v[2].x, v[3].x);
-                  stg16(q + (ptrdiff_t)estep * nx + 4 * h, v[0].y, v[1].y, v[2].y, v[3].y);
-                  stg16(q + (ptrdiff_t)estep * 2 * nx + 4 * h, v[0].z, v[1].z, v[2].z, v[3].z);
-                  stg16(q + (ptrdiff_t)estep * 3 * nx + 4 * h, v[0].w, v[1].w, v[2].w, v[3].w);
-                }
-              } else {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  double2 lo[2], hi[2];
-#pragma unroll
-                  for (int j = 0; j < 2; ++j) {
-                    const uint32_t a = sl + (uint32_t)(2 * h + j) * kSlotBytes;
-                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
-                                 : "=d"(lo[j].x), "=d"(lo[j].y) : "r"(a));
-                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
-                                 : "=d"(hi[j].x), "=d"(hi[j].y) : "r"(a + 512u));
-                  }
-                  stg16(q + 2 * h, lo[0].x, lo[1].x);
-                  stg16(q + (ptrdiff_t)estep * nx + 2 * h, lo[0].y, lo[1].y);
-                  stg16(q + (ptrdiff_t)estep * 2 * nx + 2 * h, hi[0].x, hi[1].x);
-                  stg16(q + (ptrdiff_t)estep * 3 * nx + 2 * h, hi[0].y, hi[1].y);
-                }
-              }
-            } else if (smm) {
-              // slow path: block not full, diagonal band, or grid edge
+        OutT *rowp = org + xb; // slice 0, element 0
 #pragma unroll 1
-              for (int j = 0; j < S; ++j) {
-                const int kj = dir * (xb + j - sx);
-                if (kj < blk_lo || kj > k) continue;
+        for (int m = 0; m <= me; ++m, rowp += (ptrdiff_t)(estep * 128) * nx) {
+          const uint32_t sl = stage + (uint32_t)m * kSliceBytes + 16u * (uint32_t)lane;
+          const uint32_t smm = (sm >> (4 * m)) & 0xFu;
+          const int d0 = 128 * m + 4 * lane - phi;
+          if (d0 > k || smm == 0u) continue; // nothing of this thread is inside the wedge yet
+          OutT *q = rowp;
+          if (VEC && full && smm == 0xFu && d0 + 3 <= blk_lo) {
+            if constexpr (sizeof(OutT) == 4) {
+              float4 v[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  if (((smm >> e) & 1u) && d0 + e <= kj) {
-                    OutT val;
-                    const uint32_t a = sl + (uint32_t)j * kSlotBytes;
-                    if constexpr (sizeof(OutT) == 4)
-                      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(a + 4u * e));
-                    else
-                      asm volatile("ld.shared.f64 %0, [%1];"
-                                   : "=d"(val) : "r"(a + (e >> 1) * 512u + (e & 1) * 8u));
-                    __stcs(q + (ptrdiff_t)(estep * e) * nx + j, val);
-                  }
+              for (int j = 0; j < 4; ++j)
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w)
+                             : "r"(sl + (uint32_t)j * kSlotBytes));
+              stg16(q, v[0].x, v[1].x, v[2].x, v[3].x);
+              stg16(q + (ptrdiff_t)estep * nx, v[0].y, v[1].y, v[2].y, v[3].y);
+              stg16(q + (ptrdiff_t)estep * 2 * nx, v[0].z, v[1].z, v[2].z, v[3].z);
+              stg16(q + (ptrdiff_t)estep * 3 * nx, v[0].w, v[1].w, v[2].w, v[3].w);
+            } else {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                double2 lo[2], hi[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  const uint32_t a = sl + (uint32_t)(2 * h + j) * kSlotBytes;
+                  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+                               : "=d"(lo[j].x), "=d"(lo[j].y) : "r"(a));
+                  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+                               : "=d"(hi[j].x), "=d"(hi[j].y) : "r"(a + 512u));
+                }
+                stg16(q + 2 * h, lo[0].x, lo[1].x);
+                stg16(q + (ptrdiff_t)estep * nx + 2 * h, lo[0].y, lo[1].y);
+                stg16(q + (ptrdiff_t)estep * 2 * nx + 2 * h, hi[0].x, hi[1].x);
+                stg16(q + (ptrdiff_t)estep * 3 * nx + 2 * h, hi[0].y, hi[1].y);
+              }
+            }
+          } else {
+            // slow path: block not full, diagonal band, or grid edge
+#pragma unroll 1
+            for (int j = 0; j < S; ++j) {
+              const int kj = dir * (xb + j - sx);
+              if (kj < blk_lo || kj > k) continue;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (((smm >> e) & 1u) && d0 + e <= kj) {
+                  OutT val;
+                  const uint32_t a = sl + (uint32_t)j * kSlotBytes;
+                  if constexpr (sizeof(OutT) == 4)
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(a + 4u * e));
+                  else
+                    asm volatile("ld.shared.f64 %0, [%1];"
+                                 : "=d"(val) : "r"(a + (e >> 1) * 512u + (e & 1) * 8u));
+                  __stcs(q + (ptrdiff_t)(estep * e) * nx + j, val);
                 }
               }
             }
           }
         }
-        __syncwarp();
         blk_lo = k + 1;
       }
     }
   }
+#undef VHP_SLICE
 }
 
+// One warp-sized CTA per octant; the two octants of a quadrant form a cluster:
+// rank 0 = column octant (produces the diagonal cells), rank 1 = row octant
+// (consumes them; the hand-off array lives in ITS shared memory and the column
+// octant writes it through the cluster's distributed shared memory).  Everything
+// that selects the role derives from blockIdx, so the compiler can prove the
+// control flow warp-uniform.
 template <typename OutT, int NS, bool VEC>
-__global__ void __launch_bounds__(256, NS >= 8 ? 2 : (NS >= 4 ? 3 : 4))
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32, VHP_OCT_MINB)
 sweep_octant_kernel(const OctArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int W = 128 * NS;
-  const int tid = threadIdx.x, w = tid >> 5;
-  const int64_t pair = blockIdx.x;
+  const int lane = threadIdx.x;
+  const bool isrow = blockIdx.x & 1;
+  const int qx = (blockIdx.x >> 1) & 1, qy = (blockIdx.x >> 2) & 1; // 1 = the "-" side
+  const int64_t pair = blockIdx.x >> 3;
   const int nx = p.nx, ny = p.ny;
   const int sx = __ldg(p.src_xy + 2 * pair), sy = __ldg(p.src_xy + 2 * pair + 1);
-  if ((unsigned)sx >= (unsigned)nx || (unsigned)sy >= (unsigned)ny) { // CTA-uniform
-    if (tid == 0) atomicOr(p.err, 1);
+  if ((unsigned)sx >= (unsigned)nx || (unsigned)sy >= (unsigned)ny) { // uniform over the cluster
+    if (lane == 0) atomicOr(p.err, 1);
     return;
   }
+  const int Ex = qx ? sx : nx - 1 - sx, Ey = qy ? sy : ny - 1 - sy; // quadrant extents
   const int map = p.src_map ? __ldg(p.src_map + pair) : 0;
   OutT *out = reinterpret_cast<OutT *>(p.out) + (size_t)pair * nx * ny;
-  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
-  for (int i = tid; i < 4 * kRing; i += blockDim.x) st_slot(smem0 + 8u * i, kEmpty);
-  __syncthreads();
-
   const double s0 = __ldg(p.occ + ((size_t)map * ny + sy) * nx + sx) ? 1.0 : 0.0;
-  if (tid == 0) out[(size_t)sy * nx + sx] = to_out<OutT>(s0);
+  if ((blockIdx.x & 7) == 1 && lane == 0) out[(size_t)sy * nx + sx] = to_out<OutT>(s0);
 
-  const bool isrow = w < 4;
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  if (isrow) {
+    const int nd = min(Ex, Ey) + 1;
+    for (int i = lane; i < nd; i += 32) st_slot(smem0 + 8u * i, kEmpty);
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;"
+               ::: "memory");
+
   Oct g;
-  g.dir_ac = (w & 2) ? -1 : 1;
-  g.rev = w & 1;
+  g.dir_ac = (isrow ? qy : qx) ? -1 : 1;
+  g.rev = isrow ? qx : qy;
   g.s_ac = isrow ? sy : sx;
-  g.n_ac = isrow ? ny : nx;
-  g.n_al = isrow ? nx : ny;
   const int s_al = isrow ? sx : sy;
-  g.K = g.dir_ac > 0 ? g.n_ac - 1 - g.s_ac : g.s_ac;
-  g.Dlim = g.rev ? s_al : g.n_al - 1 - s_al;
+  g.K = isrow ? Ey : Ex;
+  g.Dlim = isrow ? Ex : Ey;
   const int sp = g.rev ? W - 1 - s_al : s_al; // plane coordinate of the source
   g.phi = sp & 3;
   g.base = sp & ~3;
   g.nsl = ((g.Dlim + g.phi) >> 7) + 1;
   if (g.K == 0 || (g.rev && g.Dlim == 0)) return;
 
-  // quadrant of this octant: bit 0 = -x side, bit 1 = -y side
-  const int qx = isrow ? g.rev : (g.dir_ac < 0);
-  const int qy = isrow ? (g.dir_ac < 0) : g.rev;
-  const uint32_t ring = smem0 + 8u * kRing * (uint32_t)(qx + 2 * qy);
-
   if (isrow) {
     const uint32_t *plane = (g.rev ? p.row_r : p.row_f) + (size_t)map * p.row_plane;
-    octant_sweep<OutT, NS, VEC, true>(p, g, sx, sy, s0, plane, out, ring, 0u);
+    octant_sweep<OutT, NS, VEC, true>(p, g, sx, s0, plane, out, smem0, 0u);
   } else {
-    // staging: [octant][slice][ring slot][lane] 16-byte (fp32) / 2 x 16-byte (fp64) slots
-    const int nslp = ((ny - 1 - sy + (sy & 3)) >> 7) + 1;
-    const int nslm = ((sy + ((W - 1 - sy) & 3)) >> 7) + 1;
-    const int c = w - 4; // 0 CR+, 1 CR-, 2 CL+, 3 CL-
-    const int off = (c & 1 ? nslp : 0) + (c & 2 ? nslp + nslm : 0);
-    const uint32_t stage = smem0 + 8u * kRing * 4u + (uint32_t)off * 4096u;
+    // the row octant's copy of smem0 (cluster rank 1)
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem0), "r"(1));
     const uint32_t *plane = (g.rev ? p.col_r : p.col_f) + (size_t)map * p.col_plane;
-    octant_sweep<OutT, NS, VEC, false>(p, g, sx, sy, s0, plane, out, ring, stage);
+    octant_sweep<OutT, NS, VEC, false>(p, g, sx, s0, plane, out, remote, smem0);
   }
 }
 
@@ -531,7 +647,7 @@ cudaError_t launch_oct(const OctArgs &p, int64_t npairs, size_t smem, cudaStream
   auto kern = sweep_octant_kernel<OutT, NS, VEC>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<(unsigned)npairs, 256, smem, st>>>(p);
+  kern<<<(unsigned)(npairs * 8), 32, smem, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -596,8 +712,11 @@ cudaError_t vhp_launch_sweep_octant(const VhpOctPlanes &pl, const uint8_t *d_occ
   p.out = d_out;
   p.rtab = reinterpret_cast<const double2 *>(d_rcp2);
   p.err = d_err;
-  // rings + column staging: 2 * (slices of the +y side + slices of the -y side) * 4 KB
-  const size_t smem = 8 * kRing * 4 + (size_t)2 * (((ny + 6) >> 7) + 2) * 4096;
+  // diagonal hand-off array + the column octant's parking slots (S = 4 rings per slice)
+  const size_t slice_bytes = dtype == VHP_F32 ? 2048 : 4096;
+  // (the row octant uses the block as hand-off array, the column octant as parking slots)
+  const size_t smem = std::max(8 * (size_t)(std::min(nx, ny) + 2),
+                               (size_t)(((ny + 2) >> 7) + 1) * slice_bytes);
   const bool vec = (dtype == VHP_F32) ? (nx % 4 == 0) : (nx % 2 == 0);
   cudaError_t e;
   if (dtype == VHP_F32)
