@@ -100,6 +100,39 @@ vhp_status pack_oct(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx, i
   return VHP_OK;
 }
 
+// bit planes of the tile kernel, cached like pack_maps (same sticky flag)
+vhp_status pack_tile(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx, int ny,
+                     bool force) {
+  if (!force && ctx->packed_sticky && ctx->tile_src == d_occ && ctx->tile_nmaps == nmaps &&
+      ctx->tile_nx == nx && ctx->tile_ny == ny)
+    return VHP_OK;
+  int wx, wy, nsum;
+  vhp_tile_plane_geometry(nx, ny, &wx, &wy, &nsum);
+  const size_t row_plane = (size_t)ny * wx, col_plane = (size_t)nx * wy;
+  const size_t bytes = (size_t)nmaps * (2 * (row_plane + col_plane) + nsum) * sizeof(uint32_t);
+  if (bytes > ctx->tile_bytes) {
+    if (ctx->tile_buf) {
+      VHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      VHP_CUDA(ctx, cudaFree(ctx->tile_buf));
+      ctx->tile_buf = nullptr;
+    }
+    VHP_CUDA(ctx, cudaMalloc(&ctx->tile_buf, bytes));
+    ctx->tile_bytes = bytes;
+  }
+  uint32_t *rowF = ctx->tile_buf, *rowR = rowF + (size_t)nmaps * row_plane;
+  uint32_t *colF = rowR + (size_t)nmaps * row_plane, *colR = colF + (size_t)nmaps * col_plane;
+  uint32_t *bsum = colR + (size_t)nmaps * col_plane;
+  VHP_CUDA(ctx, vhp_launch_pack_tile(d_occ, nmaps, nx, ny, rowF, rowR, colF, colR, bsum,
+                                     ctx->stream, &ctx->launches));
+  ctx->tile.rowF = rowF; ctx->tile.rowR = rowR;
+  ctx->tile.colF = colF; ctx->tile.colR = colR;
+  ctx->tile.bsum = bsum;
+  ctx->tile.wx = wx; ctx->tile.wy = wy;
+  ctx->tile.row_plane = row_plane; ctx->tile.col_plane = col_plane;
+  ctx->tile_src = d_occ; ctx->tile_nmaps = nmaps; ctx->tile_nx = nx; ctx->tile_ny = ny;
+  return VHP_OK;
+}
+
 // (re)build the bit planes for d_occ unless they are cached for this pointer
 vhp_status pack_maps(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx, int ny,
                      bool force) {
@@ -193,6 +226,14 @@ vhp_status run_dev(vhp_context *ctx, Op op, const uint8_t *d_occ, int nmaps, int
   const bool front_fits = vhp_sweep_front_supported(nx, ny);
   const bool ring_fits = vhp_sweep_ring_supported(nx, ny);
   const bool oct_fits = vhp_sweep_octant_supported(nx, ny);
+  if ((ctx->sweep_impl == 0 || ctx->sweep_impl == 5) && vhp_sweep_tile_supported(nx, ny)) {
+    vhp_status st = ensure_rcp2(ctx, n_max + 8);
+    if (st != VHP_OK) return st;
+    if ((st = pack_tile(ctx, d_occ, nmaps, nx, ny, false)) != VHP_OK) return st;
+    VHP_CUDA(ctx, vhp_launch_sweep_tile(ctx->tile, nx, ny, d_xy, d_map, n, dtype, d_out,
+                                        ctx->rcp2_table, ctx->d_err, ctx->stream, &ctx->launches));
+    return VHP_OK;
+  }
   if (ctx->sweep_impl == 4 && oct_fits && aligned) {
     vhp_status st = ensure_rcp2(ctx, n_max + 8);
     if (st != VHP_OK) return st;
@@ -257,10 +298,15 @@ vhp_status run_host(vhp_context *ctx, Op op, const uint8_t *occ, int nmaps, int 
   ctx->packed_src = nullptr; // b_occ content changed
   ctx->packed_sticky = false;
   ctx->oct_src = nullptr;
+  ctx->tile_src = nullptr;
   if (op == Op::Sweep && ctx->sweep_impl != 1) { // pack once for all chunks
+    const bool use_tile = (ctx->sweep_impl == 0 || ctx->sweep_impl == 5) &&
+                          vhp_sweep_tile_supported(nx, ny);
     const bool use_oct = ctx->sweep_impl == 4 &&
                          vhp_sweep_octant_supported(nx, ny);
-    if (use_oct)
+    if (use_tile)
+      st = pack_tile(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, true);
+    else if (use_oct)
       st = pack_oct(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, true);
     else
       st = pack_maps(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, true);
@@ -306,6 +352,7 @@ vhp_status run_host(vhp_context *ctx, Op op, const uint8_t *occ, int nmaps, int 
   ctx->packed_sticky = false;
   ctx->packed_src = nullptr;
   ctx->oct_src = nullptr;
+  ctx->tile_src = nullptr;
   if (result != VHP_OK) return result;
   if (e1 != cudaSuccess) return cuda_fail(ctx, e1, "sync copy stream");
   if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "sync stream");
@@ -424,6 +471,7 @@ vhp_status vhp_context_create(int device, void *cuda_stream, vhp_context **out) 
   if (impl && std::strcmp(impl, "front") == 0) ctx->sweep_impl = 2;
   if (impl && std::strcmp(impl, "ring") == 0) ctx->sweep_impl = 3;
   if (impl && std::strcmp(impl, "octant") == 0) ctx->sweep_impl = 4;
+  if (impl && std::strcmp(impl, "tile") == 0) ctx->sweep_impl = 5;
   *out = ctx;
   return VHP_OK;
 }
@@ -439,6 +487,7 @@ void vhp_context_destroy(vhp_context *ctx) {
     if (b->p) cudaFree(b->p);
   if (ctx->packed_buf) cudaFree(ctx->packed_buf);
   if (ctx->oct_buf) cudaFree(ctx->oct_buf);
+  if (ctx->tile_buf) cudaFree(ctx->tile_buf);
   if (ctx->rcp_table) cudaFree(ctx->rcp_table);
   if (ctx->rcp2_table) cudaFree(ctx->rcp2_table);
   if (ctx->d_err) cudaFree(ctx->d_err);
@@ -464,6 +513,8 @@ vhp_status vhp_prepare_maps_dev(vhp_context *ctx, const uint8_t *d_occ, int nmap
   vhp_status st = pack_maps(ctx, d_occ, nmaps, nx, ny, true);
   if (st == VHP_OK && vhp_sweep_octant_supported(nx, ny))
     st = pack_oct(ctx, d_occ, nmaps, nx, ny, true);
+  if (st == VHP_OK && vhp_sweep_tile_supported(nx, ny))
+    st = pack_tile(ctx, d_occ, nmaps, nx, ny, true);
   if (st == VHP_OK) ctx->packed_sticky = true;
   return st;
 }

@@ -1,0 +1,167 @@
+// kernels_sweep_tile.cu -- K1, batched visibility sweep as a tile wavefront (the
+// default sweep kernel).
+//
+// Replaces visibilityBasedSolver::computeVisibility
+// (reference src/visibilityBasedSolver.cpp:570-696) over a batch of (map, source)
+// pairs: one CTA per pair, see sweep_tile_body.cuh for the decomposition.
+#include <algorithm>
+#include <cstdint>
+
+#include "sweep_tile_body.cuh"
+
+namespace {
+
+template <typename OutT>
+__global__ void __launch_bounds__(kTileWarps * 32)
+sweep_tile_kernel(const TileArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int64_t pair = blockIdx.x;
+  const int sx = __ldg(p.src_xy + 2 * pair), sy = __ldg(p.src_xy + 2 * pair + 1);
+  if ((unsigned)sx >= (unsigned)p.nx || (unsigned)sy >= (unsigned)p.ny) { // uniform over the CTA
+    if (threadIdx.x == 0) atomicOr(p.err, 1);
+    return;
+  }
+  const int map = p.src_map ? __ldg(p.src_map + pair) : 0;
+  OutT *out = reinterpret_cast<OutT *>(p.out) + (size_t)pair * p.nx * p.ny;
+  tile_sweep_cta<OutT>(p, map, sx, sy, out, smem_raw);
+}
+
+// ---------------------------------------------------------------------------------
+// Bit planes.  wx = ceil(nx/32) + 1 words per row line, wy likewise per column line
+// (one zero word of padding so a 32-bit window may start in the last data word).
+//   rowF[m][y][w] bit b = occ(32w + b, y)            rowR: x mirrored, p = 32*WX - 1 - x
+//   colF[m][x][w] bit b = occ(x, 32w + b)            colR: y mirrored, p = 32*WY - 1 - y
+// Bits outside the grid are 0 ("occupied").
+// ---------------------------------------------------------------------------------
+__global__ void pack_tile_rows_kernel(const uint8_t *__restrict__ occ, int nmaps, int nx, int ny,
+                                      int wx, uint32_t *__restrict__ rowF,
+                                      uint32_t *__restrict__ rowR) {
+  const size_t total = (size_t)nmaps * ny * wx;
+  const int W = 32 * (wx - 1);
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int w = (int)(idx % wx);
+    const uint8_t *row = occ + (idx / wx) * nx;
+    uint32_t f = 0, r = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int xf = 32 * w + b, xr = W - 1 - xf;
+      if (xf < nx && row[xf] != 0) f |= 1u << b;
+      if (xr >= 0 && xr < nx && row[xr] != 0) r |= 1u << b;
+    }
+    rowF[idx] = f;
+    rowR[idx] = r;
+  }
+}
+
+__global__ void pack_tile_cols_kernel(const uint8_t *__restrict__ occ, int nmaps, int nx, int ny,
+                                      int wy, uint32_t *__restrict__ colF,
+                                      uint32_t *__restrict__ colR) {
+  // x fastest across threads so the strided byte reads coalesce
+  const size_t total = (size_t)nmaps * wy * nx;
+  const int W = 32 * (wy - 1);
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % nx);
+    const size_t mw = idx / nx;
+    const int w = (int)(mw % wy);
+    const size_t m = mw / wy;
+    const uint8_t *base = occ + m * (size_t)nx * ny + x;
+    uint32_t f = 0, r = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int yf = 32 * w + b, yr = W - 1 - yf;
+      if (yf < ny && base[(size_t)yf * nx] != 0) f |= 1u << b;
+      if (yr >= 0 && yr < ny && base[(size_t)yr * nx] != 0) r |= 1u << b;
+    }
+    const size_t o = (m * nx + x) * wy + w;
+    colF[o] = f;
+    colR[o] = r;
+  }
+}
+
+// bsum[m][by][w] bit (bx & 31) of word bx >> 5 = every in-grid cell of the aligned block
+// x in [32bx, 32bx+32), y in [32by, 32by+32) is free.  One warp per block (lane = row),
+// from the forward row plane; bsum must be zeroed first.
+__global__ void pack_tile_sum_kernel(const uint32_t *__restrict__ rowF, int nmaps, int nx, int ny,
+                                     int wx, uint32_t *__restrict__ bsum) {
+  const int nbx = (nx + 31) >> 5, nby = (ny + 31) >> 5, nbw = tile_sum_words(nx);
+  const size_t total = (size_t)nmaps * nby * nbx;
+  const int lane = threadIdx.x & 31;
+  for (size_t blk = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5; blk < total;
+       blk += ((size_t)gridDim.x * blockDim.x) >> 5) {
+    const int bx = (int)(blk % nbx);
+    const size_t mb = blk / nbx;
+    const int by = (int)(mb % nby);
+    const size_t m = mb / nby;
+    const int y = 32 * by + lane;
+    const int nv = nx - 32 * bx;
+    const uint32_t valid = nv >= 32 ? ~0u : (1u << nv) - 1u;
+    bool ok = true;
+    if (y < ny) ok = (__ldg(rowF + (m * ny + y) * wx + bx) & valid) == valid;
+    if (__all_sync(0xffffffffu, ok) && lane == 0)
+      atomicOr(bsum + (m * nby + by) * nbw + (bx >> 5), 1u << (bx & 31));
+  }
+}
+
+template <typename OutT>
+cudaError_t launch_tile(const TileArgs &p, int64_t npairs, cudaStream_t st) {
+  const size_t smem = tile_smem_bytes<OutT>(p.nx, p.ny);
+  auto kern = sweep_tile_kernel<OutT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<(unsigned)npairs, kTileWarps * 32, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+} // namespace
+
+bool vhp_sweep_tile_supported(int nx, int ny) {
+  return nx >= 1 && ny >= 1 && std::max(nx, ny) <= 16384 &&
+         tile_smem_bytes<double>(nx, ny) <= 227u * 1024u;
+}
+
+void vhp_tile_plane_geometry(int nx, int ny, int *wx, int *wy, int *sum_words_per_map) {
+  *wx = ((nx + 31) >> 5) + 1;
+  *wy = ((ny + 31) >> 5) + 1;
+  *sum_words_per_map = tile_sum_words(nx) * ((ny + 31) >> 5);
+}
+
+cudaError_t vhp_launch_pack_tile(const uint8_t *d_occ, int nmaps, int nx, int ny, uint32_t *rowF,
+                                 uint32_t *rowR, uint32_t *colF, uint32_t *colR, uint32_t *bsum,
+                                 cudaStream_t st, int64_t *launches) {
+  int wx, wy, nsum;
+  vhp_tile_plane_geometry(nx, ny, &wx, &wy, &nsum);
+  const size_t tr = (size_t)nmaps * ny * wx, tc = (size_t)nmaps * nx * wy;
+  const int bs = 256;
+  const unsigned gr = (unsigned)std::min<size_t>((tr + bs - 1) / bs, 148u * 32u);
+  const unsigned gc = (unsigned)std::min<size_t>((tc + bs - 1) / bs, 148u * 32u);
+  pack_tile_rows_kernel<<<gr, bs, 0, st>>>(d_occ, nmaps, nx, ny, wx, rowF, rowR);
+  pack_tile_cols_kernel<<<gc, bs, 0, st>>>(d_occ, nmaps, nx, ny, wy, colF, colR);
+  cudaError_t e = cudaMemsetAsync(bsum, 0, (size_t)nmaps * nsum * sizeof(uint32_t), st);
+  if (e != cudaSuccess) return e;
+  const size_t nblk = (size_t)nmaps * ((nx + 31) >> 5) * ((ny + 31) >> 5);
+  const unsigned gs = (unsigned)std::min<size_t>((nblk * 32 + bs - 1) / bs, 148u * 32u);
+  pack_tile_sum_kernel<<<gs, bs, 0, st>>>(rowF, nmaps, nx, ny, wx, bsum);
+  if (launches) *launches += 3;
+  return cudaGetLastError();
+}
+
+cudaError_t vhp_launch_sweep_tile(const VhpTilePlanes &pl, int nx, int ny, const int32_t *d_src_xy,
+                                  const int32_t *d_src_map, int64_t npairs, vhp_dtype dtype,
+                                  void *d_out, const double *d_rcp2, int *d_err, cudaStream_t st,
+                                  int64_t *launches) {
+  TileArgs p;
+  p.pl = pl;
+  p.nx = nx;
+  p.ny = ny;
+  p.src_xy = d_src_xy;
+  p.src_map = d_src_map;
+  p.out = d_out;
+  p.rtab = reinterpret_cast<const double2 *>(d_rcp2);
+  p.err = d_err;
+  const size_t esz = dtype == VHP_F32 ? 4 : 8;
+  p.vec = ((uintptr_t)d_out % 16 == 0 && ((size_t)nx * esz) % 16 == 0) ? 1 : 0;
+  const cudaError_t e = dtype == VHP_F32 ? launch_tile<float>(p, npairs, st)
+                                         : launch_tile<double>(p, npairs, st);
+  if (launches) *launches += 1;
+  return e;
+}

@@ -1,0 +1,379 @@
+// sweep_tile_body.cuh -- K1 as a tile wavefront: the CTA-wide device function behind
+// the batched sweep kernel (kernels_sweep_tile.cu).
+//
+// Math (reference src/visibilityBasedSolver.cpp:570-696).  In the local
+// frame of one quadrant, i = |x - sx|, j = |y - sy|, cell q(i, j) is
+//     i >  j ("column octant"): (a - c*(a - b)) * occ,  a = q(i-1, j), b = q(i-1, j-1), c = j/i
+//     j >  i ("row octant")   : (a - c*(a - b)) * occ,  a = q(i, j-1), b = q(i-1, j-1), c = i/j
+//     i == j > 0              : q(i, j-1) * occ        (the reference has no i == j branch)
+//     i == j == 0             : 1 * occ
+// with every operation rounded once (no FMA contraction).  Axis cells (i == 0 or
+// j == 0) are the c == 0 case of the same formula: a - 0*(a - b) == a for any finite
+// b, so the virtual cells outside the quadrant can hold any finite value; they hold
+// 1.0 here, which also makes the source cell q(0,0) = q(0,-1) * occ = 1 * occ.
+//
+// Every dependency of a cell lies in {i-1, i} x {j-1, j}.  The quadrant is cut into
+// tiles (I, J) by the same break points 0, a, a+32, a+64, ... along i and j, so that the
+// diagonal only crosses the tiles I == J; the first tile row / column is a <= 32 wide,
+// with a chosen per quadrant so that every other tile column starts on an absolute x
+// that is a multiple of 32 (row stores are then whole, aligned 128-byte segments).
+// Tile (I, J) needs the top row of (I, J-1), the right column of (I-1, J) and one
+// corner cell of (I-1, J-1): tiles of an anti-diagonal I + J = d are independent
+// ("wave d").  The CTA walks the waves of all four quadrants together, one warp per
+// tile, one block barrier per wave (<= 2*N/32 + 2 barriers per sweep instead of N).
+// Boundary rows / columns live in shared memory as fp64:
+//     rowE[q][i]          = q(i, j_last)       top row of the newest tile above local column i
+//     colE[q][33*J + 1+r] = q(i_last, j0 + r)  right column of the newest tile in tile row J
+//     colE[q][33*J]       = the corner cell for the NEXT tile of row J
+//
+// A tile whose inputs all equal one value v and whose cells are all free is v
+// everywhere (a - c*(a - b) with a == b is exactly a): it is written with plain
+// 128-bit row stores and no arithmetic.  Likewise all-zero inputs, or an all-occupied
+// tile, give zeros.  Everything else runs the 32-step recurrence, one cell per lane:
+//     column-octant tile: lanes along j, steps along i, values staged in shared
+//                         memory and written as rows afterwards;
+//     row-octant tile   : lanes along i, steps along j, each step is one coalesced row;
+//     diagonal tile     : both fronts plus the diagonal cell, staged.
+// c = d/k is fma(d, rh, d*rl) with (rh, rl) a double-double 1/k (correctly rounded for
+// 0 <= d < k <= 16384, verified exhaustively by vhp_selftest_ratio).
+//
+// Whether a tile is free is first asked of a per-map summary (one bit per aligned
+// 32 x 32 block, copied to shared memory): a tile inside free blocks needs no global
+// load at all.  Otherwise occupancy comes from four bit planes per map (row / column
+// major, forward / mirrored) so that a 32-cell window of any quadrant is one funnel
+// shift of two words.  The cells the reference never writes (x == 0 in the -x
+// quadrants, y == 0 in the -y quadrants) are treated as occupied
+// and stored as 0.  Axis cells shared by two quadrants are stored by the + quadrant.
+#ifndef VHP_SWEEP_TILE_BODY_CUH
+#define VHP_SWEEP_TILE_BODY_CUH
+
+#include <cstdint>
+
+#include "vhp_internal.h"
+#include "sweep_common.cuh"
+
+namespace {
+
+constexpr int kTileWarps = 8;          // warps per CTA
+constexpr int kTile = 32;              // tile side
+constexpr int kStagePitch = 33;        // staging tile pitch (elements)
+constexpr int kWarpScratch = 72;       // doubles per warp: [0..32] boundary stream, [33..64] new edge
+constexpr unsigned kAll = 0xffffffffu;
+
+struct TileArgs {
+  VhpTilePlanes pl;
+  int nx, ny;
+  const int32_t *src_xy, *src_map;
+  void *out;
+  const double2 *rtab; // {RN(1/k), RN((1 - k*rh)*rh)}
+  int *err;
+  int vec;             // rows are 16-byte aligned: 128-bit stores allowed
+};
+
+// geometry of one quadrant (shared memory, written once per sweep)
+struct TQuad {
+  int dirx, diry;   // +1 / -1
+  int Ex, Ey;       // largest local i / j inside the grid
+  int TX, TY;       // tile columns / rows (0: the quadrant does not exist)
+  int rowOff, colOff; // offsets of rowE / colE in the edge region (doubles)
+  int psx, psy;     // plane coordinate of the source along x / y
+  int a;            // width of the first tile row / column (1..32)
+  int pad0;
+};
+
+__host__ __device__ inline int tile_edge_doubles(int nx, int ny) {
+  // per direction a quadrant has at most E/32 + 2 tile columns (rows); two quadrants share
+  // each x (y) direction and the + and - extents add up to nx - 1 (ny - 1)
+  return 2 * kTile * ((nx - 1) / kTile + 4) + 2 * 33 * ((ny - 1) / kTile + 4);
+}
+
+// block summary: one bit per aligned 32 x 32 block, tile_sum_words(nx) words per block row
+__host__ __device__ inline int tile_sum_words(int nx) { return (((nx + 31) >> 5) + 31) >> 5; }
+__host__ __device__ inline int tile_sum_bytes(int nx, int ny) {
+  return (4 * tile_sum_words(nx) * ((ny + 31) >> 5) + 15) & ~15;
+}
+
+template <typename OutT>
+__host__ __device__ inline size_t tile_smem_bytes(int nx, int ny) {
+  return 256 + tile_sum_bytes(nx, ny) + sizeof(double) * (size_t)tile_edge_doubles(nx, ny) +
+         (size_t)kTileWarps * (kTile * kStagePitch * sizeof(OutT) + kWarpScratch * sizeof(double));
+}
+
+// 16-byte streaming store of one value replicated
+__device__ __forceinline__ void stg16_fill(float *q, float v) {
+  __stcs(reinterpret_cast<float4 *>(q), make_float4(v, v, v, v));
+}
+__device__ __forceinline__ void stg16_fill(double *q, double v) {
+  __stcs(reinterpret_cast<double2 *>(q), make_double2(v, v));
+}
+
+// One tile (I, J) of quadrant g by one warp.
+template <typename OutT>
+__device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
+                                             const uint32_t *__restrict__ rowpl,
+                                             const uint32_t *__restrict__ colpl,
+                                             const uint32_t *__restrict__ bsum, const int sx,
+                                             const int sy, const int I, const int J,
+                                             OutT *__restrict__ out, double *edges,
+                                             OutT *stage, double *wscr, const int lane) {
+  const int nx = p.nx;
+  const int wi = I ? kTile : g.a, wj = J ? kTile : g.a;          // tile extent
+  const int i0 = I ? g.a + kTile * (I - 1) : 0, j0 = J ? g.a + kTile * (J - 1) : 0;
+  const int il = i0 + lane, jr = j0 + lane;
+  // the never-written border column / row is "occupied": exclude it from the compute extent
+  const int ExC = g.Ex - (g.dirx < 0), EyC = g.Ey - (g.diry < 0);
+  const int nvx = min(wi, ExC - i0 + 1), nvy = min(wj, EyC - j0 + 1); // columns / rows to compute
+  const uint32_t cmask = nvx >= 32 ? ~0u : (nvx <= 0 ? 0u : (1u << nvx) - 1u);
+  const uint32_t rmask = nvy >= 32 ? ~0u : (nvy <= 0 ? 0u : (1u << nvy) - 1u);
+  const bool colc = (cmask >> lane) & 1u, rowc = (rmask >> lane) & 1u;
+  double *rowE = edges + g.rowOff + i0;
+  double *colE = edges + g.colOff + 33 * J;
+
+  // ---- occupancy: block summary first, bit plane otherwise --------------------------
+  bool allfree = false, allocc = true, sumfree = false;
+  uint32_t wrow = 0;
+  if (nvx > 0 && nvy > 0) {
+    const int xa = sx + g.dirx * i0, xb = sx + g.dirx * (i0 + nvx - 1);
+    const int ya = sy + g.diry * j0, yb = sy + g.diry * (j0 + nvy - 1);
+    const int bx0 = min(xa, xb) >> 5, bx1 = max(xa, xb) >> 5;
+    const int by0 = min(ya, yb) >> 5, by1 = max(ya, yb) >> 5;
+    const int nbw = tile_sum_words(nx);
+    const uint32_t *s0 = bsum + by0 * nbw, *s1 = bsum + by1 * nbw;
+    sumfree = ((s0[bx0 >> 5] >> (bx0 & 31)) & (s0[bx1 >> 5] >> (bx1 & 31)) &
+               (s1[bx0 >> 5] >> (bx0 & 31)) & (s1[bx1 >> 5] >> (bx1 & 31)) & 1u) != 0u;
+    if (sumfree) {
+      wrow = rowc ? cmask : 0u;
+      allfree = true;
+      allocc = false;
+    } else {
+      if (rowc) { // occupancy of row jr, bit b <-> local column i0 + b
+        const int p0 = g.psx + i0;
+        const uint32_t *rp = rowpl + (size_t)(sy + g.diry * jr) * p.pl.wx + (p0 >> 5);
+        wrow = __funnelshift_r(__ldg(rp), __ldg(rp + 1), p0 & 31) & cmask;
+      }
+      allfree = __all_sync(kAll, wrow == (rowc ? cmask : 0u));
+      allocc = __all_sync(kAll, wrow == 0u);
+    }
+  }
+  const double Bv = rowE[lane], Lv = colE[1 + lane], cor = colE[0];
+  const bool inuni = __all_sync(kAll, (!colc || Bv == cor) && (!rowc || Lv == cor));
+  const bool zero_in = inuni && cor == 0.0;
+
+  // store geometry: lane <-> column il of rows j0 .. j0 + wj - 1
+  const bool lane_st = lane < wi && il <= g.Ex && !(g.dirx < 0 && il == 0);
+  OutT *const ptr = out + (ptrdiff_t)(sy + g.diry * j0) * nx + (sx + g.dirx * il);
+  const ptrdiff_t rs = (ptrdiff_t)g.diry * nx;
+  const int r0 = (g.diry < 0 && j0 == 0) ? 1 : 0;   // the axis row belongs to the +y quadrant
+  const int rlast = min(wj - 1, g.Ey - j0);          // last row inside the grid
+
+  if (allocc || zero_in || (inuni && allfree)) {
+    // ---- uniform tile: no arithmetic -------------------------------------------------
+    const bool zero = allocc || zero_in;
+    if (allocc && !zero_in) { // live inputs end here
+      if (lane == wi - 1) colE[0] = Bv;
+      if (lane < wi) rowE[lane] = 0.0;
+      if (lane < wj) colE[1 + lane] = 0.0;
+    }
+    const int rc = min(wj - 1, EyC - j0); // last computed row; a border row (if any) follows
+    if (p.vec && nvx == 32 && (I > 0 || g.dirx > 0)) {
+      // all 32 columns are stored and x0 is a multiple of 32: 128-bit stores
+      constexpr int EPL = 16 / (int)sizeof(OutT), LPR = 32 / EPL; // elements per lane, lanes per row
+      const int sub = lane / LPR;
+      const int xlow = g.dirx > 0 ? sx + i0 : sx - i0 - 31;
+      const OutT v = to_out<OutT>(zero ? 0.0 : cor);
+      OutT *q = out + (ptrdiff_t)(sy + g.diry * (j0 + r0 + sub)) * nx + (xlow + (lane % LPR) * EPL);
+#pragma unroll 4
+      for (int r = r0 + sub; r <= rc; r += EPL, q += EPL * rs) stg16_fill(q, v);
+      if (rc < rlast && sub == 0)
+        stg16_fill(out + (ptrdiff_t)(sy + g.diry * (j0 + rlast)) * nx + (xlow + (lane % LPR) * EPL),
+                   (OutT)0);
+    } else if (lane_st) {
+      const OutT lv = to_out<OutT>((zero || !colc) ? 0.0 : cor);
+      OutT *q = ptr + r0 * rs;
+#pragma unroll 4
+      for (int r = r0; r <= rc; ++r, q += rs) __stcs(q, lv);
+      if (rc < rlast) __stcs(ptr + rlast * rs, (OutT)0);
+    }
+    return;
+  }
+
+  const double fd = (double)(I > J ? jr : il); // offset along the front (i0 == j0 on the diagonal)
+  wscr[1 + lane] = Bv;
+  if (lane == 0) wscr[0] = cor;
+  double *wnew = wscr + 33;
+  __syncwarp();
+
+  if (I > J) {
+    // ---- column-octant tile: lanes along j, steps along i (wi == 32) -------------------
+    double F = Lv;
+    const int ns = min(32, g.Ex - i0 + 1);
+#pragma unroll 4
+    for (int s = 0; s < ns; ++s) {
+      const double2 rr = __ldg(p.rtab + i0 + s);
+      const double up = __shfl_up_sync(kAll, F, 1);
+      const double b = lane ? up : wscr[s];
+      const double c = __fma_rn(fd, rr.x, __dmul_rn(fd, rr.y));
+      const double v = lerp_rn(F, b, c);
+      F = ((wrow >> s) & 1u) ? v : 0.0;
+      stage[lane * kStagePitch + s] = to_out<OutT>(F);
+      if (lane == wj - 1) wnew[s] = F;
+    }
+    __syncwarp();
+    if (lane == 31) colE[0] = Bv;
+    rowE[lane] = wnew[lane];
+    if (lane < wj) colE[1 + lane] = F;
+  } else {
+    // occupancy of column il, bit b <-> local row j0 + b
+    uint32_t wcol = 0;
+    if (colc) {
+      if (sumfree) {
+        wcol = rmask;
+      } else {
+        const int q0 = g.psy + j0;
+        const uint32_t *cp = colpl + (size_t)(sx + g.dirx * il) * p.pl.wy + (q0 >> 5);
+        wcol = __funnelshift_r(__ldg(cp), __ldg(cp + 1), q0 & 31) & rmask;
+      }
+    }
+    if (J > I) {
+      // ---- row-octant tile: lanes along i, steps along j (wj == 32) --------------------
+      double F = Bv;
+      const int ns = rlast + 1;
+      OutT *q = ptr;
+#pragma unroll 4
+      for (int s = 0; s < ns; ++s, q += rs) {
+        const double2 rr = __ldg(p.rtab + j0 + s);
+        const double up = __shfl_up_sync(kAll, F, 1);
+        const double b = lane ? up : colE[s];
+        const double c = __fma_rn(fd, rr.x, __dmul_rn(fd, rr.y));
+        const double v = lerp_rn(F, b, c);
+        F = ((wcol >> s) & 1u) ? v : 0.0;
+        if (lane_st) __stcs(q, to_out<OutT>(F)); // r0 == 0 here (J > 0)
+        if (lane == wi - 1) wnew[s] = F;
+      }
+      __syncwarp();
+      if (lane == wi - 1) colE[0] = Bv;
+      if (lane < wi) rowE[lane] = F;
+      colE[1 + lane] = wnew[lane];
+      return;
+    }
+    // ---- diagonal tile: both fronts and the diagonal cell (wi == wj) ---------------------
+    double C = 0.0, R = 0.0; // C[l] = q(k-1, j0+l), R[l] = q(i0+l, k-1); set when lane l joins
+    const int ns = min(wi, max(g.Ex, g.Ey) - i0 + 1);
+#pragma unroll 2
+    for (int k = 0; k < ns; ++k) {
+      const double2 rr = __ldg(p.rtab + i0 + k);
+      const double c = __fma_rn(fd, rr.x, __dmul_rn(fd, rr.y));
+      const double upC = __shfl_up_sync(kAll, C, 1);
+      const double upR = __shfl_up_sync(kAll, R, 1);
+      const double bC = lane ? upC : wscr[k];
+      const double bR = lane ? upR : colE[k];
+      const double vC = lerp_rn(C, bC, c), vR = lerp_rn(R, bR, c);
+      if (lane < k) {
+        C = ((wrow >> k) & 1u) ? vC : 0.0;
+        R = ((wcol >> k) & 1u) ? vR : 0.0;
+        stage[lane * kStagePitch + k] = to_out<OutT>(C);
+        stage[k * kStagePitch + lane] = to_out<OutT>(R);
+      }
+      // diagonal cell q(k,k) = q(k,k-1) * occ: q(k,k-1) is lane k-1's new C (k == 0: B[0])
+      const double dsrc = __shfl_up_sync(kAll, C, 1);
+      if (lane == k) {
+        const double dv = ((wrow >> k) & 1u) ? (k ? dsrc : Bv) : 0.0;
+        C = dv;
+        R = dv;
+        stage[k * kStagePitch + k] = to_out<OutT>(dv);
+      }
+    }
+    __syncwarp();
+    if (lane == wi - 1) colE[0] = Bv;
+    if (lane < wi) {
+      rowE[lane] = R;
+      colE[1 + lane] = C;
+    }
+  }
+  // ---- write the staged tile as rows ---------------------------------------------------
+  __syncwarp();
+  if (lane_st) {
+    OutT *q = ptr + r0 * rs;
+#pragma unroll 4
+    for (int r = r0; r <= rlast; ++r, q += rs) __stcs(q, stage[r * kStagePitch + lane]);
+  }
+  __syncwarp();
+}
+
+// One complete sweep from (sx, sy) by the whole CTA (kTileWarps warps, all threads
+// must call).  Writes every cell of out[ny][nx] exactly once (cells on the never-
+// written border get 0).  smem_raw: tile_smem_bytes<OutT>(nx, ny) bytes, 16-aligned.
+// Ends with a block barrier.
+template <typename OutT>
+__device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map, const int sx,
+                                               const int sy, OutT *__restrict__ out,
+                                               unsigned char *smem_raw) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nx = p.nx, ny = p.ny;
+  TQuad *quads = reinterpret_cast<TQuad *>(smem_raw);
+  uint32_t *bsum = reinterpret_cast<uint32_t *>(smem_raw + 256);
+  const int nsum = tile_sum_words(nx) * ((ny + 31) >> 5);
+  double *edges = reinterpret_cast<double *>(smem_raw + 256 + tile_sum_bytes(nx, ny));
+  const int nedge = tile_edge_doubles(nx, ny);
+  unsigned char *wbase = reinterpret_cast<unsigned char *>(edges + nedge);
+  double *wscr = reinterpret_cast<double *>(wbase) + warp * kWarpScratch;
+  OutT *stage = reinterpret_cast<OutT *>(wbase + kTileWarps * kWarpScratch * sizeof(double)) +
+                warp * (kTile * kStagePitch);
+
+  if (tid == 0) {
+    const int WXb = 32 * ((nx + 31) >> 5), WYb = 32 * ((ny + 31) >> 5);
+    int off = 0;
+    for (int q = 0; q < 4; ++q) { // Q1 (+,+), Q2 (-,+), Q3 (-,-), Q4 (+,-): reference order
+      TQuad g;
+      g.dirx = (q == 0 || q == 3) ? 1 : -1;
+      g.diry = (q < 2) ? 1 : -1;
+      g.Ex = g.dirx > 0 ? nx - 1 - sx : sx;
+      g.Ey = g.diry > 0 ? ny - 1 - sy : sy;
+      // first tile width: the next tile column starts (+x) / ends (-x) on a multiple of 32
+      g.a = g.dirx > 0 ? 32 - (sx & 31) : ((sx + 1) & 31);
+      if (g.a == 0) g.a = 32;
+      const bool exists = (g.dirx > 0 || sx > 0) && (g.diry > 0 || sy > 0);
+      g.TX = !exists ? 0 : (g.Ex < g.a ? 1 : (g.Ex - g.a) / kTile + 2);
+      g.TY = !exists ? 0 : (g.Ey < g.a ? 1 : (g.Ey - g.a) / kTile + 2);
+      g.rowOff = off;
+      off += g.TX * kTile;
+      g.colOff = off;
+      off += g.TY * 33;
+      g.psx = g.dirx > 0 ? sx : WXb - 1 - sx;
+      g.psy = g.diry > 0 ? sy : WYb - 1 - sy;
+      g.pad0 = 0;
+      quads[q] = g;
+    }
+  }
+  for (int i = tid; i < nsum; i += blockDim.x) bsum[i] = __ldg(p.pl.bsum + (size_t)map * nsum + i);
+  for (int i = tid; i < nedge; i += blockDim.x) edges[i] = 1.0; // virtual boundary
+  __syncthreads();
+
+  int Dmax = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (quads[q].TX) Dmax = max(Dmax, quads[q].TX + quads[q].TY - 2);
+
+  for (int d = 0; d <= Dmax; ++d) {
+    int base = 0;
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+      const TQuad &g = quads[q];
+      if (g.TX == 0) continue;
+      const int lo = max(0, d - (g.TY - 1)), hi = min(d, g.TX - 1);
+      const int n = hi - lo + 1;
+      if (n <= 0) continue;
+      const uint32_t *rowpl = (g.dirx > 0 ? p.pl.rowF : p.pl.rowR) + (size_t)map * p.pl.row_plane;
+      const uint32_t *colpl = (g.diry > 0 ? p.pl.colF : p.pl.colR) + (size_t)map * p.pl.col_plane;
+#pragma unroll 1
+      for (int t = (warp - base) & (kTileWarps - 1); t < n; t += kTileWarps)
+        process_tile<OutT>(p, g, rowpl, colpl, bsum, sx, sy, lo + t, d - lo - t, out, edges, stage,
+                           wscr, lane);
+      base += n;
+    }
+    __syncthreads();
+  }
+}
+
+} // namespace
+#endif

@@ -31,6 +31,16 @@ struct VhpOctPlanes {
   size_t row_plane = 0, col_plane = 0; // words per map
 };
 
+// Bit planes of the tile sweep kernel (built by vhp_launch_pack_tile): row / column
+// major, forward / mirrored, wx (wy) words per row (column) line including one zero
+// word of padding (see kernels_sweep_tile.cu).
+struct VhpTilePlanes {
+  const uint32_t *rowF = nullptr, *rowR = nullptr, *colF = nullptr, *colR = nullptr;
+  const uint32_t *bsum = nullptr;      // [map][block row][words]: 1 = aligned 32x32 block is free
+  int wx = 0, wy = 0;
+  size_t row_plane = 0, col_plane = 0; // words per map
+};
+
 // grow-only device buffer
 struct VhpDevBuf {
   void *p = nullptr;
@@ -69,10 +79,17 @@ struct vhp_context {
   uint32_t *oct_buf = nullptr;
   size_t oct_bytes = 0;
   VhpOctPlanes oct;
+  // tile-kernel bit planes (cached like `packed`)
+  const uint8_t *tile_src = nullptr;
+  int tile_nmaps = 0, tile_nx = 0, tile_ny = 0;
+  uint32_t *tile_buf = nullptr;
+  size_t tile_bytes = 0;
+  VhpTilePlanes tile;
   // which K1 implementation vhp_visibility_batch* uses (env VHP_SWEEP_IMPL):
   // 0 = auto (octant kernel where it fits), 1 = naive reference kernel, 2 = front
   // kernel (every thread serves all four fronts), 3 = ring kernel (one front per
-  // warp, block barrier per ring), 4 = octant kernel (one octant per warp, no barriers)
+  // warp, block barrier per ring), 4 = octant kernel (one octant per warp, no barriers),
+  // 5 = tile wavefront kernel (the default where it fits)
   int sweep_impl = 0;
 };
 
@@ -131,6 +148,17 @@ cudaError_t vhp_launch_sweep_octant(const VhpOctPlanes &pl, const uint8_t *d_occ
                                     int64_t npairs, vhp_dtype dtype, void *d_out,
                                     const double *d_rcp2, int *d_err, cudaStream_t st,
                                     int64_t *launches);
+
+// K1, tile wavefront (32 x 32 tiles, uniform tiles are plain fills): the default.
+bool vhp_sweep_tile_supported(int nx, int ny);
+void vhp_tile_plane_geometry(int nx, int ny, int *wx, int *wy, int *sum_words_per_map);
+cudaError_t vhp_launch_pack_tile(const uint8_t *d_occ, int nmaps, int nx, int ny, uint32_t *rowF,
+                                 uint32_t *rowR, uint32_t *colF, uint32_t *colR, uint32_t *bsum,
+                                 cudaStream_t st, int64_t *launches);
+cudaError_t vhp_launch_sweep_tile(const VhpTilePlanes &pl, int nx, int ny, const int32_t *d_src_xy,
+                                  const int32_t *d_src_map, int64_t npairs, vhp_dtype dtype,
+                                  void *d_out, const double *d_rcp2, int *d_err, cudaStream_t st,
+                                  int64_t *launches);
 
 // K4 ray casting
 cudaError_t vhp_launch_raycast(const uint8_t *d_occ, int nx, int ny,
