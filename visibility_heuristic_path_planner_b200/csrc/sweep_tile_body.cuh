@@ -37,6 +37,13 @@
 // c = d/k is fma(d, rh, d*rl) with (rh, rl) a double-double 1/k (correctly rounded for
 // 0 <= d < k <= 16384, verified exhaustively by vhp_selftest_ratio).
 //
+// Lit staircase.  With the virtual boundary at 1.0, tile (I, J) is 1.0 everywhere iff
+// every tile of the rectangle [0..I] x [0..J] is free, so the provably lit region of a
+// quadrant is a staircase: Lm(J) = min over J' <= J of the number of leading free tiles
+// of tile row J'.  Before the wavefront starts, the CTA writes that region as long
+// contiguous row spans (the -x and +x quadrants of a grid row merge into one span) and
+// the wavefront skips those tiles; on an empty map the whole sweep is this pass.
+//
 // Whether a tile is free is first asked of a per-map summary (one bit per aligned
 // 32 x 32 block, copied to shared memory): a tile inside free blocks needs no global
 // load at all.  Otherwise occupancy comes from four bit planes per map (row / column
@@ -93,9 +100,13 @@ __host__ __device__ inline int tile_sum_bytes(int nx, int ny) {
   return (4 * tile_sum_words(nx) * ((ny + 31) >> 5) + 15) & ~15;
 }
 
+// lit staircase: Lm[q][J], tile_lm_cap(ny) entries per quadrant
+__host__ __device__ inline int tile_lm_cap(int ny) { return (ny - 1) / kTile + 4; }
+
 template <typename OutT>
 __host__ __device__ inline size_t tile_smem_bytes(int nx, int ny) {
-  return 256 + tile_sum_bytes(nx, ny) + sizeof(double) * (size_t)tile_edge_doubles(nx, ny) +
+  return 256 + tile_sum_bytes(nx, ny) + 16 * (size_t)tile_lm_cap(ny) +
+         sizeof(double) * (size_t)tile_edge_doubles(nx, ny) +
          (size_t)kTileWarps * (kTile * kStagePitch * sizeof(OutT) + kWarpScratch * sizeof(double));
 }
 
@@ -105,6 +116,49 @@ __device__ __forceinline__ void stg16_fill(float *q, float v) {
 }
 __device__ __forceinline__ void stg16_fill(double *q, double v) {
   __stcs(reinterpret_cast<double2 *>(q), make_double2(v, v));
+}
+
+// first local index and extent of tile column / row T
+__device__ __forceinline__ int tile_start(const int a, const int T) {
+  return T ? a + kTile * (T - 1) : 0;
+}
+
+// Does the block summary prove every cell tile (I, J) has to compute is free?  (A tile
+// with nothing to compute -- only border cells -- counts as free.)
+__device__ __forceinline__ bool tile_sum_free(const TQuad &g, const uint32_t *bsum, const int nbw,
+                                              const int sx, const int sy, const int I,
+                                              const int J) {
+  const int i0 = tile_start(g.a, I), j0 = tile_start(g.a, J);
+  const int nvx = min(I ? kTile : g.a, g.Ex - (g.dirx < 0) - i0 + 1);
+  const int nvy = min(J ? kTile : g.a, g.Ey - (g.diry < 0) - j0 + 1);
+  if (nvx <= 0 || nvy <= 0) return true;
+  const int xa = sx + g.dirx * i0, xb = sx + g.dirx * (i0 + nvx - 1);
+  const int ya = sy + g.diry * j0, yb = sy + g.diry * (j0 + nvy - 1);
+  const int bx0 = min(xa, xb) >> 5, bx1 = max(xa, xb) >> 5;
+  const int by0 = min(ya, yb) >> 5, by1 = max(ya, yb) >> 5;
+  const uint32_t *s0 = bsum + by0 * nbw, *s1 = bsum + by1 * nbw;
+  return ((s0[bx0 >> 5] >> (bx0 & 31)) & (s0[bx1 >> 5] >> (bx1 & 31)) &
+          (s1[bx0 >> 5] >> (bx0 & 31)) & (s1[bx1 >> 5] >> (bx1 & 31)) & 1u) != 0u;
+}
+
+// row[xa..xb] = v by one warp (128-bit stores where the row is 16-byte aligned)
+template <typename OutT>
+__device__ __forceinline__ void fill_span(OutT *__restrict__ row, const int xa, const int xb,
+                                          const OutT v, const int lane, const bool vec) {
+  if (vec) {
+    constexpr int EPL = 16 / (int)sizeof(OutT);
+    for (int x = (xa & ~(EPL - 1)) + EPL * lane; x <= xb; x += 32 * EPL) {
+      if (x >= xa && x + EPL - 1 <= xb) {
+        stg16_fill(row + x, v);
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e)
+          if (x + e >= xa && x + e <= xb) __stcs(row + x + e, v);
+      }
+    }
+  } else {
+    for (int x = xa + lane; x <= xb; x += 32) __stcs(row + x, v);
+  }
 }
 
 // One tile (I, J) of quadrant g by one warp.
@@ -118,7 +172,7 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
                                              OutT *stage, double *wscr, const int lane) {
   const int nx = p.nx;
   const int wi = I ? kTile : g.a, wj = J ? kTile : g.a;          // tile extent
-  const int i0 = I ? g.a + kTile * (I - 1) : 0, j0 = J ? g.a + kTile * (J - 1) : 0;
+  const int i0 = tile_start(g.a, I), j0 = tile_start(g.a, J);
   const int il = i0 + lane, jr = j0 + lane;
   // the never-written border column / row is "occupied": exclude it from the compute extent
   const int ExC = g.Ex - (g.dirx < 0), EyC = g.Ey - (g.diry < 0);
@@ -133,14 +187,7 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
   bool allfree = false, allocc = true, sumfree = false;
   uint32_t wrow = 0;
   if (nvx > 0 && nvy > 0) {
-    const int xa = sx + g.dirx * i0, xb = sx + g.dirx * (i0 + nvx - 1);
-    const int ya = sy + g.diry * j0, yb = sy + g.diry * (j0 + nvy - 1);
-    const int bx0 = min(xa, xb) >> 5, bx1 = max(xa, xb) >> 5;
-    const int by0 = min(ya, yb) >> 5, by1 = max(ya, yb) >> 5;
-    const int nbw = tile_sum_words(nx);
-    const uint32_t *s0 = bsum + by0 * nbw, *s1 = bsum + by1 * nbw;
-    sumfree = ((s0[bx0 >> 5] >> (bx0 & 31)) & (s0[bx1 >> 5] >> (bx1 & 31)) &
-               (s1[bx0 >> 5] >> (bx0 & 31)) & (s1[bx1 >> 5] >> (bx1 & 31)) & 1u) != 0u;
+    sumfree = tile_sum_free(g, bsum, tile_sum_words(nx), sx, sy, I, J);
     if (sumfree) {
       wrow = rowc ? cmask : 0u;
       allfree = true;
@@ -313,7 +360,9 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
   TQuad *quads = reinterpret_cast<TQuad *>(smem_raw);
   uint32_t *bsum = reinterpret_cast<uint32_t *>(smem_raw + 256);
   const int nsum = tile_sum_words(nx) * ((ny + 31) >> 5);
-  double *edges = reinterpret_cast<double *>(smem_raw + 256 + tile_sum_bytes(nx, ny));
+  const int lmcap = tile_lm_cap(ny);
+  int *Lm = reinterpret_cast<int *>(smem_raw + 256 + tile_sum_bytes(nx, ny));
+  double *edges = reinterpret_cast<double *>(smem_raw + 256 + tile_sum_bytes(nx, ny) + 16 * lmcap);
   const int nedge = tile_edge_doubles(nx, ny);
   unsigned char *wbase = reinterpret_cast<unsigned char *>(edges + nedge);
   double *wscr = reinterpret_cast<double *>(wbase) + warp * kWarpScratch;
@@ -349,12 +398,73 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
   for (int i = tid; i < nedge; i += blockDim.x) edges[i] = 1.0; // virtual boundary
   __syncthreads();
 
-  int Dmax = 0;
+  // ---- lit staircase: leading free tiles per tile row, then the running minimum ---------
+  const int nbw = tile_sum_words(nx);
+  for (int q = 0; q < 4; ++q) {
+    const TQuad &g = quads[q];
+    for (int J = warp; J < g.TY; J += kTileWarps) {
+      int L = 0;
+      for (int Ib = 0; Ib < g.TX; Ib += 32) {
+        const bool fr = Ib + lane < g.TX && tile_sum_free(g, bsum, nbw, sx, sy, Ib + lane, J);
+        const unsigned m = __ballot_sync(kAll, fr);
+        const int run = __ffs(~m) - 1; // leading ones (-1: all 32)
+        L += run < 0 ? 32 : run;
+        if (run >= 0) break;
+      }
+      if (lane == 0) Lm[q * lmcap + J] = L;
+    }
+  }
+  __syncthreads();
+  int *dfirst = reinterpret_cast<int *>(smem_raw + 240); // first wave with a tile outside the staircase
+  if (tid < 4) {
+    const TQuad &g = quads[tid];
+    int m = g.TX, dq = 0x3fffffff;
+    for (int J = 0; J < g.TY; ++J) {
+      m = min(m, Lm[tid * lmcap + J]);
+      Lm[tid * lmcap + J] = m;
+      if (m < g.TX) dq = min(dq, m + J);
+    }
+    dfirst[tid] = dq;
+  }
+  __syncthreads();
+
+  // ---- write the lit region: one warp per grid row, -x and +x runs merged -----------------
+  for (int y = warp; y < ny; y += kTileWarps) {
+    const bool upper = y >= sy;
+    const int j = upper ? y - sy : sy - y;
+    int nR = 0, nL = 0; // lit cells i = 0 .. n-1 of the +x / -x quadrant in this row
+    {
+      const TQuad &g = quads[upper ? 0 : 3];
+      if (g.TX) nR = min(tile_start(g.a, Lm[(upper ? 0 : 3) * lmcap + (j < g.a ? 0 : (j - g.a) / kTile + 1)]), g.Ex + 1);
+    }
+    {
+      const TQuad &g = quads[upper ? 1 : 2];
+      if (g.TX) nL = min(tile_start(g.a, Lm[(upper ? 1 : 2) * lmcap + (j < g.a ? 0 : (j - g.a) / kTile + 1)]), g.Ex + 1);
+    }
+    OutT *row = out + (size_t)y * nx;
+    const OutT v = (!upper && y == 0) ? (OutT)0 : (OutT)1; // y == 0 below the source: never written
+    int xa = sx - (nL - 1), xb = sx + nR - 1;
+    if (nL > 0 && xa == 0) { // x == 0 left of the source: never written
+      if (lane == 0) __stcs(row, (OutT)0);
+      xa = 1;
+    }
+    if (nR > 0 && nL > 1) {
+      fill_span<OutT>(row, xa, xb, v, lane, p.vec);
+    } else {
+      if (nL > 1) fill_span<OutT>(row, xa, sx - 1, v, lane, p.vec);
+      if (nR > 0) fill_span<OutT>(row, sx, xb, v, lane, p.vec);
+    }
+  }
+
+  int Dmax = 0, Dmin = 0x3fffffff;
 #pragma unroll
   for (int q = 0; q < 4; ++q)
-    if (quads[q].TX) Dmax = max(Dmax, quads[q].TX + quads[q].TY - 2);
+    if (quads[q].TX) {
+      Dmax = max(Dmax, quads[q].TX + quads[q].TY - 2);
+      Dmin = min(Dmin, dfirst[q]);
+    }
 
-  for (int d = 0; d <= Dmax; ++d) {
+  for (int d = Dmin; d <= Dmax; ++d) {
     int base = 0;
 #pragma unroll 1
     for (int q = 0; q < 4; ++q) {
@@ -367,8 +477,9 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
       const uint32_t *colpl = (g.diry > 0 ? p.pl.colF : p.pl.colR) + (size_t)map * p.pl.col_plane;
 #pragma unroll 1
       for (int t = (warp - base) & (kTileWarps - 1); t < n; t += kTileWarps)
-        process_tile<OutT>(p, g, rowpl, colpl, bsum, sx, sy, lo + t, d - lo - t, out, edges, stage,
-                           wscr, lane);
+        if (lo + t >= Lm[q * lmcap + d - lo - t]) // not inside the lit staircase
+          process_tile<OutT>(p, g, rowpl, colpl, bsum, sx, sy, lo + t, d - lo - t, out, edges,
+                             stage, wscr, lane);
       base += n;
     }
     __syncthreads();
