@@ -209,6 +209,72 @@ def cpu_baseline(maps, src, nx, ny):
             "sample": f"oracle/vhp_oracle.c (-O2 -ffp-contract=off), {n1} sources, 1 thread"}
 
 
+def planner_workload(rank):
+    """Batched planner problems: 16 random 256x256 obstacle maps x 64 (start, end) pairs."""
+    nx = ny = 256
+    nmaps, per = 16, 64
+    g = np.random.default_rng(777 + rank)
+    maps = np.ones((nmaps, ny, nx), dtype=np.uint8)
+    for m in range(nmaps):
+        for _ in range(12):
+            x, y = int(g.integers(1, nx)), int(g.integers(1, ny))
+            w, h = int(g.integers(8, 41)), int(g.integers(8, 41))
+            maps[m, y:y + h, x:x + w] = 0
+    se = np.zeros((nmaps * per, 4), dtype=np.int32)
+    pmap = np.repeat(np.arange(nmaps, dtype=np.int32), per)
+    for m in range(nmaps):
+        free = np.argwhere(maps[m] != 0)
+        a = free[g.integers(0, len(free), per)]
+        b = free[g.integers(0, len(free), per)]
+        se[m * per:(m + 1) * per] = np.stack([a[:, 1], a[:, 0], b[:, 1], b[:, 0]], axis=1)
+    return maps, se, pmap
+
+
+def planner_leg(vhp, local_rank, rank, world, dist, dev, with_cpu):
+    """Secondary metric of BASELINE.json: planner solves/s (solve() + reconstructPath() per
+    problem, whole loop on the device), through the host-buffer C-ABI call."""
+    import torch
+    maps, se, pmap = planner_workload(rank)
+    thr, max_iter = 0.5, 100
+    ctx = vhp.Context(local_rank)
+    ctx.planner_batch(maps, se, prob_map=pmap, threshold=thr, max_iter=max_iter, fields=False)  # warm-up
+    torch.cuda.synchronize()
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r = ctx.planner_batch(maps, se, prob_map=pmap, threshold=thr, max_iter=max_iter, fields=False)
+    torch.cuda.synchronize()
+    t = (time.perf_counter() - t0) / reps
+    ctx.close()
+    if world > 1:
+        tt = torch.tensor([t], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt.item())
+    out = {"metric": "planner solves/s", "value": world * len(se) / t, "unit": "solves/s",
+           "problems_per_gpu": len(se), "ms_per_batch": t * 1e3,
+           "workload": "16 random 256x256 maps (12 rectangles 8-40) x 64 (start,end) pairs per GPU, "
+                       "threshold 0.5, max_iter 100; host-buffer vhp_planner_batch, small outputs only",
+           "solved": int((r["status"] == 0).sum()), "max_iter_hit": int((r["status"] == 5).sum()),
+           "mean_sources": float(r["nb_sources"].mean()), "sweeps": int(r["nb_sources"].sum())}
+    if with_cpu and rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        from oracle_py import Ref
+        if Ref.available("fast"):
+            ref = Ref("fast")
+            cores = os.cpu_count() or 1
+            nm = 4  # bounded sample: 4 of the 16 maps
+            secs = 0.0
+            for m in range(nm):
+                sel = se[pmap == m]
+                secs += ref.time_solve(maps[m].astype(np.float64), sel, thr, max_iter, nthreads=cores)[0]
+            n_cpu = int((pmap < nm).sum())
+            out["cpu_reference"] = {"value": n_cpu / secs, "unit": "solves/s", "cores": cores,
+                                    "kind": "reference",
+                                    "sample": f"reference solve() ({ref.flags()}), {n_cpu} problems of the "
+                                              f"same batch on {cores} threads"}
+    return out
+
+
 # ----------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -221,6 +287,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=0, help="override pairs per GPU (profiling only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-planner", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -343,6 +410,11 @@ def main():
         host_ctx.close()
         del out_h
 
+    planner = None
+    if not args.no_planner:
+        planner = planner_leg(vhp, local_rank, rank, world, dist if world > 1 else None, dev,
+                              not args.no_cpu and world == 1)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -371,7 +443,7 @@ def main():
                        "pairs_per_gpu": n, "store": args.store, "parallelism": f"batch-shard x{world}, no collective",
                        "l2": "outputs (%.1f GB per step) exceed the 126 MB L2; the shared map is L2-resident by design" % (n * nx * ny * esz / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": int(launches)}
+            "gpu_launches": int(launches), "planner": planner}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

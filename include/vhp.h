@@ -88,9 +88,10 @@ const char *vhp_last_error(const vhp_context *ctx); /* ctx may be NULL: global *
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t vhp_launch_count(const vhp_context *ctx);
 
-/* diagnostic: the sweep kernels compute c = i/k as RN(1/k) plus one correction
- * step instead of an IEEE divide; this counts the (i,k), 0 <= i < k <= kmax, for
- * which the two differ on this device (must be 0; kmax <= 16384). */
+/* diagnostic: the sweep kernel computes c = i/k as fma(i, rh, i*rl) with (rh, rl) a
+ * double-double 1/k instead of an IEEE divide; this counts the (i,k),
+ * 0 <= i < k <= kmax, for which the two differ on this device (must be 0;
+ * kmax <= 16384). */
 vhp_status vhp_selftest_ratio(vhp_context *ctx, int kmax, int64_t *mismatches);
 
 /* ---- a1: batched stand-alone visibility sweep (computeVisibility) ------------
@@ -111,8 +112,8 @@ vhp_status vhp_visibility_batch_dev(vhp_context *ctx, const uint8_t *d_occ,
                                     const int32_t *d_src_map, int64_t npairs,
                                     vhp_dtype dtype, void *d_out);
 /* Optional, for repeated _dev calls on the same maps: packs the maps into the
- * bit-plane layout the sweep kernel reads (row-major and column-major bit maps)
- * once, so later vhp_visibility_batch_dev calls with the same d_occ pointer,
+ * bit-plane layout the sweep kernel reads (row- and column-major bit maps, forward
+ * and mirrored, plus a free-block summary) once, so later vhp_visibility_batch_dev calls with the same d_occ pointer,
  * nmaps, nx, ny skip the packing pass.  Invalidate by calling it again. */
 vhp_status vhp_prepare_maps_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps,
                                 int nx, int ny);

@@ -43,20 +43,6 @@ vhp_status ensure(vhp_context *ctx, VhpDevBuf &b, size_t bytes) {
   return VHP_OK;
 }
 
-vhp_status ensure_rcp(vhp_context *ctx, int len) {
-  if (len <= ctx->rcp_len) return VHP_OK;
-  len = std::max(len, 4096 + 8);
-  if (ctx->rcp_table) {
-    VHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    VHP_CUDA(ctx, cudaFree(ctx->rcp_table));
-    ctx->rcp_table = nullptr;
-  }
-  VHP_CUDA(ctx, cudaMalloc(&ctx->rcp_table, (size_t)len * 2 * sizeof(double)));
-  VHP_CUDA(ctx, vhp_launch_rcp_table(ctx->rcp_table, len, ctx->stream, &ctx->launches));
-  ctx->rcp_len = len;
-  return VHP_OK;
-}
-
 vhp_status ensure_rcp2(vhp_context *ctx, int len) {
   if (len <= ctx->rcp2_len) return VHP_OK;
   len = std::max(len, 4096 + 8);
@@ -71,39 +57,10 @@ vhp_status ensure_rcp2(vhp_context *ctx, int len) {
   return VHP_OK;
 }
 
-// bit planes of the octant kernel, cached like pack_maps (same sticky flag)
-vhp_status pack_oct(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx, int ny,
-                    bool force) {
-  if (!force && ctx->packed_sticky && ctx->oct_src == d_occ && ctx->oct_nmaps == nmaps &&
-      ctx->oct_nx == nx && ctx->oct_ny == ny)
-    return VHP_OK;
-  const int wp = vhp_oct_words_per_line(nx, ny);
-  const size_t row_plane = (size_t)ny * wp, col_plane = (size_t)nx * wp;
-  const size_t bytes = (size_t)nmaps * 2 * (row_plane + col_plane) * sizeof(uint32_t);
-  if (bytes > ctx->oct_bytes) {
-    if (ctx->oct_buf) {
-      VHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      VHP_CUDA(ctx, cudaFree(ctx->oct_buf));
-      ctx->oct_buf = nullptr;
-    }
-    VHP_CUDA(ctx, cudaMalloc(&ctx->oct_buf, bytes));
-    ctx->oct_bytes = bytes;
-  }
-  uint32_t *row_f = ctx->oct_buf, *row_r = row_f + (size_t)nmaps * row_plane;
-  uint32_t *col_f = row_r + (size_t)nmaps * row_plane, *col_r = col_f + (size_t)nmaps * col_plane;
-  VHP_CUDA(ctx, vhp_launch_pack_oct(d_occ, nmaps, nx, ny, row_f, row_r, col_f, col_r, ctx->stream,
-                                    &ctx->launches));
-  ctx->oct.row_f = row_f; ctx->oct.row_r = row_r;
-  ctx->oct.col_f = col_f; ctx->oct.col_r = col_r;
-  ctx->oct.row_plane = row_plane; ctx->oct.col_plane = col_plane;
-  ctx->oct_src = d_occ; ctx->oct_nmaps = nmaps; ctx->oct_nx = nx; ctx->oct_ny = ny;
-  return VHP_OK;
-}
-
-// bit planes of the tile kernel, cached like pack_maps (same sticky flag)
+// (re)build the bit planes of the tile kernel for d_occ unless they are cached for this pointer
 vhp_status pack_tile(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx, int ny,
                      bool force) {
-  if (!force && ctx->packed_sticky && ctx->tile_src == d_occ && ctx->tile_nmaps == nmaps &&
+  if (!force && ctx->planes_sticky && ctx->tile_src == d_occ && ctx->tile_nmaps == nmaps &&
       ctx->tile_nx == nx && ctx->tile_ny == ny)
     return VHP_OK;
   int wx, wy, nsum;
@@ -130,42 +87,6 @@ vhp_status pack_tile(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx, 
   ctx->tile.wx = wx; ctx->tile.wy = wy;
   ctx->tile.row_plane = row_plane; ctx->tile.col_plane = col_plane;
   ctx->tile_src = d_occ; ctx->tile_nmaps = nmaps; ctx->tile_nx = nx; ctx->tile_ny = ny;
-  return VHP_OK;
-}
-
-// (re)build the bit planes for d_occ unless they are cached for this pointer
-vhp_status pack_maps(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx, int ny,
-                     bool force) {
-  if (!force && ctx->packed_sticky && ctx->packed_src == d_occ &&
-      ctx->packed_nmaps == nmaps && ctx->packed_nx == nx && ctx->packed_ny == ny)
-    return VHP_OK;
-  ctx->packed_sticky = false;
-  const int wpr = vhp_words_padded(nx), wpc = vhp_words_padded(ny);
-  const size_t row_plane = (size_t)ny * wpr, col_plane = (size_t)nx * wpc;
-  const size_t bytes = (size_t)nmaps * (row_plane + col_plane) * sizeof(uint32_t);
-  if (bytes > ctx->packed_bytes) {
-    if (ctx->packed_buf) {
-      VHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      VHP_CUDA(ctx, cudaFree(ctx->packed_buf));
-      ctx->packed_buf = nullptr;
-    }
-    VHP_CUDA(ctx, cudaMalloc(&ctx->packed_buf, bytes));
-    ctx->packed_bytes = bytes;
-  }
-  uint32_t *rowbits = ctx->packed_buf;
-  uint32_t *colbits = ctx->packed_buf + (size_t)nmaps * row_plane;
-  VHP_CUDA(ctx, vhp_launch_pack_maps(d_occ, nmaps, nx, ny, rowbits, colbits, wpr, wpc,
-                                     ctx->stream, &ctx->launches));
-  ctx->packed.rowbits = rowbits;
-  ctx->packed.colbits = colbits;
-  ctx->packed.wpr = wpr;
-  ctx->packed.wpc = wpc;
-  ctx->packed.row_plane = row_plane;
-  ctx->packed.col_plane = col_plane;
-  ctx->packed_src = d_occ;
-  ctx->packed_nmaps = nmaps;
-  ctx->packed_nx = nx;
-  ctx->packed_ny = ny;
   return VHP_OK;
 }
 
@@ -221,44 +142,15 @@ vhp_status run_dev(vhp_context *ctx, Op op, const uint8_t *d_occ, int nmaps, int
     return VHP_OK;
   }
   const size_t esz = dtype == VHP_F32 ? 4 : 8;
-  const bool aligned = ((uintptr_t)d_out % 16) == 0 && ((size_t)nx * ny * esz) % 16 == 0;
-  const int n_max = std::max(nx, ny);
-  const bool front_fits = vhp_sweep_front_supported(nx, ny);
-  const bool ring_fits = vhp_sweep_ring_supported(nx, ny);
-  const bool oct_fits = vhp_sweep_octant_supported(nx, ny);
-  if ((ctx->sweep_impl == 0 || ctx->sweep_impl == 5) && vhp_sweep_tile_supported(nx, ny)) {
-    vhp_status st = ensure_rcp2(ctx, n_max + 8);
+  if (ctx->sweep_impl == 0 && vhp_sweep_tile_supported(nx, ny)) {
+    vhp_status st = ensure_rcp2(ctx, std::max(nx, ny) + 8);
     if (st != VHP_OK) return st;
     if ((st = pack_tile(ctx, d_occ, nmaps, nx, ny, false)) != VHP_OK) return st;
     VHP_CUDA(ctx, vhp_launch_sweep_tile(ctx->tile, nx, ny, d_xy, d_map, n, dtype, d_out,
                                         ctx->rcp2_table, ctx->d_err, ctx->stream, &ctx->launches));
     return VHP_OK;
   }
-  if (ctx->sweep_impl == 4 && oct_fits && aligned) {
-    vhp_status st = ensure_rcp2(ctx, n_max + 8);
-    if (st != VHP_OK) return st;
-    if ((st = pack_oct(ctx, d_occ, nmaps, nx, ny, false)) != VHP_OK) return st;
-    VHP_CUDA(ctx, vhp_launch_sweep_octant(ctx->oct, d_occ, nx, ny, d_xy, d_map, n, dtype, d_out,
-                                          ctx->rcp2_table, ctx->d_err, ctx->stream,
-                                          &ctx->launches));
-    return VHP_OK;
-  }
-  if (ctx->sweep_impl != 1 && (front_fits || ring_fits) && aligned) {
-    vhp_status st = ensure_rcp(ctx, n_max + 8);
-    if (st != VHP_OK) return st;
-    st = pack_maps(ctx, d_occ, nmaps, nx, ny, false);
-    if (st != VHP_OK) return st;
-    if (ring_fits && (ctx->sweep_impl == 3 || (ctx->sweep_impl == 0 && !front_fits)))
-      VHP_CUDA(ctx, vhp_launch_sweep_ring(ctx->packed, nx, ny, d_xy, d_map, n, dtype, d_out,
-                                          ctx->rcp_table, ctx->d_err, ctx->stream,
-                                          &ctx->launches));
-    else
-      VHP_CUDA(ctx, vhp_launch_sweep_front(ctx->packed, nx, ny, d_xy, d_map, n, dtype, d_out,
-                                           ctx->rcp_table, ctx->d_err, ctx->stream,
-                                           &ctx->launches));
-    return VHP_OK;
-  }
-  // reference kernel: chunk so that the scratch fronts stay small
+  // naive kernel: chunk so that the scratch fronts stay small
   const int64_t chunk = 4096;
   vhp_status st = ensure(ctx, ctx->b_scratch, vhp_sweep_naive_scratch_bytes(nx, ny, std::min(n, chunk)));
   if (st != VHP_OK) return st;
@@ -295,23 +187,13 @@ vhp_status run_host(vhp_context *ctx, Op op, const uint8_t *occ, int nmaps, int 
   if (maps)
     VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_map.p, maps, (size_t)n * sizeof(int32_t),
                                   cudaMemcpyHostToDevice, ctx->stream));
-  ctx->packed_src = nullptr; // b_occ content changed
-  ctx->packed_sticky = false;
-  ctx->oct_src = nullptr;
+  ctx->planes_sticky = false; // b_occ content changed
   ctx->tile_src = nullptr;
-  if (op == Op::Sweep && ctx->sweep_impl != 1) { // pack once for all chunks
-    const bool use_tile = (ctx->sweep_impl == 0 || ctx->sweep_impl == 5) &&
-                          vhp_sweep_tile_supported(nx, ny);
-    const bool use_oct = ctx->sweep_impl == 4 &&
-                         vhp_sweep_octant_supported(nx, ny);
-    if (use_tile)
-      st = pack_tile(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, true);
-    else if (use_oct)
-      st = pack_oct(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, true);
-    else
-      st = pack_maps(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, true);
-    if (st != VHP_OK) return st;
-    ctx->packed_sticky = true;
+  if (op == Op::Sweep && ctx->sweep_impl == 0 && vhp_sweep_tile_supported(nx, ny)) {
+    // pack once for all chunks
+    if ((st = pack_tile(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, true)) != VHP_OK)
+      return st;
+    ctx->planes_sticky = true;
   }
   const size_t chunk_bytes_target = (size_t)1 << 30;
   int64_t chunk = std::max<int64_t>(1, (int64_t)(chunk_bytes_target / (cells * esz)));
@@ -349,9 +231,7 @@ vhp_status run_host(vhp_context *ctx, Op op, const uint8_t *occ, int nmaps, int 
   cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream);
   cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
   if (registered) cudaHostUnregister(out);
-  ctx->packed_sticky = false;
-  ctx->packed_src = nullptr;
-  ctx->oct_src = nullptr;
+  ctx->planes_sticky = false;
   ctx->tile_src = nullptr;
   if (result != VHP_OK) return result;
   if (e1 != cudaSuccess) return cuda_fail(ctx, e1, "sync copy stream");
@@ -370,9 +250,9 @@ vhp_status planner_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx
     return fail(ctx, VHP_ERR_UNSUPPORTED, "planner: grid too large for the single-CTA kernel");
   if (ls_cap < max_iter + 2 || max_iter < 0)
     return fail(ctx, VHP_ERR_INVALID_ARG, "planner: ls_cap must be >= max_iter + 2");
-  vhp_status st = ensure_rcp(ctx, std::max(nx, ny) + 8);
+  vhp_status st = ensure_rcp2(ctx, std::max(nx, ny) + 8);
   if (st != VHP_OK) return st;
-  if ((st = pack_maps(ctx, d_occ, nmaps, nx, ny, false)) != VHP_OK) return st;
+  if ((st = pack_tile(ctx, d_occ, nmaps, nx, ny, false)) != VHP_OK) return st;
   const size_t cells = (size_t)nx * ny;
   const bool vis_user = dtype == VHP_F64 && o.vis, vg_user = dtype == VHP_F64 && o.vg;
   const size_t per_prob = (vis_user ? 0 : 8 * cells) + (vg_user ? 0 : 8 * cells) +
@@ -402,8 +282,8 @@ vhp_status planner_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx
     int32_t *came = o.came ? o.came + q0 * cells : ws_came;
     float *vg32 = (dtype == VHP_F32 && o.vg) ? (float *)o.vg + q0 * cells : nullptr;
     float *vis32 = (dtype == VHP_F32 && o.vis) ? (float *)o.vis + q0 * cells : nullptr;
-    VHP_CUDA(ctx, vhp_launch_planner(ctx->packed, nx, ny, d_se + 4 * q0, d_pmap ? d_pmap + q0 : nullptr,
-                                     n, thr, max_iter, ls_cap, ctx->rcp_table, vis, vg, came,
+    VHP_CUDA(ctx, vhp_launch_planner(ctx->tile, nx, ny, d_se + 4 * q0, d_pmap ? d_pmap + q0 : nullptr,
+                                     n, thr, max_iter, ls_cap, ctx->rcp2_table, vis, vg, came,
                                      status + q0, nb + q0, ls + 2 * (size_t)ls_cap * q0, plen + q0,
                                      pn + q0, path + 2 * (size_t)ls_cap * q0, vg32, vis32,
                                      ctx->d_err, ctx->stream, &ctx->launches));
@@ -468,10 +348,6 @@ vhp_status vhp_context_create(int device, void *cuda_stream, vhp_context **out) 
   const char *impl = std::getenv("VHP_SWEEP_IMPL");
   ctx->sweep_impl = 0;
   if (impl && std::strcmp(impl, "naive") == 0) ctx->sweep_impl = 1;
-  if (impl && std::strcmp(impl, "front") == 0) ctx->sweep_impl = 2;
-  if (impl && std::strcmp(impl, "ring") == 0) ctx->sweep_impl = 3;
-  if (impl && std::strcmp(impl, "octant") == 0) ctx->sweep_impl = 4;
-  if (impl && std::strcmp(impl, "tile") == 0) ctx->sweep_impl = 5;
   *out = ctx;
   return VHP_OK;
 }
@@ -485,10 +361,7 @@ void vhp_context_destroy(vhp_context *ctx) {
                        &ctx->b_scratch, &ctx->b_planner, &ctx->b_misc};
   for (VhpDevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
-  if (ctx->packed_buf) cudaFree(ctx->packed_buf);
-  if (ctx->oct_buf) cudaFree(ctx->oct_buf);
   if (ctx->tile_buf) cudaFree(ctx->tile_buf);
-  if (ctx->rcp_table) cudaFree(ctx->rcp_table);
   if (ctx->rcp2_table) cudaFree(ctx->rcp2_table);
   if (ctx->d_err) cudaFree(ctx->d_err);
   for (int i = 0; i < 2; ++i) {
@@ -510,12 +383,9 @@ vhp_status vhp_prepare_maps_dev(vhp_context *ctx, const uint8_t *d_occ, int nmap
   if (!ctx || !d_occ || nmaps < 1 || nx < 1 || ny < 1)
     return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_prepare_maps_dev: bad argument");
   VHP_CUDA(ctx, cudaSetDevice(ctx->device));
-  vhp_status st = pack_maps(ctx, d_occ, nmaps, nx, ny, true);
-  if (st == VHP_OK && vhp_sweep_octant_supported(nx, ny))
-    st = pack_oct(ctx, d_occ, nmaps, nx, ny, true);
-  if (st == VHP_OK && vhp_sweep_tile_supported(nx, ny))
-    st = pack_tile(ctx, d_occ, nmaps, nx, ny, true);
-  if (st == VHP_OK) ctx->packed_sticky = true;
+  if (!vhp_sweep_tile_supported(nx, ny)) return VHP_OK; // the naive kernel reads the byte maps
+  const vhp_status st = pack_tile(ctx, d_occ, nmaps, nx, ny, true);
+  if (st == VHP_OK) ctx->planes_sticky = true;
   return st;
 }
 
@@ -554,14 +424,10 @@ vhp_status vhp_selftest_ratio(vhp_context *ctx, int kmax, int64_t *mismatches) {
   if (!ctx || !mismatches || kmax < 1 || kmax > 16384)
     return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_selftest_ratio: bad argument");
   VHP_CUDA(ctx, cudaSetDevice(ctx->device));
-  vhp_status st = ensure_rcp(ctx, kmax + 8);
+  vhp_status st = ensure_rcp2(ctx, kmax + 8);
   if (st != VHP_OK) return st;
   if ((st = ensure(ctx, ctx->b_misc, 64)) != VHP_OK) return st;
   VHP_CUDA(ctx, cudaMemsetAsync(ctx->b_misc.p, 0, 8, ctx->stream));
-  VHP_CUDA(ctx, vhp_launch_ratio_selftest(ctx->rcp_table, kmax,
-                                          (unsigned long long *)ctx->b_misc.p, ctx->stream,
-                                          &ctx->launches));
-  if ((st = ensure_rcp2(ctx, kmax + 8)) != VHP_OK) return st;
   VHP_CUDA(ctx, vhp_launch_ratio2_selftest(ctx->rcp2_table, kmax,
                                            (unsigned long long *)ctx->b_misc.p, ctx->stream,
                                            &ctx->launches));
@@ -605,10 +471,10 @@ vhp_status vhp_planner_batch(vhp_context *ctx, const uint8_t *occ, int nmaps, in
   VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_src.p, se_xy, (size_t)nprob * 16, cudaMemcpyHostToDevice, ctx->stream));
   if (prob_map)
     VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_map.p, prob_map, (size_t)nprob * 4, cudaMemcpyHostToDevice, ctx->stream));
-  ctx->packed_src = nullptr;
-  ctx->packed_sticky = false;
-  if ((st = pack_maps(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, true)) != VHP_OK) return st;
-  ctx->packed_sticky = true;
+  ctx->tile_src = nullptr;
+  ctx->planes_sticky = false;
+  if ((st = pack_tile(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, true)) != VHP_OK) return st;
+  ctx->planes_sticky = true;
   // device staging for the requested outputs, a chunk of problems at a time
   const size_t per_prob = (h.vis ? esz * cells : 0) + (h.vg ? esz * cells : 0) + (h.came ? 4 * cells : 0) +
                           4 + 4 + 8 + 4 + 2 * (size_t)ls_cap * 8 + 64;
@@ -652,8 +518,8 @@ vhp_status vhp_planner_batch(vhp_context *ctx, const uint8_t *occ, int nmaps, in
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess && result == VHP_OK) result = cuda_fail(ctx, e, "planner sync");
   }
-  ctx->packed_sticky = false;
-  ctx->packed_src = nullptr;
+  ctx->planes_sticky = false;
+  ctx->tile_src = nullptr;
   if (result != VHP_OK) return result;
   return check_device_error(ctx);
 }

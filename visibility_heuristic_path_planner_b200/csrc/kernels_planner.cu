@@ -8,8 +8,9 @@
 //
 // One persistent CTA per problem runs the whole data-dependent loop without any
 // host round trip:
-//   1. sweep from the current light source (the tuned K1 body, fp64 store) into
-//      the local visibility field `vis`  -- the DP part of updateVisibility;
+//   1. sweep from the current light source (the tile-wavefront K1 body of
+//      sweep_tile_body.cuh, fp64 store) into the local visibility field `vis`
+//      -- the DP part of updateVisibility;
 //   2. fused per-cell epilogue over the grid (coalesced): global visibility
 //      max-merge (:417-418), first-writer parent (:419-423), heuristic
 //      h = scale*vg + (d(cell,end) + d(cell,parent)) (:424-430) and the arg-min
@@ -27,12 +28,12 @@
 // them, loop bounds :434-438,:478-483,:522-527) get no epilogue.
 #include <cstdint>
 
-#include "sweep_front_body.cuh"
+#include "sweep_tile_body.cuh"
 
 namespace {
 
 struct PlannerParams {
-  FrontParams fp;
+  TileArgs fp;
   const int32_t *se_xy, *prob_map;
   double thr;
   int max_iter, ls_cap;
@@ -62,8 +63,7 @@ __device__ __forceinline__ double eval_d(int ax, int ay, int bx, int by) {
   return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), (double)(dy * dy)));
 }
 
-template <bool VEC, int MAXNT, int MINB>
-__global__ void __launch_bounds__(MAXNT, MINB) planner_kernel(const PlannerParams p) {
+__global__ void __launch_bounds__(kTileWarps * 32) planner_kernel(const PlannerParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_ctl[4];              // {done, next x, next y, status}
   __shared__ Best s_best[32];
@@ -74,22 +74,20 @@ __global__ void __launch_bounds__(MAXNT, MINB) planner_kernel(const PlannerParam
   const int stx = p.se_xy[4 * q], sty = p.se_xy[4 * q + 1];
   const int ex = p.se_xy[4 * q + 2], ey = p.se_xy[4 * q + 3];
   const int map = p.prob_map ? p.prob_map[q] : 0;
-  const uint32_t *rowbits = p.fp.rowbits + (size_t)map * p.fp.row_plane;
-  const uint32_t *colbits = p.fp.colbits + (size_t)map * p.fp.col_plane;
+  const uint32_t *rowbits = p.fp.pl.rowF + (size_t)map * p.fp.pl.row_plane;
   double *vis = p.vis + q * cells, *vg = p.vg + q * cells;
   int32_t *came = p.came + q * cells;
   int32_t *ls = p.ls + q * (size_t)p.ls_cap * 2;
   const double thr = p.thr;
 
-  // reset(): :42-60
+  // reset(): :42-60 (every sweep writes all of `vis`, border cells included)
   for (size_t c = tid; c < cells; c += blockDim.x) {
-    vis[c] = 0.0;
     vg[c] = 0.0;
     came[c] = VHP_NO_PARENT;
   }
   if (tid == 0) {
     auto free_cell = [&](int x, int y) {
-      return (rowbits[(size_t)y * p.fp.wpr + (x >> 5)] >> (x & 31)) & 1u;
+      return (rowbits[(size_t)y * p.fp.pl.wx + (x >> 5)] >> (x & 31)) & 1u;
     };
     int st = VHP_OK; // checks in the reference's order, :89-116
     if ((unsigned)stx >= (unsigned)nx || (unsigned)sty >= (unsigned)ny) st = VHP_START_OOB;
@@ -118,7 +116,7 @@ __global__ void __launch_bounds__(MAXNT, MINB) planner_kernel(const PlannerParam
     bool done = s_ctl[0] != 0;
     while (!done) {
       // ---- 1. sweep (visibility_.reset() + the DP of updateVisibility)
-      sweep_front_body<double, VEC>(p.fp, sx, sy, rowbits, colbits, vis, smem_raw);
+      tile_sweep_cta<double>(p.fp, map, sx, sy, vis, smem_raw);
       // ---- 2. per-cell epilogue + arg-min
       Best best{~0ull, ~0ull};
       for (size_t c = tid; c < cells; c += blockDim.x) {
@@ -191,6 +189,8 @@ __global__ void __launch_bounds__(MAXNT, MINB) planner_kernel(const PlannerParam
     }
   }
 
+  if (nb == 0) // no sweep ran: visibility_ keeps the zeros of reset() (:43)
+    for (size_t c = tid; c < cells; c += blockDim.x) vis[c] = 0.0;
   if (tid == 0) {
     p.status[q] = status;
     p.nb[q] = nb;
@@ -231,39 +231,34 @@ __global__ void __launch_bounds__(MAXNT, MINB) planner_kernel(const PlannerParam
 
 } // namespace
 
-bool vhp_planner_supported(int nx, int ny) { return vhp_sweep_front_supported(nx, ny); }
+bool vhp_planner_supported(int nx, int ny) { return vhp_sweep_tile_supported(nx, ny); }
 
-cudaError_t vhp_launch_planner(const VhpPackedMaps &maps, int nx, int ny, const int32_t *d_se_xy,
+cudaError_t vhp_launch_planner(const VhpTilePlanes &pl, int nx, int ny, const int32_t *d_se_xy,
                                const int32_t *d_prob_map, int64_t nprob, double threshold,
-                               int32_t max_iter, int32_t ls_cap, const double *d_rcp,
+                               int32_t max_iter, int32_t ls_cap, const double *d_rcp2,
                                double *d_vis, double *d_vg, int32_t *d_came, int32_t *d_status,
                                int32_t *d_nb, int32_t *d_ls, double *d_path_len, int32_t *d_path_n,
                                int32_t *d_path, float *d_vg32, float *d_vis32, int *d_err,
                                cudaStream_t st, int64_t *launches) {
+  if (!vhp_sweep_tile_supported(nx, ny)) return cudaErrorInvalidConfiguration;
   PlannerParams p;
-  p.fp.err = d_err;
-  p.fp.rowbits = maps.rowbits; p.fp.colbits = maps.colbits;
-  p.fp.wpr = maps.wpr; p.fp.wpc = maps.wpc;
-  p.fp.row_plane = maps.row_plane; p.fp.col_plane = maps.col_plane;
+  p.fp.pl = pl;
   p.fp.nx = nx; p.fp.ny = ny;
   p.fp.src_xy = nullptr; p.fp.src_map = nullptr; p.fp.out = nullptr;
-  p.fp.rcp = d_rcp;
-  int nt; size_t smem;
-  front_geometry(nx, ny, VHP_F64, nt, p.fp.edge_p2, smem);
-  if (smem > 227 * 1024 || nt > 1024) return cudaErrorInvalidConfiguration;
+  p.fp.rtab = reinterpret_cast<const double2 *>(d_rcp2);
+  p.fp.err = d_err;
+  p.fp.vec = ((uintptr_t)d_vis % 16 == 0 && nx % 2 == 0) ? 1 : 0;
   p.se_xy = d_se_xy; p.prob_map = d_prob_map;
   p.thr = threshold; p.max_iter = max_iter; p.ls_cap = ls_cap;
   p.vis = d_vis; p.vg = d_vg; p.came = d_came;
   p.status = d_status; p.nb = d_nb; p.ls = d_ls;
   p.path_len = d_path_len; p.path_n = d_path_n; p.path = d_path;
   p.vg32 = d_vg32; p.vis32 = d_vis32;
-  const bool vec = nx % 2 == 0;
-  void (*kern)(const PlannerParams);
-  if (nt <= 256) kern = vec ? planner_kernel<true, 256, 2> : planner_kernel<false, 256, 2>;
-  else kern = vec ? planner_kernel<true, 1024, 1> : planner_kernel<false, 1024, 1>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = tile_smem_bytes<double>(nx, ny);
+  cudaError_t e = cudaFuncSetAttribute(planner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<(unsigned)nprob, nt, smem, st>>>(p);
+  planner_kernel<<<(unsigned)nprob, kTileWarps * 32, smem, st>>>(p);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }

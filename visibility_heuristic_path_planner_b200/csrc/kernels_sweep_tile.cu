@@ -102,6 +102,35 @@ __global__ void pack_tile_sum_kernel(const uint32_t *__restrict__ rowF, int nmap
   }
 }
 
+// rtab[k] = {rh, rl}: rh = RN(1/k), rl = RN((1 - rh*k) * rh)
+__global__ void rcp2_table_kernel(double2 *table, int len) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < len) {
+    double rh = 0.0, rl = 0.0;
+    if (k > 0) {
+      const double fk = (double)k;
+      rh = __drcp_rn(fk);
+      rl = __dmul_rn(__fma_rn(-rh, fk, 1.0), rh);
+    }
+    table[k] = make_double2(rh, rl);
+  }
+}
+
+// diagnostic: count (d, k), 0 <= d < k <= kmax, where fma(d, rh, d*rl) != d/k
+__global__ void ratio2_selftest_kernel(const double2 *__restrict__ tab, int kmax,
+                                       unsigned long long *mismatches) {
+  const int k = blockIdx.x + 1;
+  if (k > kmax) return;
+  const double fk = (double)k;
+  const double2 rr = tab[k];
+  unsigned long long bad = 0;
+  for (int d = threadIdx.x; d < k; d += blockDim.x) {
+    const double fd = (double)d;
+    if (__fma_rn(fd, rr.x, __dmul_rn(fd, rr.y)) != __ddiv_rn(fd, fk)) ++bad;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
 template <typename OutT>
 cudaError_t launch_tile(const TileArgs &p, int64_t npairs, cudaStream_t st) {
   const size_t smem = tile_smem_bytes<OutT>(p.nx, p.ny);
@@ -142,6 +171,21 @@ cudaError_t vhp_launch_pack_tile(const uint8_t *d_occ, int nmaps, int nx, int ny
   const unsigned gs = (unsigned)std::min<size_t>((nblk * 32 + bs - 1) / bs, 148u * 32u);
   pack_tile_sum_kernel<<<gs, bs, 0, st>>>(rowF, nmaps, nx, ny, wx, bsum);
   if (launches) *launches += 3;
+  return cudaGetLastError();
+}
+
+cudaError_t vhp_launch_rcp2_table(double *d_table, int len, cudaStream_t st, int64_t *launches) {
+  rcp2_table_kernel<<<(len + 255) / 256, 256, 0, st>>>(reinterpret_cast<double2 *>(d_table), len);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t vhp_launch_ratio2_selftest(const double *d_rcp2, int kmax,
+                                       unsigned long long *d_mismatches, cudaStream_t st,
+                                       int64_t *launches) {
+  ratio2_selftest_kernel<<<kmax, 128, 0, st>>>(reinterpret_cast<const double2 *>(d_rcp2), kmax,
+                                               d_mismatches);
+  if (launches) *launches += 1;
   return cudaGetLastError();
 }
 
