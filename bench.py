@@ -35,17 +35,19 @@ METRIC = "Gcells/s visibility sweep (1000² grid, batched sources)"
 
 
 # ----------------------------------------------------------------------------
-def workload(name, rank):
+def workload(name, rank, world=1):
     """Synthetic batch for one rank: (maps uint8 [nmaps,ny,nx], src_xy, src_map, desc)."""
     if name == "c2":
+        from visibility_heuristic_path_planner_b200.sharding import shard_batch
         nx = ny = 1000
-        n = 4096
+        n = 4096 * world  # global batch, cut into contiguous blocks of 4096 per rank
         maps = np.ones((1, ny, nx), dtype=np.uint8)
-        g = np.random.default_rng(1234 + rank)
+        g = np.random.default_rng(1234)
         src = np.stack([g.integers(0, nx, n), g.integers(0, ny, n)], axis=1).astype(np.int32)
-        if rank == 0:
-            src[0] = (500, 500)  # the reference's benchmarkSeries case
-        return maps, src, None, "1000x1000 empty grid, 4096 light sources per GPU (PCG64 seed 1234+rank)"
+        src[0] = (500, 500)  # the reference's benchmarkSeries case
+        maps, src, _, _ = shard_batch(maps, src, None, rank, world)
+        return maps, src, None, ("1000x1000 empty grid, 4096 light sources per GPU "
+                                 "(global batch PCG64 seed 1234, contiguous block per rank)")
     if name == "c4":
         nx = ny = 256
         nmaps, per = 1024, 16
@@ -310,7 +312,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    maps, src, smap, desc = workload(args.workload, rank)
+    maps, src, smap, desc = workload(args.workload, rank, world)
     if args.pairs:
         src = np.ascontiguousarray(src[:args.pairs])
         smap = None if smap is None else np.ascontiguousarray(smap[:args.pairs])
