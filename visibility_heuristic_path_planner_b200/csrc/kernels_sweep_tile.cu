@@ -11,8 +11,11 @@
 
 namespace {
 
+#ifndef VHP_TILE_MINB
+#define VHP_TILE_MINB 3
+#endif
 template <typename OutT>
-__global__ void __launch_bounds__(kTileWarps * 32)
+__global__ void __launch_bounds__(kTileWarps * 32, VHP_TILE_MINB)
 sweep_tile_kernel(const TileArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int64_t pair = blockIdx.x;

@@ -18,13 +18,16 @@
 // with a chosen per quadrant so that every other tile column starts on an absolute x
 // that is a multiple of 32 (row stores are then whole, aligned 128-byte segments).
 // Tile (I, J) needs the top row of (I, J-1), the right column of (I-1, J) and one
-// corner cell of (I-1, J-1): tiles of an anti-diagonal I + J = d are independent
-// ("wave d").  The CTA walks the waves of all four quadrants together, one warp per
-// tile, one block barrier per wave (<= 2*N/32 + 2 barriers per sweep instead of N).
-// Boundary rows / columns live in shared memory as fp64:
-//     rowE[q][i]          = q(i, j_last)       top row of the newest tile above local column i
-//     colE[q][33*J + 1+r] = q(i_last, j0 + r)  right column of the newest tile in tile row J
-//     colE[q][33*J]       = the corner cell for the NEXT tile of row J
+// corner cell of (I-1, J-1).  Tile rows are pipelines: a warp owns tile row J of a
+// quadrant and walks I = 0, 1, ... keeping the right column and the corner in
+// registers; the top row of every finished tile goes to shared memory (fp64),
+//     rowE[q][i] = q(i, j_last)    top row of the newest tile above local column i,
+// followed by a release store of the row's progress counter.  The warp of row J + 1
+// acquires that counter before it starts tile I, so rows run skewed by one tile with
+// no block barrier at all (the first kernels of this repo had one barrier per ring).
+// Rows are dealt to the 8 warps of the CTA in (J, quadrant) order, which keeps the
+// four quadrants in flight together and cannot deadlock: a row only ever waits for a
+// row earlier in that order.
 //
 // A tile whose inputs all equal one value v and whose cells are all free is v
 // everywhere (a - c*(a - b) with a == b is exactly a): it is written with plain
@@ -64,7 +67,7 @@ namespace {
 constexpr int kTileWarps = 8;          // warps per CTA
 constexpr int kTile = 32;              // tile side
 constexpr int kStagePitch = 33;        // staging tile pitch (elements)
-constexpr int kWarpScratch = 72;       // doubles per warp: [0..32] boundary stream, [33..64] new edge
+constexpr int kWarpScratch = 104;      // doubles per warp: bottom stream [33], left stream [33], new edge [32]
 constexpr unsigned kAll = 0xffffffffu;
 
 struct TileArgs {
@@ -82,16 +85,18 @@ struct TQuad {
   int dirx, diry;   // +1 / -1
   int Ex, Ey;       // largest local i / j inside the grid
   int TX, TY;       // tile columns / rows (0: the quadrant does not exist)
-  int rowOff, colOff; // offsets of rowE / colE in the edge region (doubles)
+  int rowOff;       // offset of rowE in the edge region (doubles)
+  int pad1;
   int psx, psy;     // plane coordinate of the source along x / y
   int a;            // width of the first tile row / column (1..32)
   int pad0;
 };
 
 __host__ __device__ inline int tile_edge_doubles(int nx, int ny) {
-  // per direction a quadrant has at most E/32 + 2 tile columns (rows); two quadrants share
-  // each x (y) direction and the + and - extents add up to nx - 1 (ny - 1)
-  return 2 * kTile * ((nx - 1) / kTile + 4) + 2 * 33 * ((ny - 1) / kTile + 4);
+  // per direction a quadrant has at most E/32 + 2 tile columns; two quadrants share each x
+  // direction and the + and - extents add up to nx - 1
+  (void)ny;
+  return 2 * kTile * ((nx - 1) / kTile + 4);
 }
 
 // block summary: one bit per aligned 32 x 32 block, tile_sum_words(nx) words per block row
@@ -100,12 +105,12 @@ __host__ __device__ inline int tile_sum_bytes(int nx, int ny) {
   return (4 * tile_sum_words(nx) * ((ny + 31) >> 5) + 15) & ~15;
 }
 
-// lit staircase: Lm[q][J], tile_lm_cap(ny) entries per quadrant
+// lit staircase Lm[q][J] and row progress prog[q][J]: tile_lm_cap(ny) entries per quadrant each
 __host__ __device__ inline int tile_lm_cap(int ny) { return (ny - 1) / kTile + 4; }
 
 template <typename OutT>
 __host__ __device__ inline size_t tile_smem_bytes(int nx, int ny) {
-  return 256 + tile_sum_bytes(nx, ny) + 16 * (size_t)tile_lm_cap(ny) +
+  return 256 + tile_sum_bytes(nx, ny) + 32 * (size_t)tile_lm_cap(ny) +
          sizeof(double) * (size_t)tile_edge_doubles(nx, ny) +
          (size_t)kTileWarps * (kTile * kStagePitch * sizeof(OutT) + kWarpScratch * sizeof(double));
 }
@@ -161,7 +166,19 @@ __device__ __forceinline__ void fill_span(OutT *__restrict__ row, const int xa, 
   }
 }
 
-// One tile (I, J) of quadrant g by one warp.
+__device__ __forceinline__ int ld_acquire_shared(const int *a) {
+  int v;
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];"
+               : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(a)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_shared(int *a, int v) {
+  asm volatile("st.release.cta.shared.s32 [%0], %1;"
+               :: "r"((uint32_t)__cvta_generic_to_shared(a)), "r"(v) : "memory");
+}
+
+// One tile (I, J) of quadrant g by one warp.  Lv (lane r: q(i0-1, j0+r)) and cor
+// (q(i0-1, j0-1)) are the left inputs; on return they hold the same for tile (I+1, J).
 template <typename OutT>
 __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
                                              const uint32_t *__restrict__ rowpl,
@@ -169,7 +186,14 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
                                              const uint32_t *__restrict__ bsum, const int sx,
                                              const int sy, const int I, const int J,
                                              OutT *__restrict__ out, double *edges,
-                                             OutT *stage, double *wscr, const int lane) {
+                                             OutT *stage, double *wscr, const int lane,
+                                             double &Lv, double &cor, int *done_flag) {
+  // the row above may start its tile I as soon as rowE holds this tile's top row: publish
+  // before the global stores
+  auto publish = [&]() {
+    __syncwarp();
+    if (lane == 0) st_release_shared(done_flag, I + 1);
+  };
   const int nx = p.nx;
   const int wi = I ? kTile : g.a, wj = J ? kTile : g.a;          // tile extent
   const int i0 = tile_start(g.a, I), j0 = tile_start(g.a, J);
@@ -181,7 +205,6 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
   const uint32_t rmask = nvy >= 32 ? ~0u : (nvy <= 0 ? 0u : (1u << nvy) - 1u);
   const bool colc = (cmask >> lane) & 1u, rowc = (rmask >> lane) & 1u;
   double *rowE = edges + g.rowOff + i0;
-  double *colE = edges + g.colOff + 33 * J;
 
   // ---- occupancy: block summary first, bit plane otherwise --------------------------
   bool allfree = false, allocc = true, sumfree = false;
@@ -202,7 +225,7 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
       allocc = __all_sync(kAll, wrow == 0u);
     }
   }
-  const double Bv = rowE[lane], Lv = colE[1 + lane], cor = colE[0];
+  const double Bv = rowE[lane];
   const bool inuni = __all_sync(kAll, (!colc || Bv == cor) && (!rowc || Lv == cor));
   const bool zero_in = inuni && cor == 0.0;
 
@@ -217,10 +240,11 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
     // ---- uniform tile: no arithmetic -------------------------------------------------
     const bool zero = allocc || zero_in;
     if (allocc && !zero_in) { // live inputs end here
-      if (lane == wi - 1) colE[0] = Bv;
       if (lane < wi) rowE[lane] = 0.0;
-      if (lane < wj) colE[1 + lane] = 0.0;
+      Lv = 0.0;
+      cor = __shfl_sync(kAll, Bv, wi - 1);
     }
+    publish();
     const int rc = min(wj - 1, EyC - j0); // last computed row; a border row (if any) follows
     if (p.vec && nvx == 32 && (I > 0 || g.dirx > 0)) {
       // all 32 columns are stored and x0 is a multiple of 32: 128-bit stores
@@ -245,15 +269,22 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
   }
 
   const double fd = (double)(I > J ? jr : il); // offset along the front (i0 == j0 on the diagonal)
+  double *lx = wscr + 33, *wnew = wscr + 66;       // wscr: bottom stream, lx: left stream
+  const double cor_next = __shfl_sync(kAll, Bv, wi - 1);
+  __syncwarp();
   wscr[1 + lane] = Bv;
-  if (lane == 0) wscr[0] = cor;
-  double *wnew = wscr + 33;
+  lx[1 + lane] = Lv;
+  if (lane == 0) {
+    wscr[0] = cor;
+    lx[0] = cor;
+  }
   __syncwarp();
 
   if (I > J) {
     // ---- column-octant tile: lanes along j, steps along i (wi == 32) -------------------
     double F = Lv;
     const int ns = min(32, g.Ex - i0 + 1);
+    if (ns < 32 && lane >= ns) wnew[lane] = 0.0; // columns beyond the grid
 #pragma unroll 4
     for (int s = 0; s < ns; ++s) {
       const double2 rr = __ldg(p.rtab + i0 + s);
@@ -266,9 +297,9 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
       if (lane == wj - 1) wnew[s] = F;
     }
     __syncwarp();
-    if (lane == 31) colE[0] = Bv;
     rowE[lane] = wnew[lane];
-    if (lane < wj) colE[1 + lane] = F;
+    Lv = F;
+    publish();
   } else {
     // occupancy of column il, bit b <-> local row j0 + b
     uint32_t wcol = 0;
@@ -290,7 +321,7 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
       for (int s = 0; s < ns; ++s, q += rs) {
         const double2 rr = __ldg(p.rtab + j0 + s);
         const double up = __shfl_up_sync(kAll, F, 1);
-        const double b = lane ? up : colE[s];
+        const double b = lane ? up : lx[s];
         const double c = __fma_rn(fd, rr.x, __dmul_rn(fd, rr.y));
         const double v = lerp_rn(F, b, c);
         F = ((wcol >> s) & 1u) ? v : 0.0;
@@ -298,9 +329,10 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
         if (lane == wi - 1) wnew[s] = F;
       }
       __syncwarp();
-      if (lane == wi - 1) colE[0] = Bv;
       if (lane < wi) rowE[lane] = F;
-      colE[1 + lane] = wnew[lane];
+      Lv = wnew[lane];
+      cor = cor_next;
+      publish();
       return;
     }
     // ---- diagonal tile: both fronts and the diagonal cell (wi == wj) ---------------------
@@ -313,7 +345,7 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
       const double upC = __shfl_up_sync(kAll, C, 1);
       const double upR = __shfl_up_sync(kAll, R, 1);
       const double bC = lane ? upC : wscr[k];
-      const double bR = lane ? upR : colE[k];
+      const double bR = lane ? upR : lx[k];
       const double vC = lerp_rn(C, bC, c), vR = lerp_rn(R, bR, c);
       if (lane < k) {
         C = ((wrow >> k) & 1u) ? vC : 0.0;
@@ -331,12 +363,11 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
       }
     }
     __syncwarp();
-    if (lane == wi - 1) colE[0] = Bv;
-    if (lane < wi) {
-      rowE[lane] = R;
-      colE[1 + lane] = C;
-    }
+    if (lane < wi) rowE[lane] = R;
+    Lv = C;
+    publish();
   }
+  cor = cor_next;
   // ---- write the staged tile as rows ---------------------------------------------------
   __syncwarp();
   if (lane_st) {
@@ -344,7 +375,6 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
 #pragma unroll 4
     for (int r = r0; r <= rlast; ++r, q += rs) __stcs(q, stage[r * kStagePitch + lane]);
   }
-  __syncwarp();
 }
 
 // One complete sweep from (sx, sy) by the whole CTA (kTileWarps warps, all threads
@@ -362,7 +392,8 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
   const int nsum = tile_sum_words(nx) * ((ny + 31) >> 5);
   const int lmcap = tile_lm_cap(ny);
   int *Lm = reinterpret_cast<int *>(smem_raw + 256 + tile_sum_bytes(nx, ny));
-  double *edges = reinterpret_cast<double *>(smem_raw + 256 + tile_sum_bytes(nx, ny) + 16 * lmcap);
+  int *prog = Lm + 4 * lmcap; // tiles finished (or lit) at the head of tile row (q, J)
+  double *edges = reinterpret_cast<double *>(smem_raw + 256 + tile_sum_bytes(nx, ny) + 32 * lmcap);
   const int nedge = tile_edge_doubles(nx, ny);
   unsigned char *wbase = reinterpret_cast<unsigned char *>(edges + nedge);
   double *wscr = reinterpret_cast<double *>(wbase) + warp * kWarpScratch;
@@ -386,8 +417,7 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
       g.TY = !exists ? 0 : (g.Ey < g.a ? 1 : (g.Ey - g.a) / kTile + 2);
       g.rowOff = off;
       off += g.TX * kTile;
-      g.colOff = off;
-      off += g.TY * 33;
+      g.pad1 = 0;
       g.psx = g.dirx > 0 ? sx : WXb - 1 - sx;
       g.psy = g.diry > 0 ? sy : WYb - 1 - sy;
       g.pad0 = 0;
@@ -415,16 +445,14 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
     }
   }
   __syncthreads();
-  int *dfirst = reinterpret_cast<int *>(smem_raw + 240); // first wave with a tile outside the staircase
   if (tid < 4) {
     const TQuad &g = quads[tid];
-    int m = g.TX, dq = 0x3fffffff;
+    int m = g.TX;
     for (int J = 0; J < g.TY; ++J) {
       m = min(m, Lm[tid * lmcap + J]);
       Lm[tid * lmcap + J] = m;
-      if (m < g.TX) dq = min(dq, m + J);
+      prog[tid * lmcap + J] = m;
     }
-    dfirst[tid] = dq;
   }
   __syncthreads();
 
@@ -456,34 +484,35 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
     }
   }
 
-  int Dmax = 0, Dmin = 0x3fffffff;
+  // ---- the rest: tile rows as pipelines, dealt to the warps in (J, quadrant) order ---------
+  int maxTY = 0;
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
-    if (quads[q].TX) {
-      Dmax = max(Dmax, quads[q].TX + quads[q].TY - 2);
-      Dmin = min(Dmin, dfirst[q]);
-    }
-
-  for (int d = Dmin; d <= Dmax; ++d) {
-    int base = 0;
+  for (int q = 0; q < 4; ++q) maxTY = max(maxTY, quads[q].TY);
+  int cnt = 0;
+  for (int J = 0; J < maxTY; ++J) {
 #pragma unroll 1
     for (int q = 0; q < 4; ++q) {
       const TQuad &g = quads[q];
-      if (g.TX == 0) continue;
-      const int lo = max(0, d - (g.TY - 1)), hi = min(d, g.TX - 1);
-      const int n = hi - lo + 1;
-      if (n <= 0) continue;
+      if (J >= g.TY) continue;
+      const int I0 = Lm[q * lmcap + J];
+      if (I0 >= g.TX) continue; // the whole row is lit
+      if ((cnt++ & (kTileWarps - 1)) != warp) continue;
       const uint32_t *rowpl = (g.dirx > 0 ? p.pl.rowF : p.pl.rowR) + (size_t)map * p.pl.row_plane;
       const uint32_t *colpl = (g.diry > 0 ? p.pl.colF : p.pl.colR) + (size_t)map * p.pl.col_plane;
+      double Lv = 1.0, cor = 1.0; // left of the first tile: lit tiles or the virtual boundary
 #pragma unroll 1
-      for (int t = (warp - base) & (kTileWarps - 1); t < n; t += kTileWarps)
-        if (lo + t >= Lm[q * lmcap + d - lo - t]) // not inside the lit staircase
-          process_tile<OutT>(p, g, rowpl, colpl, bsum, sx, sy, lo + t, d - lo - t, out, edges,
-                             stage, wscr, lane);
-      base += n;
+      for (int I = I0; I < g.TX; ++I) {
+        if (J > 0) { // tile (I, J-1) must be finished
+          const int *flag = prog + q * lmcap + J - 1;
+          while (ld_acquire_shared(flag) <= I) __nanosleep(40);
+        }
+        process_tile<OutT>(p, g, rowpl, colpl, bsum, sx, sy, I, J, out, edges, stage, wscr, lane,
+                           Lv, cor, prog + q * lmcap + J);
+        __syncwarp();
+      }
     }
-    __syncthreads();
   }
+  __syncthreads();
 }
 
 } // namespace
