@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) planner_kernel(const PlannerP
     bool done = s_ctl[0] != 0;
     while (!done) {
       // ---- 1. sweep (visibility_.reset() + the DP of updateVisibility)
-      tile_sweep_cta<double>(p.fp, map, sx, sy, vis, smem_raw);
+      tile_sweep_cta<double, kTileWarps>(p.fp, map, sx, sy, vis, smem_raw);
       // ---- 2. per-cell epilogue + arg-min
       Best best{~0ull, ~0ull};
       for (size_t c = tid; c < cells; c += blockDim.x) {

@@ -6,16 +6,18 @@
 // pairs: one CTA per pair, see sweep_tile_body.cuh for the decomposition.
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 #include "sweep_tile_body.cuh"
 
 namespace {
 
-#ifndef VHP_TILE_MINB
-#define VHP_TILE_MINB 3
-#endif
-template <typename OutT>
-__global__ void __launch_bounds__(kTileWarps * 32, VHP_TILE_MINB)
+// NW warps per CTA: 8 for large grids (a pair's boundary rows take tens of KB of shared
+// memory, so few CTAs fit an SM and each must bring its own parallelism); small maps use 4,
+// or 1 when the batch alone fills the machine (32 independent single-warp CTAs per SM: no
+// flag polling, no imbalance between the warps of a pair).
+template <typename OutT, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
 sweep_tile_kernel(const TileArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int64_t pair = blockIdx.x;
@@ -26,7 +28,7 @@ sweep_tile_kernel(const TileArgs p) {
   }
   const int map = p.src_map ? __ldg(p.src_map + pair) : 0;
   OutT *out = reinterpret_cast<OutT *>(p.out) + (size_t)pair * p.nx * p.ny;
-  tile_sweep_cta<OutT>(p, map, sx, sy, out, smem_raw);
+  tile_sweep_cta<OutT, NW>(p, map, sx, sy, out, smem_raw);
 }
 
 // ---------------------------------------------------------------------------------
@@ -134,14 +136,34 @@ __global__ void ratio2_selftest_kernel(const double2 *__restrict__ tab, int kmax
   if (bad) atomicAdd(mismatches, bad);
 }
 
-template <typename OutT>
-cudaError_t launch_tile(const TileArgs &p, int64_t npairs, cudaStream_t st) {
-  const size_t smem = tile_smem_bytes<OutT>(p.nx, p.ny);
-  auto kern = sweep_tile_kernel<OutT>;
+template <typename OutT, int NW, int MINB>
+cudaError_t launch_tile_nw(const TileArgs &p, int64_t npairs, cudaStream_t st) {
+  const size_t smem = tile_smem_bytes<OutT>(p.nx, p.ny, NW);
+  auto kern = sweep_tile_kernel<OutT, NW, MINB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<(unsigned)npairs, kTileWarps * 32, smem, st>>>(p);
+  kern<<<(unsigned)npairs, NW * 32, smem, st>>>(p);
   return cudaGetLastError();
+}
+
+int tile_warps_for(int nx, int ny, int64_t npairs) {
+  static const int forced = [] {
+    const char *e = std::getenv("VHP_TILE_WARPS");
+    return e ? std::atoi(e) : 0;
+  }();
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced;
+  if (std::max(nx, ny) > 512) return 8;
+  return npairs >= 148 * 16 ? 1 : 4; // enough pairs to fill the SMs with single-warp CTAs?
+}
+
+template <typename OutT>
+cudaError_t launch_tile(const TileArgs &p, int64_t npairs, cudaStream_t st) {
+  switch (tile_warps_for(p.nx, p.ny, npairs)) {
+    case 1: return launch_tile_nw<OutT, 1, 32>(p, npairs, st);
+    case 2: return launch_tile_nw<OutT, 2, 12>(p, npairs, st);
+    case 4: return launch_tile_nw<OutT, 4, 8>(p, npairs, st);
+    default: return launch_tile_nw<OutT, 8, 3>(p, npairs, st);
+  }
 }
 
 } // namespace

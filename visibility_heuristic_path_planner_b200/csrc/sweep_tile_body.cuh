@@ -64,7 +64,7 @@
 
 namespace {
 
-constexpr int kTileWarps = 8;          // warps per CTA
+constexpr int kTileWarps = 8;          // warps per CTA (default; small maps use fewer)
 constexpr int kTile = 32;              // tile side
 constexpr int kStagePitch = 33;        // staging tile pitch (elements)
 constexpr int kWarpScratch = 104;      // doubles per warp: bottom stream [33], left stream [33], new edge [32]
@@ -92,11 +92,11 @@ struct TQuad {
   int pad0;
 };
 
-__host__ __device__ inline int tile_edge_doubles(int nx, int ny) {
+__host__ __device__ inline int tile_edge_doubles(int nx, int nwarps) {
   // per direction a quadrant has at most E/32 + 2 tile columns; two quadrants share each x
-  // direction and the + and - extents add up to nx - 1
-  (void)ny;
-  return 2 * kTile * ((nx - 1) / kTile + 4);
+  // direction and the + and - extents add up to nx - 1.  A single-warp CTA sweeps one
+  // quadrant after the other and reuses one boundary row.
+  return nwarps == 1 ? kTile * ((nx - 1) / kTile + 2) : 2 * kTile * ((nx - 1) / kTile + 4);
 }
 
 // block summary: one bit per aligned 32 x 32 block, tile_sum_words(nx) words per block row
@@ -109,10 +109,10 @@ __host__ __device__ inline int tile_sum_bytes(int nx, int ny) {
 __host__ __device__ inline int tile_lm_cap(int ny) { return (ny - 1) / kTile + 4; }
 
 template <typename OutT>
-__host__ __device__ inline size_t tile_smem_bytes(int nx, int ny) {
+__host__ __device__ inline size_t tile_smem_bytes(int nx, int ny, int nwarps = kTileWarps) {
   return 256 + tile_sum_bytes(nx, ny) + 32 * (size_t)tile_lm_cap(ny) +
-         sizeof(double) * (size_t)tile_edge_doubles(nx, ny) +
-         (size_t)kTileWarps * (kTile * kStagePitch * sizeof(OutT) + kWarpScratch * sizeof(double));
+         sizeof(double) * (size_t)tile_edge_doubles(nx, nwarps) +
+         (size_t)nwarps * (kTile * kStagePitch * sizeof(OutT) + kWarpScratch * sizeof(double));
 }
 
 // 16-byte streaming store of one value replicated
@@ -377,11 +377,10 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
   }
 }
 
-// One complete sweep from (sx, sy) by the whole CTA (kTileWarps warps, all threads
-// must call).  Writes every cell of out[ny][nx] exactly once (cells on the never-
-// written border get 0).  smem_raw: tile_smem_bytes<OutT>(nx, ny) bytes, 16-aligned.
+// One complete sweep from (sx, sy) by the whole CTA (NW warps, all threads must call).  Writes every cell of out[ny][nx] exactly once (cells on the never-
+// written border get 0).  smem_raw: tile_smem_bytes<OutT>(nx, ny, NW) bytes, 16-aligned.
 // Ends with a block barrier.
-template <typename OutT>
+template <typename OutT, int NW>
 __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map, const int sx,
                                                const int sy, OutT *__restrict__ out,
                                                unsigned char *smem_raw) {
@@ -394,10 +393,10 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
   int *Lm = reinterpret_cast<int *>(smem_raw + 256 + tile_sum_bytes(nx, ny));
   int *prog = Lm + 4 * lmcap; // tiles finished (or lit) at the head of tile row (q, J)
   double *edges = reinterpret_cast<double *>(smem_raw + 256 + tile_sum_bytes(nx, ny) + 32 * lmcap);
-  const int nedge = tile_edge_doubles(nx, ny);
+  const int nedge = tile_edge_doubles(nx, NW);
   unsigned char *wbase = reinterpret_cast<unsigned char *>(edges + nedge);
   double *wscr = reinterpret_cast<double *>(wbase) + warp * kWarpScratch;
-  OutT *stage = reinterpret_cast<OutT *>(wbase + kTileWarps * kWarpScratch * sizeof(double)) +
+  OutT *stage = reinterpret_cast<OutT *>(wbase + NW * kWarpScratch * sizeof(double)) +
                 warp * (kTile * kStagePitch);
 
   if (tid == 0) {
@@ -415,7 +414,7 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
       const bool exists = (g.dirx > 0 || sx > 0) && (g.diry > 0 || sy > 0);
       g.TX = !exists ? 0 : (g.Ex < g.a ? 1 : (g.Ex - g.a) / kTile + 2);
       g.TY = !exists ? 0 : (g.Ey < g.a ? 1 : (g.Ey - g.a) / kTile + 2);
-      g.rowOff = off;
+      g.rowOff = NW == 1 ? 0 : off;
       off += g.TX * kTile;
       g.pad1 = 0;
       g.psx = g.dirx > 0 ? sx : WXb - 1 - sx;
@@ -432,7 +431,7 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
   const int nbw = tile_sum_words(nx);
   for (int q = 0; q < 4; ++q) {
     const TQuad &g = quads[q];
-    for (int J = warp; J < g.TY; J += kTileWarps) {
+    for (int J = warp; J < g.TY; J += NW) {
       int L = 0;
       for (int Ib = 0; Ib < g.TX; Ib += 32) {
         const bool fr = Ib + lane < g.TX && tile_sum_free(g, bsum, nbw, sx, sy, Ib + lane, J);
@@ -457,58 +456,98 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
   __syncthreads();
 
   // ---- write the lit region: one warp per grid row, -x and +x runs merged -----------------
-  for (int y = warp; y < ny; y += kTileWarps) {
-    const bool upper = y >= sy;
-    const int j = upper ? y - sy : sy - y;
-    int nR = 0, nL = 0; // lit cells i = 0 .. n-1 of the +x / -x quadrant in this row
-    {
-      const TQuad &g = quads[upper ? 0 : 3];
-      if (g.TX) nR = min(tile_start(g.a, Lm[(upper ? 0 : 3) * lmcap + (j < g.a ? 0 : (j - g.a) / kTile + 1)]), g.Ex + 1);
+  {
+    // per quadrant: first tile width, extent, existence (registers; q = 0..3)
+    int qa[4], qex[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      qa[q] = quads[q].a;
+      qex[q] = quads[q].TX ? quads[q].Ex : -1;
     }
-    {
-      const TQuad &g = quads[upper ? 1 : 2];
-      if (g.TX) nL = min(tile_start(g.a, Lm[(upper ? 1 : 2) * lmcap + (j < g.a ? 0 : (j - g.a) / kTile + 1)]), g.Ex + 1);
-    }
-    OutT *row = out + (size_t)y * nx;
-    const OutT v = (!upper && y == 0) ? (OutT)0 : (OutT)1; // y == 0 below the source: never written
-    int xa = sx - (nL - 1), xb = sx + nR - 1;
-    if (nL > 0 && xa == 0) { // x == 0 left of the source: never written
-      if (lane == 0) __stcs(row, (OutT)0);
-      xa = 1;
-    }
-    if (nR > 0 && nL > 1) {
-      fill_span<OutT>(row, xa, xb, v, lane, p.vec);
-    } else {
-      if (nL > 1) fill_span<OutT>(row, xa, sx - 1, v, lane, p.vec);
-      if (nR > 0) fill_span<OutT>(row, sx, xb, v, lane, p.vec);
+    // lit cells i = 0 .. n-1 of quadrant q in local row j; the staircase is looked up once
+    // per tile row (cj = cached tile row, cn = its run length)
+    int cj[4] = {-1, -1, -1, -1}, cn[4] = {0, 0, 0, 0};
+    auto lit_run = [&](const int q, const int j) -> int {
+      if (qex[q] < 0) return 0;
+      const int J = j < qa[q] ? 0 : ((j - qa[q]) >> 5) + 1;
+      if (J != cj[q]) {
+        cj[q] = J;
+        cn[q] = min(tile_start(qa[q], Lm[q * lmcap + J]), qex[q] + 1);
+      }
+      return cn[q];
+    };
+    bool any_lit = false;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) any_lit |= quads[q].TX && Lm[q * lmcap] > 0;
+    for (int y = warp; any_lit && y < ny; y += NW) {
+      const bool upper = y >= sy;
+      const int j = upper ? y - sy : sy - y;
+      const int nR = upper ? lit_run(0, j) : lit_run(3, j);
+      const int nL = upper ? lit_run(1, j) : lit_run(2, j);
+      if (nR == 0 && nL <= 1) continue;
+      OutT *row = out + (size_t)y * nx;
+      const OutT v = (!upper && y == 0) ? (OutT)0 : (OutT)1; // y == 0 below the source: never written
+      int xa = sx - (nL - 1), xb = sx + nR - 1;
+      if (nL > 0 && xa == 0) { // x == 0 left of the source: never written
+        if (lane == 0) __stcs(row, (OutT)0);
+        xa = 1;
+      }
+      if (nR > 0 && nL > 1) {
+        fill_span<OutT>(row, xa, xb, v, lane, p.vec);
+      } else {
+        if (nL > 1) fill_span<OutT>(row, xa, sx - 1, v, lane, p.vec);
+        if (nR > 0) fill_span<OutT>(row, sx, xb, v, lane, p.vec);
+      }
     }
   }
 
-  // ---- the rest: tile rows as pipelines, dealt to the warps in (J, quadrant) order ---------
-  int maxTY = 0;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) maxTY = max(maxTY, quads[q].TY);
-  int cnt = 0;
-  for (int J = 0; J < maxTY; ++J) {
+  // ---- the rest: tile rows as pipelines ------------------------------------------------------
+  auto run_row = [&](const int q, const int J, const int I0) {
+    const TQuad &g = quads[q];
+    const uint32_t *rowpl = (g.dirx > 0 ? p.pl.rowF : p.pl.rowR) + (size_t)map * p.pl.row_plane;
+    const uint32_t *colpl = (g.diry > 0 ? p.pl.colF : p.pl.colR) + (size_t)map * p.pl.col_plane;
+    double Lv = 1.0, cor = 1.0; // left of the first tile: lit tiles or the virtual boundary
 #pragma unroll 1
+    for (int I = I0; I < g.TX; ++I) {
+      if (NW > 1 && J > 0) { // tile (I, J-1) must be finished
+        const int *flag = prog + q * lmcap + J - 1;
+        while (ld_acquire_shared(flag) <= I) __nanosleep(40);
+      }
+      process_tile<OutT>(p, g, rowpl, colpl, bsum, sx, sy, I, J, out, edges, stage, wscr, lane, Lv,
+                         cor, prog + q * lmcap + J);
+      __syncwarp();
+    }
+  };
+  if (NW == 1) {
+    // one warp: quadrant after quadrant, rows in order (every dependency is program order);
+    // the boundary row is shared, so reset it to the virtual boundary per quadrant
     for (int q = 0; q < 4; ++q) {
-      const TQuad &g = quads[q];
-      if (J >= g.TY) continue;
-      const int I0 = Lm[q * lmcap + J];
-      if (I0 >= g.TX) continue; // the whole row is lit
-      if ((cnt++ & (kTileWarps - 1)) != warp) continue;
-      const uint32_t *rowpl = (g.dirx > 0 ? p.pl.rowF : p.pl.rowR) + (size_t)map * p.pl.row_plane;
-      const uint32_t *colpl = (g.diry > 0 ? p.pl.colF : p.pl.colR) + (size_t)map * p.pl.col_plane;
-      double Lv = 1.0, cor = 1.0; // left of the first tile: lit tiles or the virtual boundary
-#pragma unroll 1
-      for (int I = I0; I < g.TX; ++I) {
-        if (J > 0) { // tile (I, J-1) must be finished
-          const int *flag = prog + q * lmcap + J - 1;
-          while (ld_acquire_shared(flag) <= I) __nanosleep(40);
-        }
-        process_tile<OutT>(p, g, rowpl, colpl, bsum, sx, sy, I, J, out, edges, stage, wscr, lane,
-                           Lv, cor, prog + q * lmcap + J);
+      const int TXq = quads[q].TX, TYq = quads[q].TY;
+      if (q > 0 && TXq) {
         __syncwarp();
+        for (int i = lane; i < TXq * kTile; i += 32) edges[i] = 1.0;
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int J = 0; J < TYq; ++J) {
+        const int I0 = Lm[q * lmcap + J];
+        if (I0 < TXq) run_row(q, J, I0);
+      }
+    }
+  } else {
+    // dealt to the warps in (J, quadrant) order
+    int maxTY = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) maxTY = max(maxTY, quads[q].TY);
+    int cnt = 0;
+    for (int J = 0; J < maxTY; ++J) {
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        if (J >= quads[q].TY) continue;
+        const int I0 = Lm[q * lmcap + J];
+        if (I0 >= quads[q].TX) continue; // the whole row is lit
+        if ((cnt++ & (NW - 1)) != warp) continue;
+        run_row(q, J, I0);
       }
     }
   }
