@@ -256,7 +256,7 @@ vhp_status planner_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx
   const size_t cells = (size_t)nx * ny;
   const bool vis_user = dtype == VHP_F64 && o.vis, vg_user = dtype == VHP_F64 && o.vg;
   const size_t per_prob = (vis_user ? 0 : 8 * cells) + (vg_user ? 0 : 8 * cells) +
-                          (o.came ? 0 : 4 * cells);
+                          (o.came ? 0 : 4 * cells) + 8 * cells; // + the cached heuristic field
   const size_t small_pp = 4 + 4 + 8 + 4 + 2 * (size_t)ls_cap * 8 + 32;
   int64_t chunk = nprob;
   const size_t ws_limit = (size_t)8 << 30;
@@ -268,6 +268,7 @@ vhp_status planner_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx
   auto take = [&](size_t bytes) { char *r = w; w += (bytes + 15) & ~(size_t)15; return r; };
   double *ws_vis = vis_user ? nullptr : (double *)take(8 * cells * chunk);
   double *ws_vg = vg_user ? nullptr : (double *)take(8 * cells * chunk);
+  double *ws_hc = (double *)take(8 * cells * chunk);
   int32_t *ws_came = o.came ? nullptr : (int32_t *)take(4 * cells * chunk);
   int32_t *status = o.status ? o.status : (int32_t *)take(4 * nprob);
   int32_t *nb = o.nb_sources ? o.nb_sources : (int32_t *)take(4 * nprob);
@@ -283,7 +284,7 @@ vhp_status planner_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx
     float *vg32 = (dtype == VHP_F32 && o.vg) ? (float *)o.vg + q0 * cells : nullptr;
     float *vis32 = (dtype == VHP_F32 && o.vis) ? (float *)o.vis + q0 * cells : nullptr;
     VHP_CUDA(ctx, vhp_launch_planner(ctx->tile, nx, ny, d_se + 4 * q0, d_pmap ? d_pmap + q0 : nullptr,
-                                     n, thr, max_iter, ls_cap, ctx->rcp2_table, vis, vg, came,
+                                     n, thr, max_iter, ls_cap, ctx->rcp2_table, vis, vg, ws_hc, came,
                                      status + q0, nb + q0, ls + 2 * (size_t)ls_cap * q0, plen + q0,
                                      pn + q0, path + 2 * (size_t)ls_cap * q0, vg32, vis32,
                                      ctx->d_err, ctx->stream, &ctx->launches));

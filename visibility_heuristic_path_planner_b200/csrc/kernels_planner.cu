@@ -21,6 +21,16 @@
 //      quadrant that visits the cell;
 //   3. next source = arg-min cell, ++nb_of_sources, max_iter check, end-visible
 //      test (:127-140).
+// Two exact shortcuts keep the loop cheap:
+//   * h of a cell only depends on (vg, end, parent) and the parent never changes once
+//     set (:419-423), so h is cached per cell (`hc`) and recomputed only where vg rose or
+//     the parent was just assigned; the arg-min then reads 16 bytes per cell and the
+//     push-order key is only evaluated for cells that tie or beat the running minimum.
+//   * the reference has no closed set: once the arg-min cell IS the current source it is
+//     picked again forever (same sweep -> same fields -> same h), until max_iter
+//     (SURVEY A.2 item 7).  That fixed point is detected and the remaining identical
+//     iterations are not executed: the light-source list is filled with the repeated
+//     cell and the status is VHP_MAX_ITER, exactly as the reference ends.
 // Afterwards thread 0 walks cameFrom_/lightSources_ from the end point
 // (reconstructPath) and sums the segment lengths.
 //
@@ -39,6 +49,7 @@ struct PlannerParams {
   int max_iter, ls_cap;
   // working fields, fp64, [nprob][ny][nx]
   double *vis, *vg;
+  double *hc;      // cached heuristic h per cell, +inf where the cell has no parent yet
   int32_t *came;
   // small outputs, [nprob]...
   int32_t *status, *nb, *ls, *path_n, *path;
@@ -65,7 +76,7 @@ __device__ __forceinline__ double eval_d(int ax, int ay, int bx, int by) {
 
 __global__ void __launch_bounds__(kTileWarps * 32) planner_kernel(const PlannerParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_ctl[4];              // {done, next x, next y, status}
+  __shared__ int s_ctl[5];              // {done, next x, next y, status, nb_of_sources}
   __shared__ Best s_best[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
   const int64_t q = blockIdx.x;
@@ -75,7 +86,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) planner_kernel(const PlannerP
   const int ex = p.se_xy[4 * q + 2], ey = p.se_xy[4 * q + 3];
   const int map = p.prob_map ? p.prob_map[q] : 0;
   const uint32_t *rowbits = p.fp.pl.rowF + (size_t)map * p.fp.pl.row_plane;
-  double *vis = p.vis + q * cells, *vg = p.vg + q * cells;
+  double *vis = p.vis + q * cells, *vg = p.vg + q * cells, *hc = p.hc + q * cells;
   int32_t *came = p.came + q * cells;
   int32_t *ls = p.ls + q * (size_t)p.ls_cap * 2;
   const double thr = p.thr;
@@ -83,6 +94,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) planner_kernel(const PlannerP
   // reset(): :42-60 (every sweep writes all of `vis`, border cells included)
   for (size_t c = tid; c < cells; c += blockDim.x) {
     vg[c] = 0.0;
+    hc[c] = __longlong_as_double(0x7ff0000000000000ll);
     came[c] = VHP_NO_PARENT;
   }
   if (tid == 0) {
@@ -119,30 +131,46 @@ __global__ void __launch_bounds__(kTileWarps * 32) planner_kernel(const PlannerP
       tile_sweep_cta<double, kTileWarps>(p.fp, map, sx, sy, vis, smem_raw);
       // ---- 2. per-cell epilogue + arg-min
       Best best{~0ull, ~0ull};
-      for (size_t c = tid; c < cells; c += blockDim.x) {
-        const int Y = (int)(c / nx), X = (int)(c - (size_t)Y * nx);
-        if ((X == 0 && sx > 0) || (Y == 0 && sy > 0)) continue; // never visited
-        const double v = __ldcg(vis + c);
-        const double g0 = __ldcg(vg + c);
-        const double g = v > g0 ? v : g0; // std::max(v, vg)
-        if (g != g0) vg[c] = g;
-        int cf = __ldcg(came + c);
-        if (v >= thr && cf == VHP_NO_PARENT) {
-          cf = nb;
-          came[c] = nb;
-        }
-        if (g >= thr && cf != VHP_NO_PARENT) {
-          const int px = __ldcg(ls + 2 * cf), py = __ldcg(ls + 2 * cf + 1);
-          const double h =
-              __dadd_rn(__dmul_rn(scale, g), __dadd_rn(eval_d(X, Y, ex, ey), eval_d(X, Y, px, py)));
-          const int dx = X - sx, dy = Y - sy;
-          unsigned long long qd, i, j;
-          if (dx >= 0 && dy >= 0) { qd = 0; i = dx; j = dy; }
-          else if (dx < 0 && dy >= 0) { qd = 1; i = -dx; j = dy; }
-          else if (dx <= 0 && (dx < 0 || sx >= 1)) { qd = 2; i = -dx; j = -dy; }
-          else { qd = 3; i = dx; j = -dy; }
-          const Best cand{(unsigned long long)__double_as_longlong(h), (qd << 40) | (i << 20) | j};
-          if (better(cand, best)) best = cand;
+      {
+        int X = tid % nx, Y = tid / nx; // cell c = tid + k * blockDim.x, walked incrementally
+        const int bdx = blockDim.x % nx, bdy = blockDim.x / nx;
+        for (size_t c = tid; c < cells; c += blockDim.x) {
+          const bool visited = !((X == 0 && sx > 0) || (Y == 0 && sy > 0));
+          if (visited) {
+            const double v = __ldcg(vis + c);
+            double h = __ldcg(hc + c);
+            if (v > 0.0 || thr <= 0.0) { // a dark cell cannot raise vg or gain a parent (thr > 0)
+              const double g0 = __ldcg(vg + c);
+              const double g = v > g0 ? v : g0; // std::max(v, vg)
+              if (g != g0) vg[c] = g;
+              int cf = __ldcg(came + c);
+              const bool fresh = v >= thr && cf == VHP_NO_PARENT;
+              if (fresh) {
+                cf = nb;
+                came[c] = nb;
+              }
+              if (cf != VHP_NO_PARENT && (fresh || g != g0)) { // (parent set implies vg >= thr)
+                const int px = __ldcg(ls + 2 * cf), py = __ldcg(ls + 2 * cf + 1);
+                h = __dadd_rn(__dmul_rn(scale, g),
+                              __dadd_rn(eval_d(X, Y, ex, ey), eval_d(X, Y, px, py)));
+                hc[c] = h;
+              }
+            }
+            const unsigned long long hb = (unsigned long long)__double_as_longlong(h);
+            if (hb <= best.h && hb != 0x7ff0000000000000ull) {
+              const int dx = X - sx, dy = Y - sy;
+              unsigned long long qd, i, j; // first quadrant that visits the cell, :388-564
+              if (dx >= 0 && dy >= 0) { qd = 0; i = dx; j = dy; }
+              else if (dx < 0 && dy >= 0) { qd = 1; i = -dx; j = dy; }
+              else if (dx <= 0 && (dx < 0 || sx >= 1)) { qd = 2; i = -dx; j = -dy; }
+              else { qd = 3; i = dx; j = -dy; }
+              const Best cand{hb, (qd << 40) | (i << 20) | j};
+              if (better(cand, best)) best = cand;
+            }
+          }
+          X += bdx;
+          Y += bdy;
+          if (X >= nx) { X -= nx; ++Y; }
         }
       }
 #pragma unroll
@@ -168,7 +196,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) planner_kernel(const PlannerP
           const int qd = (int)(b.key >> 40), i = (int)((b.key >> 20) & 0xFFFFF), j = (int)(b.key & 0xFFFFF);
           const int tx = (qd == 0 || qd == 3) ? sx + i : sx - i;
           const int ty = (qd < 2) ? sy + j : sy - j;
-          const int nnb = nb + 1;
+          int nnb = nb + 1;
           ls[2 * nnb] = tx;
           ls[2 * nnb + 1] = ty;
           s_ctl[1] = tx;
@@ -176,11 +204,22 @@ __global__ void __launch_bounds__(kTileWarps * 32) planner_kernel(const PlannerP
           int d = 0;
           if (nnb > p.max_iter) { d = 1; s_ctl[3] = VHP_MAX_ITER; }
           else if (!(__ldcg(vg + (size_t)ey * nx + ex) <= thr)) d = 1; // loop test :127
+          else if (tx == sx && ty == sy) {
+            // fixed point: the same source again -> every further iteration is identical
+            while (nnb <= p.max_iter) {
+              ++nnb;
+              ls[2 * nnb] = tx;
+              ls[2 * nnb + 1] = ty;
+            }
+            d = 1;
+            s_ctl[3] = VHP_MAX_ITER;
+          }
           s_ctl[0] = d;
+          s_ctl[4] = nnb;
         }
       }
       __syncthreads();
-      ++nb;
+      nb = s_ctl[4];
       sx = s_ctl[1];
       sy = s_ctl[2];
       done = s_ctl[0] != 0;
@@ -236,7 +275,8 @@ bool vhp_planner_supported(int nx, int ny) { return vhp_sweep_tile_supported(nx,
 cudaError_t vhp_launch_planner(const VhpTilePlanes &pl, int nx, int ny, const int32_t *d_se_xy,
                                const int32_t *d_prob_map, int64_t nprob, double threshold,
                                int32_t max_iter, int32_t ls_cap, const double *d_rcp2,
-                               double *d_vis, double *d_vg, int32_t *d_came, int32_t *d_status,
+                               double *d_vis, double *d_vg, double *d_hc, int32_t *d_came,
+                               int32_t *d_status,
                                int32_t *d_nb, int32_t *d_ls, double *d_path_len, int32_t *d_path_n,
                                int32_t *d_path, float *d_vg32, float *d_vis32, int *d_err,
                                cudaStream_t st, int64_t *launches) {
@@ -250,7 +290,7 @@ cudaError_t vhp_launch_planner(const VhpTilePlanes &pl, int nx, int ny, const in
   p.fp.vec = ((uintptr_t)d_vis % 16 == 0 && nx % 2 == 0) ? 1 : 0;
   p.se_xy = d_se_xy; p.prob_map = d_prob_map;
   p.thr = threshold; p.max_iter = max_iter; p.ls_cap = ls_cap;
-  p.vis = d_vis; p.vg = d_vg; p.came = d_came;
+  p.vis = d_vis; p.vg = d_vg; p.hc = d_hc; p.came = d_came;
   p.status = d_status; p.nb = d_nb; p.ls = d_ls;
   p.path_len = d_path_len; p.path_n = d_path_n; p.path = d_path;
   p.vg32 = d_vg32; p.vis32 = d_vis32;

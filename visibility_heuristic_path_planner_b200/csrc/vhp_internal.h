@@ -95,7 +95,8 @@ bool vhp_planner_supported(int nx, int ny);
 cudaError_t vhp_launch_planner(const VhpTilePlanes &pl, int nx, int ny, const int32_t *d_se_xy,
                                const int32_t *d_prob_map, int64_t nprob, double threshold,
                                int32_t max_iter, int32_t ls_cap, const double *d_rcp2,
-                               double *d_vis, double *d_vg, int32_t *d_came, int32_t *d_status,
+                               double *d_vis, double *d_vg, double *d_hc, int32_t *d_came,
+                               int32_t *d_status,
                                int32_t *d_nb, int32_t *d_ls, double *d_path_len, int32_t *d_path_n,
                                int32_t *d_path, float *d_vg32, float *d_vis32, int *d_err,
                                cudaStream_t st, int64_t *launches);
