@@ -145,6 +145,35 @@ def test_random_problems_vs_oracle(ctx, vhp, oracle):
             check(r, k, ref)
 
 
+def test_large_map_planner_vs_oracle(ctx, vhp, oracle):
+    """A map well beyond the BASELINE planner sizes (1536 x 1200, dense obstacles): the
+    single-CTA device loop against the CPU oracle, all fields bit-exact."""
+    nx, ny = 1536, 1200
+    occ = oracle.generate_environment(nx, ny, 220, 12, 90, 12, 90, 17)
+    free = np.argwhere(occ != 0)
+    s, e = free[7], free[-9]
+    se = np.array([[s[1], s[0], e[1], e[0]]], dtype=np.int32)
+    r = ctx.planner_batch(occ, se, threshold=0.3, max_iter=40)
+    ref = oracle.solve(occ, se[0][:2], se[0][2:], 0.3, 40)
+    check(r, 0, ref)
+
+
+def test_fixed_point_fast_forward_matches_reference_stall(ctx, vhp, oracle):
+    """maze_5 at the shipped threshold 0.25 re-selects the same cell
+    until max_iter.  The kernel detects the fixed point and skips the identical
+    iterations; status, nb_of_sources, the light-source list and every field must still be
+    what the reference ends with."""
+    g = load_golden("maze5.npz")
+    ny, nx = g["shape"]
+    occ = np.unpackbits(g["occ_bits"])[: ny * nx].reshape(ny, nx)
+    se = np.array([tuple(g["start"]) + tuple(g["end"])], dtype=np.int32)
+    for max_iter in (150, 197):
+        r = ctx.planner_batch(occ, se, threshold=0.25, max_iter=max_iter)
+        ref = oracle.solve(occ, se[0][:2], se[0][2:], 0.25, max_iter)
+        assert ref["status"] == 5 and ref["nb_of_sources"] == max_iter + 1
+        check(r, 0, ref)
+
+
 def test_f32_export(ctx, vhp, oracle):
     occ = oracle.generate_environment(101, 101, 10, 10, 20, 10, 20, 2)
     r64 = ctx.planner_batch(occ, [(5, 5, 95, 95)], threshold=0.25, max_iter=100, dtype=vhp.F64)

@@ -148,6 +148,30 @@ def test_large_grid_vs_naive(vhp):
     a.close(); b.close()
 
 
+def test_giant_grid_8192_vs_naive(vhp):
+    """BASELINE configs[4] size (8192 x 8192 dense random obstacles): the tile kernel's
+    boundary rows still fit shared memory (one CTA per SM); bit-identical to the naive
+    kernel, fp32 store (fp64 on chip)."""
+    n = 8192
+    g = np.random.default_rng(8192)
+    occ = np.ones((n, n), dtype=np.uint8)
+    for _ in range(6000):
+        x, y = int(g.integers(1, n)), int(g.integers(1, n))
+        w, h = int(g.integers(8, 65)), int(g.integers(8, 65))
+        occ[y:y + h, x:x + w] = 0
+    srcs = [(int(x), int(y)) for y, x in np.argwhere(occ[4000:4100, 4000:4100] != 0)[:1] + 4000] + [(0, 0)]
+    assert occ[srcs[0][1], srcs[0][0]] != 0
+    os.environ["VHP_SWEEP_IMPL"] = "naive"
+    a = vhp.Context(0)
+    os.environ.pop("VHP_SWEEP_IMPL")
+    b = vhp.Context(0)
+    ra = a.visibility_batch(occ, srcs, dtype=vhp.F32)
+    rb = b.visibility_batch(occ, srcs, dtype=vhp.F32)
+    assert np.array_equal(ra, rb)
+    assert int((rb[0] > 0.5).sum()) > 100 and float((rb[0] > 0.5).mean()) < 0.99
+    a.close(); b.close()
+
+
 def test_tile_equals_naive_full_size(vhp):
     """Size-independent property at BASELINE size: the tile kernel and the simple
     kernel agree bit-for-bit on a 64-source 1000x1000 batch."""
