@@ -58,6 +58,7 @@
 #define VHP_SWEEP_TILE_BODY_CUH
 
 #include <cstdint>
+#include <type_traits>
 
 #include "vhp_internal.h"
 #include "sweep_common.cuh"
@@ -231,6 +232,7 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
 
   // store geometry: lane <-> column il of rows j0 .. j0 + wj - 1
   const bool lane_st = lane < wi && il <= g.Ex && !(g.dirx < 0 && il == 0);
+  const bool lane_st_all = nvx == 32 && (I > 0 || g.dirx > 0); // every lane stores
   OutT *const ptr = out + (ptrdiff_t)(sy + g.diry * j0) * nx + (sx + g.dirx * il);
   const ptrdiff_t rs = (ptrdiff_t)g.diry * nx;
   const int r0 = (g.diry < 0 && j0 == 0) ? 1 : 0;   // the axis row belongs to the +y quadrant
@@ -285,17 +287,21 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
     double F = Lv;
     const int ns = min(32, g.Ex - i0 + 1);
     if (ns < 32 && lane >= ns) wnew[lane] = 0.0; // columns beyond the grid
+    auto steps = [&](auto masked) { // masked: the tile has occupied cells (or cells off the grid)
 #pragma unroll 4
-    for (int s = 0; s < ns; ++s) {
-      const double2 rr = __ldg(p.rtab + i0 + s);
-      const double up = __shfl_up_sync(kAll, F, 1);
-      const double b = lane ? up : wscr[s];
-      const double c = __fma_rn(fd, rr.x, __dmul_rn(fd, rr.y));
-      const double v = lerp_rn(F, b, c);
-      F = ((wrow >> s) & 1u) ? v : 0.0;
-      stage[lane * kStagePitch + s] = to_out<OutT>(F);
-      if (lane == wj - 1) wnew[s] = F;
-    }
+      for (int s = 0; s < ns; ++s) {
+        const double2 rr = __ldg(p.rtab + i0 + s);
+        const double up = __shfl_up_sync(kAll, F, 1);
+        const double b = lane ? up : wscr[s];
+        const double c = __fma_rn(fd, rr.x, __dmul_rn(fd, rr.y));
+        const double v = lerp_rn(F, b, c);
+        F = (!decltype(masked)::value || ((wrow >> s) & 1u)) ? v : 0.0;
+        stage[lane * kStagePitch + s] = to_out<OutT>(F);
+        if (lane == wj - 1) wnew[s] = F;
+      }
+    };
+    if (allfree && nvx == 32 && nvy == 32) steps(std::false_type{});
+    else steps(std::true_type{});
     __syncwarp();
     rowE[lane] = wnew[lane];
     Lv = F;
@@ -316,18 +322,22 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
       // ---- row-octant tile: lanes along i, steps along j (wj == 32) --------------------
       double F = Bv;
       const int ns = rlast + 1;
-      OutT *q = ptr;
+      auto steps = [&](auto masked) {
+        OutT *q = ptr;
 #pragma unroll 4
-      for (int s = 0; s < ns; ++s, q += rs) {
-        const double2 rr = __ldg(p.rtab + j0 + s);
-        const double up = __shfl_up_sync(kAll, F, 1);
-        const double b = lane ? up : lx[s];
-        const double c = __fma_rn(fd, rr.x, __dmul_rn(fd, rr.y));
-        const double v = lerp_rn(F, b, c);
-        F = ((wcol >> s) & 1u) ? v : 0.0;
-        if (lane_st) __stcs(q, to_out<OutT>(F)); // r0 == 0 here (J > 0)
-        if (lane == wi - 1) wnew[s] = F;
-      }
+        for (int s = 0; s < ns; ++s, q += rs) {
+          const double2 rr = __ldg(p.rtab + j0 + s);
+          const double up = __shfl_up_sync(kAll, F, 1);
+          const double b = lane ? up : lx[s];
+          const double c = __fma_rn(fd, rr.x, __dmul_rn(fd, rr.y));
+          const double v = lerp_rn(F, b, c);
+          F = (!decltype(masked)::value || ((wcol >> s) & 1u)) ? v : 0.0;
+          if (!decltype(masked)::value || lane_st) __stcs(q, to_out<OutT>(F)); // r0 == 0 (J > 0)
+          if (lane == wi - 1) wnew[s] = F;
+        }
+      };
+      if (allfree && nvx == 32 && nvy == 32 && lane_st_all) steps(std::false_type{});
+      else steps(std::true_type{});
       __syncwarp();
       if (lane < wi) rowE[lane] = F;
       Lv = wnew[lane];
@@ -476,10 +486,17 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
       }
       return cn[q];
     };
-    bool any_lit = false;
+    // Lm is non-increasing in J, so the lit rows of a quadrant are j < jl[q]
+    int jl[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) any_lit |= quads[q].TX && Lm[q * lmcap] > 0;
-    for (int y = warp; any_lit && y < ny; y += NW) {
+    for (int q = 0; q < 4; ++q) {
+      int Jz = 0;
+      while (Jz < quads[q].TY && Lm[q * lmcap + Jz] > 0) ++Jz;
+      jl[q] = qex[q] < 0 ? 0 : min(tile_start(qa[q], Jz), quads[q].Ey + 1);
+    }
+    // rows below the source are j = 1 .. jl - 1, rows from the source upwards j = 0 .. jl - 1
+    const int ylo = sy - max(max(jl[2], jl[3]) - 1, 0), yhi = sy + max(jl[0], jl[1]) - 1;
+    for (int y = max(ylo, 0) + warp; y <= min(yhi, ny - 1); y += NW) {
       const bool upper = y >= sy;
       const int j = upper ? y - sy : sy - y;
       const int nR = upper ? lit_run(0, j) : lit_run(3, j);
