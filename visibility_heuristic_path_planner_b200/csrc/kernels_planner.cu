@@ -36,8 +36,10 @@
 //
 // Cells the reference never visits (column 0 / row 0 unless the source lies on
 // them, loop bounds :434-438,:478-483,:522-527) get no epilogue.
+#include <cmath>
 #include <cstdint>
 
+#include "planner_common.cuh"
 #include "sweep_tile_body.cuh"
 
 namespace {
@@ -57,22 +59,6 @@ struct PlannerParams {
   // optional fp32 exports of vg / vis (NULL: none)
   float *vg32, *vis32;
 };
-
-struct Best {
-  unsigned long long h;   // IEEE bits of h (h >= 0, so the bit pattern is monotonic)
-  unsigned long long key; // quadrant << 40 | i << 20 | j  (push order)
-};
-
-__device__ __forceinline__ bool better(const Best &a, const Best &b) {
-  return a.h < b.h || (a.h == b.h && a.key < b.key);
-}
-
-__device__ __forceinline__ double eval_d(int ax, int ay, int bx, int by) {
-  // include/solver/visibilityBasedSolver.h:112-115 (all operands are exact integers)
-  const double dx = (double)(ax - bx);
-  const int dy = ay - by;
-  return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), (double)(dy * dy)));
-}
 
 __global__ void __launch_bounds__(kTileWarps * 32) planner_kernel(const PlannerParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -135,39 +121,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) planner_kernel(const PlannerP
         int X = tid % nx, Y = tid / nx; // cell c = tid + k * blockDim.x, walked incrementally
         const int bdx = blockDim.x % nx, bdy = blockDim.x / nx;
         for (size_t c = tid; c < cells; c += blockDim.x) {
-          const bool visited = !((X == 0 && sx > 0) || (Y == 0 && sy > 0));
-          if (visited) {
-            const double v = __ldcg(vis + c);
-            double h = __ldcg(hc + c);
-            if (v > 0.0 || thr <= 0.0) { // a dark cell cannot raise vg or gain a parent (thr > 0)
-              const double g0 = __ldcg(vg + c);
-              const double g = v > g0 ? v : g0; // std::max(v, vg)
-              if (g != g0) vg[c] = g;
-              int cf = __ldcg(came + c);
-              const bool fresh = v >= thr && cf == VHP_NO_PARENT;
-              if (fresh) {
-                cf = nb;
-                came[c] = nb;
-              }
-              if (cf != VHP_NO_PARENT && (fresh || g != g0)) { // (parent set implies vg >= thr)
-                const int px = __ldcg(ls + 2 * cf), py = __ldcg(ls + 2 * cf + 1);
-                h = __dadd_rn(__dmul_rn(scale, g),
-                              __dadd_rn(eval_d(X, Y, ex, ey), eval_d(X, Y, px, py)));
-                hc[c] = h;
-              }
-            }
-            const unsigned long long hb = (unsigned long long)__double_as_longlong(h);
-            if (hb <= best.h && hb != 0x7ff0000000000000ull) {
-              const int dx = X - sx, dy = Y - sy;
-              unsigned long long qd, i, j; // first quadrant that visits the cell, :388-564
-              if (dx >= 0 && dy >= 0) { qd = 0; i = dx; j = dy; }
-              else if (dx < 0 && dy >= 0) { qd = 1; i = -dx; j = dy; }
-              else if (dx <= 0 && (dx < 0 || sx >= 1)) { qd = 2; i = -dx; j = -dy; }
-              else { qd = 3; i = dx; j = -dy; }
-              const Best cand{hb, (qd << 40) | (i << 20) | j};
-              if (better(cand, best)) best = cand;
-            }
-          }
+          epilogue_cell(X, Y, c, sx, sy, ex, ey, thr, scale, nb, ls, vis, vg, hc, came, best);
           X += bdx;
           Y += bdy;
           if (X >= nx) { X -= nx; ++Y; }
@@ -268,7 +222,74 @@ __global__ void __launch_bounds__(kTileWarps * 32) planner_kernel(const PlannerP
   }
 }
 
+// ---- strip epilogue (giant-map path): the same per-cell epilogue over the rows
+// [y0, y1) one rank owns, whole GPU, then a one-CTA reduction of the per-CTA minima.
+struct StripEpilogueParams {
+  int nx, y0, y1, sx, sy, ex, ey, nb;
+  double thr, scale;
+  const int32_t *ls;
+  const double *vis;
+  double *vg, *hc;
+  int32_t *came;
+  Best *partial; // [gridDim.x]
+};
+
+__global__ void __launch_bounds__(256) strip_epilogue_kernel(const StripEpilogueParams p) {
+  __shared__ Best s_best[8];
+  const size_t cells = (size_t)(p.y1 - p.y0) * p.nx;
+  Best best{~0ull, ~0ull};
+  for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < cells;
+       c += (size_t)gridDim.x * blockDim.x) {
+    const int Yl = (int)(c / p.nx), X = (int)(c - (size_t)Yl * p.nx);
+    epilogue_cell(X, p.y0 + Yl, c, p.sx, p.sy, p.ex, p.ey, p.thr, p.scale, p.nb, p.ls, p.vis, p.vg,
+                  p.hc, p.came, best);
+  }
+  best = warp_best(best);
+  if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    Best b = threadIdx.x < 8 ? s_best[threadIdx.x] : Best{~0ull, ~0ull};
+    b = warp_best(b);
+    if (threadIdx.x == 0) p.partial[blockIdx.x] = b;
+  }
+}
+
+__global__ void __launch_bounds__(256) strip_best_kernel(const Best *partial, int n, Best *out) {
+  __shared__ Best s_best[8];
+  Best best{~0ull, ~0ull};
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (better(partial[i], best)) best = partial[i];
+  best = warp_best(best);
+  if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    Best b = threadIdx.x < 8 ? s_best[threadIdx.x] : Best{~0ull, ~0ull};
+    b = warp_best(b);
+    if (threadIdx.x == 0) *out = b;
+  }
+}
+
 } // namespace
+
+int vhp_strip_epilogue_blocks(int sm_count) { return sm_count * 8; }
+
+cudaError_t vhp_launch_strip_epilogue(int nx, int ny, int y0, int y1, int sx, int sy, int ex, int ey,
+                                      double thr, int nb, const int32_t *d_ls, const double *d_vis,
+                                      double *d_vg, double *d_hc, int32_t *d_came,
+                                      unsigned long long *d_partial, int nblocks,
+                                      unsigned long long *d_best, cudaStream_t st,
+                                      int64_t *launches) {
+  StripEpilogueParams p;
+  p.nx = nx; p.y0 = y0; p.y1 = y1; p.sx = sx; p.sy = sy; p.ex = ex; p.ey = ey; p.nb = nb;
+  p.thr = thr;
+  p.scale = std::sqrt((double)((unsigned long long)ny * ny + (unsigned long long)nx * nx)); // :49
+  p.ls = d_ls; p.vis = d_vis; p.vg = d_vg; p.hc = d_hc; p.came = d_came;
+  p.partial = reinterpret_cast<Best *>(d_partial);
+  strip_epilogue_kernel<<<nblocks, 256, 0, st>>>(p);
+  strip_best_kernel<<<1, 256, 0, st>>>(p.partial, nblocks, reinterpret_cast<Best *>(d_best));
+  if (launches) *launches += 2;
+  return cudaGetLastError();
+}
 
 bool vhp_planner_supported(int nx, int ny) { return vhp_sweep_tile_supported(nx, ny); }
 
@@ -288,6 +309,9 @@ cudaError_t vhp_launch_planner(const VhpTilePlanes &pl, int nx, int ny, const in
   p.fp.rtab = reinterpret_cast<const double2 *>(d_rcp2);
   p.fp.err = d_err;
   p.fp.vec = ((uintptr_t)d_vis % 16 == 0 && nx % 2 == 0) ? 1 : 0;
+  p.fp.win_y0 = 0;
+  p.fp.win_y1 = ny;
+  for (int q = 0; q < 4; ++q) p.fp.halo[q] = nullptr;
   p.se_xy = d_se_xy; p.prob_map = d_prob_map;
   p.thr = threshold; p.max_iter = max_iter; p.ls_cap = ls_cap;
   p.vis = d_vis; p.vg = d_vg; p.hc = d_hc; p.came = d_came;

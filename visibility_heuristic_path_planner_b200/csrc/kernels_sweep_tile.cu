@@ -31,6 +31,16 @@ sweep_tile_kernel(const TileArgs p) {
   tile_sweep_cta<OutT, NW>(p, map, sx, sy, out, smem_raw);
 }
 
+// One sweep of map 0 restricted to the grid rows [win_y0, win_y1) (strip partition):
+// p.out is the strip buffer, row win_y0 first.
+template <typename OutT>
+__global__ void __launch_bounds__(kTileWarps * 32, 1)
+sweep_window_kernel(const TileArgs p, const int sx, const int sy) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  OutT *out = reinterpret_cast<OutT *>(p.out) - (ptrdiff_t)p.win_y0 * p.nx;
+  tile_sweep_cta<OutT, kTileWarps>(p, 0, sx, sy, out, smem_raw);
+}
+
 // ---------------------------------------------------------------------------------
 // Bit planes.  wx = ceil(nx/32) + 1 words per row line, wy likewise per column line
 // (one zero word of padding so a 32-bit window may start in the last data word).
@@ -229,8 +239,53 @@ cudaError_t vhp_launch_sweep_tile(const VhpTilePlanes &pl, int nx, int ny, const
   p.err = d_err;
   const size_t esz = dtype == VHP_F32 ? 4 : 8;
   p.vec = ((uintptr_t)d_out % 16 == 0 && ((size_t)nx * esz) % 16 == 0) ? 1 : 0;
+  p.win_y0 = 0;
+  p.win_y1 = ny;
+  for (int q = 0; q < 4; ++q) p.halo[q] = nullptr;
   const cudaError_t e = dtype == VHP_F32 ? launch_tile<float>(p, npairs, st)
                                          : launch_tile<double>(p, npairs, st);
   if (launches) *launches += 1;
   return e;
+}
+
+void vhp_window_halo_rows(int nx, int ny, int sx, int sy, int y0, int y1, int32_t rows[4]) {
+  for (int q = 0; q < 4; ++q) {
+    int jw0, jw1, Jlo, Jhi, hy;
+    tile_window_of(q, nx, ny, sx, sy, y0, y1, &jw0, &jw1, &Jlo, &Jhi, &hy);
+    rows[q] = hy;
+  }
+}
+
+cudaError_t vhp_launch_sweep_window(const VhpTilePlanes &pl, int nx, int ny, int sx, int sy, int y0,
+                                    int y1, const double *const d_halo[4], vhp_dtype dtype,
+                                    void *d_out_strip, const double *d_rcp2, int *d_err,
+                                    cudaStream_t st, int64_t *launches) {
+  TileArgs p;
+  p.pl = pl;
+  p.nx = nx;
+  p.ny = ny;
+  p.src_xy = nullptr;
+  p.src_map = nullptr;
+  p.out = d_out_strip;
+  p.rtab = reinterpret_cast<const double2 *>(d_rcp2);
+  p.err = d_err;
+  const size_t esz = dtype == VHP_F32 ? 4 : 8;
+  p.vec = ((uintptr_t)d_out_strip % 16 == 0 && ((size_t)nx * esz) % 16 == 0) ? 1 : 0;
+  p.win_y0 = y0;
+  p.win_y1 = y1;
+  for (int q = 0; q < 4; ++q) p.halo[q] = d_halo ? d_halo[q] : nullptr;
+  cudaError_t e;
+  if (dtype == VHP_F32) {
+    const size_t smem = tile_smem_bytes<float>(nx, ny);
+    e = cudaFuncSetAttribute(sweep_window_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    sweep_window_kernel<float><<<1, kTileWarps * 32, smem, st>>>(p, sx, sy);
+  } else {
+    const size_t smem = tile_smem_bytes<double>(nx, ny);
+    e = cudaFuncSetAttribute(sweep_window_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    sweep_window_kernel<double><<<1, kTileWarps * 32, smem, st>>>(p, sx, sy);
+  }
+  if (launches) *launches += 1;
+  return cudaGetLastError();
 }

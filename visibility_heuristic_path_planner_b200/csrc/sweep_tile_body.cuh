@@ -54,6 +54,14 @@
 // shift of two words.  The cells the reference never writes (x == 0 in the -x
 // quadrants, y == 0 in the -y quadrants) are treated as occupied
 // and stored as 0.  Axis cells shared by two quadrants are stored by the + quadrant.
+//
+// Window mode (strip partition of one giant map over several GPUs).  A call
+// may be restricted to the grid rows [y0, y1): per quadrant only the tile rows that
+// intersect the window run, stores are clipped to the window, and the boundary row below
+// the first tile row is not the virtual 1.0 but the fp64 visibility row the neighbouring
+// strip computed (the "halo" row, one per quadrant because the -x and +x quadrants cut
+// their tile rows at different offsets).  Rows of a tile row that lie outside the window
+// are recomputed (at most 31) and not stored.
 #ifndef VHP_SWEEP_TILE_BODY_CUH
 #define VHP_SWEEP_TILE_BODY_CUH
 
@@ -79,6 +87,10 @@ struct TileArgs {
   const double2 *rtab; // {RN(1/k), RN((1 - k*rh)*rh)}
   int *err;
   int vec;             // rows are 16-byte aligned: 128-bit stores allowed
+  // window mode: rows [win_y0, win_y1) only (whole grid: 0, ny); halo[q] = the fp64
+  // visibility row (indexed by x) just below the first tile row of quadrant q, or null
+  int win_y0, win_y1;
+  const double *halo[4];
 };
 
 // geometry of one quadrant (shared memory, written once per sweep)
@@ -87,11 +99,41 @@ struct TQuad {
   int Ex, Ey;       // largest local i / j inside the grid
   int TX, TY;       // tile columns / rows (0: the quadrant does not exist)
   int rowOff;       // offset of rowE in the edge region (doubles)
-  int pad1;
   int psx, psy;     // plane coordinate of the source along x / y
   int a;            // width of the first tile row / column (1..32)
-  int pad0;
+  int jw0, jw1;     // local rows j to store (window; whole quadrant: 0, Ey)
+  int Jlo, Jhi;     // tile rows to run
 };
+
+__host__ __device__ inline int tile_row_of(const int a, const int j) {
+  return j < a ? 0 : (j - a) / kTile + 1;
+}
+
+// Window geometry of quadrant q (Q1 (+,+), Q2 (-,+), Q3 (-,-), Q4 (+,-)) for a sweep from
+// (sx, sy) restricted to rows [y0, y1): first tile row to run and the grid row whose fp64
+// visibility is its lower boundary (-1: the quadrant has no rows in the window, or starts
+// at the source).  Shared by the kernel and by the host-side exchange plan.
+__host__ __device__ inline void tile_window_of(const int q, const int nx, const int ny, const int sx,
+                                               const int sy, const int y0, const int y1, int *jw0,
+                                               int *jw1, int *Jlo, int *Jhi, int *halo_y) {
+  const int dirx = (q == 0 || q == 3) ? 1 : -1, diry = (q < 2) ? 1 : -1;
+  const int Ey = diry > 0 ? ny - 1 - sy : sy;
+  int a = dirx > 0 ? 32 - (sx & 31) : ((sx + 1) & 31);
+  if (a == 0) a = 32;
+  const bool exists = (dirx > 0 || sx > 0) && (diry > 0 || sy > 0);
+  int lo = diry > 0 ? y0 - sy : sy - (y1 - 1), hi = diry > 0 ? y1 - 1 - sy : sy - y0;
+  lo = lo < 0 ? 0 : lo;
+  hi = hi > Ey ? Ey : hi;
+  (void)nx;
+  if (!exists || lo > hi) {
+    *jw0 = 0; *jw1 = -1; *Jlo = 0; *Jhi = -1; *halo_y = -1;
+    return;
+  }
+  *jw0 = lo; *jw1 = hi;
+  *Jlo = tile_row_of(a, lo);
+  *Jhi = tile_row_of(a, hi);
+  *halo_y = *Jlo == 0 ? -1 : sy + diry * ((a + kTile * (*Jlo - 1)) - 1);
+}
 
 __host__ __device__ inline int tile_edge_doubles(int nx, int nwarps) {
   // per direction a quadrant has at most E/32 + 2 tile columns; two quadrants share each x
@@ -235,8 +277,10 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
   const bool lane_st_all = nvx == 32 && (I > 0 || g.dirx > 0); // every lane stores
   OutT *const ptr = out + (ptrdiff_t)(sy + g.diry * j0) * nx + (sx + g.dirx * il);
   const ptrdiff_t rs = (ptrdiff_t)g.diry * nx;
-  const int r0 = (g.diry < 0 && j0 == 0) ? 1 : 0;   // the axis row belongs to the +y quadrant
-  const int rlast = min(wj - 1, g.Ey - j0);          // last row inside the grid
+  // rows to store: inside the grid and the window; the axis row belongs to the +y quadrant
+  const int r0 = max((g.diry < 0 && j0 == 0) ? 1 : 0, g.jw0 - j0);
+  const int rgrid = min(wj - 1, g.Ey - j0);          // last row inside the grid
+  const int rlast = min(rgrid, g.jw1 - j0);
 
   if (allocc || zero_in || (inuni && allfree)) {
     // ---- uniform tile: no arithmetic -------------------------------------------------
@@ -247,7 +291,7 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
       cor = __shfl_sync(kAll, Bv, wi - 1);
     }
     publish();
-    const int rc = min(wj - 1, EyC - j0); // last computed row; a border row (if any) follows
+    const int rc = min(min(wj - 1, EyC - j0), rlast); // last lit row; a border row (if any) follows
     if (p.vec && nvx == 32 && (I > 0 || g.dirx > 0)) {
       // all 32 columns are stored and x0 is a multiple of 32: 128-bit stores
       constexpr int EPL = 16 / (int)sizeof(OutT), LPR = 32 / EPL; // elements per lane, lanes per row
@@ -321,7 +365,7 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
     if (J > I) {
       // ---- row-octant tile: lanes along i, steps along j (wj == 32) --------------------
       double F = Bv;
-      const int ns = rlast + 1;
+      const int ns = rgrid + 1;
       auto steps = [&](auto masked) {
         OutT *q = ptr;
 #pragma unroll 4
@@ -332,11 +376,13 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
           const double c = __fma_rn(fd, rr.x, __dmul_rn(fd, rr.y));
           const double v = lerp_rn(F, b, c);
           F = (!decltype(masked)::value || ((wcol >> s) & 1u)) ? v : 0.0;
-          if (!decltype(masked)::value || lane_st) __stcs(q, to_out<OutT>(F)); // r0 == 0 (J > 0)
+          if (!decltype(masked)::value || (lane_st && s >= r0 && s <= rlast))
+            __stcs(q, to_out<OutT>(F));
           if (lane == wi - 1) wnew[s] = F;
         }
       };
-      if (allfree && nvx == 32 && nvy == 32 && lane_st_all) steps(std::false_type{});
+      if (allfree && nvx == 32 && nvy == 32 && lane_st_all && r0 == 0 && rlast == 31)
+        steps(std::false_type{});
       else steps(std::true_type{});
       __syncwarp();
       if (lane < wi) rowE[lane] = F;
@@ -426,10 +472,11 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
       g.TY = !exists ? 0 : (g.Ey < g.a ? 1 : (g.Ey - g.a) / kTile + 2);
       g.rowOff = NW == 1 ? 0 : off;
       off += g.TX * kTile;
-      g.pad1 = 0;
       g.psx = g.dirx > 0 ? sx : WXb - 1 - sx;
       g.psy = g.diry > 0 ? sy : WYb - 1 - sy;
-      g.pad0 = 0;
+      int halo_y;
+      tile_window_of(q, nx, ny, sx, sy, p.win_y0, p.win_y1, &g.jw0, &g.jw1, &g.Jlo, &g.Jhi, &halo_y);
+      if (g.Jhi < g.Jlo) g.TX = g.TY = 0; // nothing of this quadrant inside the window
       quads[q] = g;
     }
   }
@@ -460,7 +507,15 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
     for (int J = 0; J < g.TY; ++J) {
       m = min(m, Lm[tid * lmcap + J]);
       Lm[tid * lmcap + J] = m;
-      prog[tid * lmcap + J] = m;
+      prog[tid * lmcap + J] = J < g.Jlo ? g.TX : m; // rows below the window count as finished
+    }
+  }
+  if (NW > 1) { // boundary row below the first tile row of the window = the neighbour's halo row
+    for (int q = 0; q < 4; ++q) {
+      const TQuad &g = quads[q];
+      if (g.TX && g.Jlo > 0 && p.halo[q])
+        for (int i = tid; i <= g.Ex; i += blockDim.x)
+          edges[g.rowOff + i] = __ldg(p.halo[q] + (sx + g.dirx * i));
     }
   }
   __syncthreads();
@@ -496,7 +551,7 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
     }
     // rows below the source are j = 1 .. jl - 1, rows from the source upwards j = 0 .. jl - 1
     const int ylo = sy - max(max(jl[2], jl[3]) - 1, 0), yhi = sy + max(jl[0], jl[1]) - 1;
-    for (int y = max(ylo, 0) + warp; y <= min(yhi, ny - 1); y += NW) {
+    for (int y = max(ylo, p.win_y0) + warp; y <= min(yhi, p.win_y1 - 1); y += NW) {
       const bool upper = y >= sy;
       const int j = upper ? y - sy : sy - y;
       const int nR = upper ? lit_run(0, j) : lit_run(3, j);
@@ -540,13 +595,16 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
     // the boundary row is shared, so reset it to the virtual boundary per quadrant
     for (int q = 0; q < 4; ++q) {
       const int TXq = quads[q].TX, TYq = quads[q].TY;
-      if (q > 0 && TXq) {
+      if (TXq && (q > 0 || quads[q].Jlo > 0)) {
+        const bool use_halo = quads[q].Jlo > 0 && p.halo[q];
+        const int Exq = quads[q].Ex, dxq = quads[q].dirx;
         __syncwarp();
-        for (int i = lane; i < TXq * kTile; i += 32) edges[i] = 1.0;
+        for (int i = lane; i < TXq * kTile; i += 32)
+          edges[i] = (use_halo && i <= Exq) ? __ldg(p.halo[q] + (sx + dxq * i)) : 1.0;
         __syncwarp();
       }
 #pragma unroll 1
-      for (int J = 0; J < TYq; ++J) {
+      for (int J = quads[q].Jlo; J <= quads[q].Jhi && J < TYq; ++J) {
         const int I0 = Lm[q * lmcap + J];
         if (I0 < TXq) run_row(q, J, I0);
       }
@@ -560,7 +618,7 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
     for (int J = 0; J < maxTY; ++J) {
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
-        if (J >= quads[q].TY) continue;
+        if (J >= quads[q].TY || J < quads[q].Jlo || J > quads[q].Jhi) continue;
         const int I0 = Lm[q * lmcap + J];
         if (I0 >= quads[q].TX) continue; // the whole row is lit
         if ((cnt++ & (NW - 1)) != warp) continue;

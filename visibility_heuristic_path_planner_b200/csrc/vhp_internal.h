@@ -77,6 +77,21 @@ cudaError_t vhp_launch_sweep_tile(const VhpTilePlanes &pl, int nx, int ny, const
                                   void *d_out, const double *d_rcp2, int *d_err, cudaStream_t st,
                                   int64_t *launches);
 
+// giant-map path: one sweep of map 0 restricted to the rows [y0, y1) of a strip, and the
+// planner epilogue + arg-min over a strip (whole GPU)
+void vhp_window_halo_rows(int nx, int ny, int sx, int sy, int y0, int y1, int32_t rows[4]);
+cudaError_t vhp_launch_sweep_window(const VhpTilePlanes &pl, int nx, int ny, int sx, int sy, int y0,
+                                    int y1, const double *const d_halo[4], vhp_dtype dtype,
+                                    void *d_out_strip, const double *d_rcp2, int *d_err,
+                                    cudaStream_t st, int64_t *launches);
+int vhp_strip_epilogue_blocks(int sm_count);
+cudaError_t vhp_launch_strip_epilogue(int nx, int ny, int y0, int y1, int sx, int sy, int ex, int ey,
+                                      double thr, int nb, const int32_t *d_ls, const double *d_vis,
+                                      double *d_vg, double *d_hc, int32_t *d_came,
+                                      unsigned long long *d_partial, int nblocks,
+                                      unsigned long long *d_best, cudaStream_t st,
+                                      int64_t *launches);
+
 cudaError_t vhp_launch_rcp2_table(double *d_table, int len, cudaStream_t st, int64_t *launches);
 cudaError_t vhp_launch_ratio2_selftest(const double *d_rcp2, int kmax,
                                        unsigned long long *d_mismatches, cudaStream_t st,
