@@ -172,6 +172,38 @@ vhp_status vhp_planner_batch_dev(vhp_context *ctx, const uint8_t *d_occ,
                                  int32_t ls_cap, vhp_dtype dtype,
                                  const vhp_planner_out *d_out);
 
+/* ---- e: ONE giant map, row-strip partitioned over several GPUs -------
+ * Every rank holds the whole occupancy map (its bit planes are small) and the rows
+ * [y0, y1) of the fp64 working fields.  A sweep from (sx, sy) visits the strips in order of
+ * distance from the strip that holds the source; a strip needs, per quadrant, ONE fp64
+ * visibility row of its neighbour on the source side as lower boundary (the "halo" row; the
+ * -x and +x quadrants cut their tile rows at different offsets, hence one row each):
+ *   vhp_strip_halo_rows   grid row needed per quadrant Q1..Q4 (-1: none; the quadrant
+ *                         starts at the source or has no rows in [y0, y1))
+ *   vhp_strip_sweep_dev   computeVisibility restricted to rows [y0, y1): d_halo[q] points
+ *                         at the fp64 row vhp_strip_halo_rows named (indexed by x), d_vis_strip
+ *                         is the strip buffer [(y1 - y0)][nx] of `dtype` (fp64 for the planner)
+ *   vhp_strip_epilogue_dev  the per-cell planner epilogue of updateVisibility (:417-430)
+ *                         over the strip + the strip's arg-min: d_best[0] = IEEE bits of the
+ *                         smallest h (all ones: no candidate), d_best[1] = push-order key
+ *                         quadrant << 40 | i << 20 | j relative to (sx, sy).  The global next
+ *                         source is the lexicographic minimum of (d_best[0], d_best[1]) over
+ *                         the ranks (an all-gather of 16 bytes per rank).
+ * d_h_strip caches the heuristic per cell: initialise it to +inf, d_vg_strip to 0 and
+ * d_came_strip to VHP_NO_PARENT.  visibility_heuristic_path_planner_b200/giant.py drives
+ * these calls with torch.distributed (NCCL send/recv of the halo rows, all_gather of keys). */
+void vhp_strip_halo_rows(int nx, int ny, int sx, int sy, int y0, int y1, int32_t rows[4]);
+vhp_status vhp_strip_sweep_dev(vhp_context *ctx, const uint8_t *d_occ, int nx, int ny,
+                               int sx, int sy, int y0, int y1,
+                               const double *const d_halo[4], vhp_dtype dtype,
+                               void *d_vis_strip);
+vhp_status vhp_strip_epilogue_dev(vhp_context *ctx, int nx, int ny, int y0, int y1,
+                                  int sx, int sy, int ex, int ey, double threshold,
+                                  int32_t nb, const int32_t *d_light_sources,
+                                  const double *d_vis_strip, double *d_vg_strip,
+                                  double *d_h_strip, int32_t *d_came_strip,
+                                  uint64_t *d_best);
+
 /* widen int32 parents to the reference's Field<size_t> content (host arrays) */
 void vhp_export_came_from_u64(const int32_t *came, int64_t n, uint64_t *out);
 

@@ -439,6 +439,55 @@ vhp_status vhp_selftest_ratio(vhp_context *ctx, int kmax, int64_t *mismatches) {
   return VHP_OK;
 }
 
+void vhp_strip_halo_rows(int nx, int ny, int sx, int sy, int y0, int y1, int32_t rows[4]) {
+  vhp_window_halo_rows(nx, ny, sx, sy, y0, y1, rows);
+}
+
+vhp_status vhp_strip_sweep_dev(vhp_context *ctx, const uint8_t *d_occ, int nx, int ny, int sx,
+                               int sy, int y0, int y1, const double *const d_halo[4],
+                               vhp_dtype dtype, void *d_vis_strip) {
+  if (!ctx || !d_occ || !d_vis_strip || nx < 1 || ny < 1 || y0 < 0 || y1 > ny || y0 >= y1)
+    return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_strip_sweep_dev: bad argument");
+  if (sx < 0 || sx >= nx || sy < 0 || sy >= ny)
+    return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_strip_sweep_dev: source outside the grid");
+  if (dtype != VHP_F32 && dtype != VHP_F64) return fail(ctx, VHP_ERR_INVALID_ARG, "bad dtype");
+  if (!vhp_sweep_tile_supported(nx, ny))
+    return fail(ctx, VHP_ERR_UNSUPPORTED, "vhp_strip_sweep_dev: grid too wide for the tile kernel");
+  int32_t rows[4];
+  vhp_window_halo_rows(nx, ny, sx, sy, y0, y1, rows);
+  for (int q = 0; q < 4; ++q)
+    if (rows[q] >= 0 && (!d_halo || !d_halo[q]))
+      return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_strip_sweep_dev: missing halo row");
+  VHP_CUDA(ctx, cudaSetDevice(ctx->device));
+  vhp_status st = ensure_rcp2(ctx, std::max(nx, ny) + 8);
+  if (st != VHP_OK) return st;
+  if ((st = pack_tile(ctx, d_occ, 1, nx, ny, false)) != VHP_OK) return st;
+  VHP_CUDA(ctx, vhp_launch_sweep_window(ctx->tile, nx, ny, sx, sy, y0, y1, d_halo, dtype,
+                                        d_vis_strip, ctx->rcp2_table, ctx->d_err, ctx->stream,
+                                        &ctx->launches));
+  return VHP_OK;
+}
+
+vhp_status vhp_strip_epilogue_dev(vhp_context *ctx, int nx, int ny, int y0, int y1, int sx, int sy,
+                                  int ex, int ey, double threshold, int32_t nb,
+                                  const int32_t *d_light_sources, const double *d_vis_strip,
+                                  double *d_vg_strip, double *d_h_strip, int32_t *d_came_strip,
+                                  uint64_t *d_best) {
+  if (!ctx || !d_light_sources || !d_vis_strip || !d_vg_strip || !d_h_strip || !d_came_strip ||
+      !d_best || nx < 1 || ny < 1 || y0 < 0 || y1 > ny || y0 >= y1 || nb < 0)
+    return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_strip_epilogue_dev: bad argument");
+  VHP_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int nblocks = vhp_strip_epilogue_blocks(ctx->sm_count);
+  vhp_status st = ensure(ctx, ctx->b_misc, (size_t)nblocks * 16 + 64);
+  if (st != VHP_OK) return st;
+  VHP_CUDA(ctx, vhp_launch_strip_epilogue(nx, ny, y0, y1, sx, sy, ex, ey, threshold, nb,
+                                          d_light_sources, d_vis_strip, d_vg_strip, d_h_strip,
+                                          d_came_strip, (unsigned long long *)ctx->b_misc.p,
+                                          nblocks, (unsigned long long *)d_best, ctx->stream,
+                                          &ctx->launches));
+  return VHP_OK;
+}
+
 vhp_status vhp_planner_batch_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx,
                                  int ny, const int32_t *d_se_xy, const int32_t *d_prob_map,
                                  int64_t nprob, double threshold, int32_t max_iter,
