@@ -134,35 +134,47 @@ class StripPlanner:
             self._sweep(sx, sy)
 
     def _sweep(self, sx, sy):
-        torch = self.torch
         for k, nb in sweep_schedule(self.strips, sy):
-            y0, y1 = self.strips[k]
-            rows = halo_rows(self.lib, self.nx, self.ny, sx, sy, y0, y1)
-            need = [r for r in rows if r >= 0]
-            halo = None
-            if need:
-                lo, hi = self.strips[nb]
-                assert all(lo <= r < hi for r in need), "halo row outside the neighbouring strip"
-                src_rank, dst_rank = self.owner_of[nb], self.owner_of[k]
-                if src_rank == self.rank:  # gather the rows the consumer asked for
-                    idx = torch.tensor([r - lo if r >= 0 else 0 for r in rows], device=self.dev)
-                    halo = self.f[nb]["vis"].index_select(0, idx).contiguous()
-                if src_rank != dst_rank:
-                    if self.rank == src_rank:
-                        self.dist.send(halo, dst=dst_rank)
-                        self.halo_bytes += halo.numel() * 8
-                    elif self.rank == dst_rank:
-                        halo = torch.empty((4, self.nx), dtype=torch.float64, device=self.dev)
-                        self.dist.recv(halo, src=src_rank)
-            if k not in self.f:
-                continue
-            ptrs = (C.c_void_p * 4)(*[C.c_void_p(halo[q].data_ptr()) if (halo is not None and rows[q] >= 0)
-                                      else None for q in range(4)])
-            self._check(self.lib.vhp_strip_sweep_dev(self.ctx.h, self.occ.data_ptr(), self.nx, self.ny,
-                                                     sx, sy, y0, y1, C.byref(ptrs), F64,
-                                                     self.f[k]["vis"].data_ptr()))
-            # keep `halo` alive until the kernel that reads it has been enqueued on the same stream
-            self._last_halo = halo
+            rows = halo_rows(self.lib, self.nx, self.ny, sx, sy, *self.strips[k])
+            halo = self._fetch_halo(k, nb, rows)
+            if k in self.f:
+                self._sweep_strip(k, sx, sy, rows, halo)
+
+    def _fetch_halo(self, k, nb, rows):
+        """The (4, nx) fp64 halo rows strip k needs from its source-side neighbour nb: a local
+        gather when this rank owns both, else NCCL send (owner of nb) / recv (owner of k).
+        Both sides derive `rows` from the same geometry, so no negotiation is needed."""
+        torch = self.torch
+        if nb is None or all(r < 0 for r in rows):
+            return None
+        lo, hi = self.strips[nb]
+        assert all(lo <= r < hi for r in rows if r >= 0), "halo row outside the neighbouring strip"
+        src_rank, dst_rank = self.owner_of[nb], self.owner_of[k]
+        halo = None
+        if src_rank == self.rank:
+            idx = torch.tensor([r - lo if r >= 0 else 0 for r in rows], device=self.dev)
+            halo = self.f[nb]["vis"].index_select(0, idx).contiguous()
+        if src_rank != dst_rank:
+            op = None
+            if self.rank == src_rank:
+                op = self.dist.P2POp(self.dist.isend, halo, dst_rank)
+                self.halo_bytes += halo.numel() * 8
+            elif self.rank == dst_rank:
+                halo = torch.empty((4, self.nx), dtype=torch.float64, device=self.dev)
+                op = self.dist.P2POp(self.dist.irecv, halo, src_rank)
+            if op is not None:
+                for req in self.dist.batch_isend_irecv([op]):
+                    req.wait()
+        return halo
+
+    def _sweep_strip(self, k, sx, sy, rows, halo):
+        y0, y1 = self.strips[k]
+        ptrs = (C.c_void_p * 4)(*[C.c_void_p(halo[q].data_ptr()) if (halo is not None and rows[q] >= 0)
+                                  else None for q in range(4)])
+        self._check(self.lib.vhp_strip_sweep_dev(self.ctx.h, self.occ.data_ptr(), self.nx, self.ny,
+                                                 sx, sy, y0, y1, C.byref(ptrs), F64,
+                                                 self.f[k]["vis"].data_ptr()))
+        self._last_halo = halo  # keep it alive until the kernel that reads it has been enqueued
 
     # ---- epilogue + arg-min ----------------------------------------------------------
     def epilogue(self, sx, sy, ex, ey, thr, nb, ls_dev):
