@@ -2,12 +2,14 @@
 """bench.py -- headline benchmark: batched visibility sweep on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload c2|c4]
+                    [--workload c2|c2s|c4]
 
 A "step" is one pass of the hot path (computeVisibility) over one batch of
 synthetic (map, source) pairs:
   c2 (default, BASELINE.json configs[1]): one empty 1000x1000 grid, 4096 light
       sources per GPU; output fp64-computed visibility stored as fp32.
+  c2s: the same grid and batch size with the shipped settings.config environment
+      (15 rectangles of 100-200 cells) and free-cell sources: the penumbra regime.
   c4 (configs[3] shape): 1024 random 256x256 obstacle maps x 16 sources per GPU.
 Weak scaling: every rank sweeps its own batch (independent pairs, no data-path
 collective); `value` = cells swept by all ranks / max-over-ranks device time.
@@ -48,6 +50,23 @@ def workload(name, rank, world=1):
         maps, src, _, _ = shard_batch(maps, src, None, rank, world)
         return maps, src, None, ("1000x1000 empty grid, 4096 light sources per GPU "
                                  "(global batch PCG64 seed 1234, contiguous block per rank)")
+    if name == "c2s":
+        # the headline grid with the shipped settings.config environment (15 rectangles of
+        # 100-200 cells, config/settings.config:8-14): the DP (penumbra) regime at 1000x1000
+        nx = ny = 1000
+        n = 4096
+        g = np.random.default_rng(2500 + rank)
+        maps = np.ones((1, ny, nx), dtype=np.uint8)
+        for _ in range(15):
+            x, y = int(g.integers(1, nx)), int(g.integers(1, ny))
+            w, h = int(g.integers(100, 201)), int(g.integers(100, 201))
+            maps[0, y:y + h, x:x + w] = 0
+        free = np.argwhere(maps[0] != 0)
+        pick = free[g.integers(0, len(free), n)]
+        src = np.ascontiguousarray(pick[:, ::-1]).astype(np.int32)
+        return maps, src, None, ("1000x1000 grid with the shipped settings.config environment (15 rectangles "
+                                 "100-200 cells, %.1f%% occupied), 4096 free-cell light sources per GPU"
+                                 % (100.0 * (1.0 - maps.mean())))
     if name == "c4":
         nx = ny = 256
         nmaps, per = 1024, 16
@@ -284,7 +303,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c2s", "c4"])
     ap.add_argument("--store", default="f32", choices=["f32", "f64"])
     ap.add_argument("--pairs", type=int, default=0, help="override pairs per GPU (profiling only)")
     ap.add_argument("--no-e2e", action="store_true")
