@@ -18,6 +18,9 @@ import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "lib", "libvhp_b200.so")
+# kernel-tuning experiments only (tools/build_variant.py): load another build of the same library
+if os.environ.get("VHP_LIB_VARIANT"):
+    LIB_PATH = os.path.join(PKG, "lib_" + os.environ["VHP_LIB_VARIANT"], "libvhp_b200.so")
 
 F32, F64 = 0, 1
 NO_PARENT = -1

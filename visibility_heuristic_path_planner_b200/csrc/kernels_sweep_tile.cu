@@ -10,6 +10,10 @@
 
 #include "sweep_tile_body.cuh"
 
+#ifndef VHP_NW8_MINB
+#define VHP_NW8_MINB 3 // resident 8-warp CTAs per SM the register allocation aims at
+#endif
+
 namespace {
 
 // NW warps per CTA: 8 for large grids (a pair's boundary rows take tens of KB of shared
@@ -172,7 +176,7 @@ cudaError_t launch_tile(const TileArgs &p, int64_t npairs, cudaStream_t st) {
     case 1: return launch_tile_nw<OutT, 1, 32>(p, npairs, st);
     case 2: return launch_tile_nw<OutT, 2, 12>(p, npairs, st);
     case 4: return launch_tile_nw<OutT, 4, 8>(p, npairs, st);
-    default: return launch_tile_nw<OutT, 8, 3>(p, npairs, st);
+    default: return launch_tile_nw<OutT, 8, VHP_NW8_MINB>(p, npairs, st);
   }
 }
 

@@ -71,12 +71,29 @@
 #include "vhp_internal.h"
 #include "sweep_common.cuh"
 
+// Unroll factors of the 32-step loops.  Single-warp CTAs (small-map batches: 25+ independent
+// warps per SM, each somewhere else in the code) are instruction-fetch bound beyond the
+// 32 KB L1.5 instruction cache, so they unroll less (ncu: stall_no_instruction was the top
+// stall of the 256x256 batch with 4x unrolling); multi-warp CTAs prefer the longer bodies.
+#ifndef VHP_STEP_UNROLL
+#define VHP_STEP_UNROLL 4
+#endif
+#ifndef VHP_STEP_UNROLL_1W
+#define VHP_STEP_UNROLL_1W 2
+#endif
+#ifndef VHP_DIAG_UNROLL
+#define VHP_DIAG_UNROLL 1
+#endif
+#ifndef VHP_FILL_UNROLL
+#define VHP_FILL_UNROLL 4
+#endif
+
 namespace {
 
+constexpr int kDiagUnroll = VHP_DIAG_UNROLL, kFillUnroll = VHP_FILL_UNROLL;
 constexpr int kTileWarps = 8;          // warps per CTA (default; small maps use fewer)
 constexpr int kTile = 32;              // tile side
-constexpr int kStagePitch = 33;        // staging tile pitch (elements)
-constexpr int kWarpScratch = 104;      // doubles per warp: bottom stream [33], left stream [33], new edge [32]
+constexpr int kWarpScratch = 72;       // doubles per warp: bottom stream [33] (row-octant tiles: new left column), left stream [33]
 constexpr unsigned kAll = 0xffffffffu;
 
 struct TileArgs {
@@ -155,7 +172,7 @@ template <typename OutT>
 __host__ __device__ inline size_t tile_smem_bytes(int nx, int ny, int nwarps = kTileWarps) {
   return 256 + tile_sum_bytes(nx, ny) + 32 * (size_t)tile_lm_cap(ny) +
          sizeof(double) * (size_t)tile_edge_doubles(nx, nwarps) +
-         (size_t)nwarps * (kTile * kStagePitch * sizeof(OutT) + kWarpScratch * sizeof(double));
+         (size_t)nwarps * (kTile * kTile * sizeof(OutT) + kWarpScratch * sizeof(double));
 }
 
 // 16-byte streaming store of one value replicated
@@ -165,6 +182,10 @@ __device__ __forceinline__ void stg16_fill(float *q, float v) {
 __device__ __forceinline__ void stg16_fill(double *q, double v) {
   __stcs(reinterpret_cast<double2 *>(q), make_double2(v, v));
 }
+
+// staging tile: element (row r, column c) of a 32 x 32 tile, XOR-swizzled so that both the
+// column-wise writes of the column-octant steps and the row-wise read-out are conflict-free
+__device__ __forceinline__ int stage_at(const int r, const int c) { return r * kTile + ((c ^ r) & 31); }
 
 // first local index and extent of tile column / row T
 __device__ __forceinline__ int tile_start(const int a, const int T) {
@@ -222,7 +243,7 @@ __device__ __forceinline__ void st_release_shared(int *a, int v) {
 
 // One tile (I, J) of quadrant g by one warp.  Lv (lane r: q(i0-1, j0+r)) and cor
 // (q(i0-1, j0-1)) are the left inputs; on return they hold the same for tile (I+1, J).
-template <typename OutT>
+template <typename OutT, int NW>
 __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
                                              const uint32_t *__restrict__ rowpl,
                                              const uint32_t *__restrict__ colpl,
@@ -233,6 +254,7 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
                                              double &Lv, double &cor, int *done_flag) {
   // the row above may start its tile I as soon as rowE holds this tile's top row: publish
   // before the global stores
+  constexpr int kStepUnroll = NW == 1 ? VHP_STEP_UNROLL_1W : VHP_STEP_UNROLL;
   auto publish = [&]() {
     __syncwarp();
     if (lane == 0) st_release_shared(done_flag, I + 1);
@@ -299,7 +321,7 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
       const int xlow = g.dirx > 0 ? sx + i0 : sx - i0 - 31;
       const OutT v = to_out<OutT>(zero ? 0.0 : cor);
       OutT *q = out + (ptrdiff_t)(sy + g.diry * (j0 + r0 + sub)) * nx + (xlow + (lane % LPR) * EPL);
-#pragma unroll 4
+#pragma unroll kFillUnroll
       for (int r = r0 + sub; r <= rc; r += EPL, q += EPL * rs) stg16_fill(q, v);
       if (rc < rlast && sub == 0)
         stg16_fill(out + (ptrdiff_t)(sy + g.diry * (j0 + rlast)) * nx + (xlow + (lane % LPR) * EPL),
@@ -307,7 +329,7 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
     } else if (lane_st) {
       const OutT lv = to_out<OutT>((zero || !colc) ? 0.0 : cor);
       OutT *q = ptr + r0 * rs;
-#pragma unroll 4
+#pragma unroll kFillUnroll
       for (int r = r0; r <= rc; ++r, q += rs) __stcs(q, lv);
       if (rc < rlast) __stcs(ptr + rlast * rs, (OutT)0);
     }
@@ -315,7 +337,8 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
   }
 
   const double fd = (double)(I > J ? jr : il); // offset along the front (i0 == j0 on the diagonal)
-  double *lx = wscr + 33, *wnew = wscr + 66;       // wscr: bottom stream, lx: left stream
+  double *lx = wscr + 34, *wnew = wscr; // wscr: bottom stream, lx: left stream; wnew (row-octant tiles
+                                        // only, which never read wscr): the new left column
   const double cor_next = __shfl_sync(kAll, Bv, wi - 1);
   __syncwarp();
   wscr[1 + lane] = Bv;
@@ -330,24 +353,26 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
     // ---- column-octant tile: lanes along j, steps along i (wi == 32) -------------------
     double F = Lv;
     const int ns = min(32, g.Ex - i0 + 1);
-    if (ns < 32 && lane >= ns) wnew[lane] = 0.0; // columns beyond the grid
+    // this tile's bottom inputs are in wscr by now: its top row goes straight into rowE
+    if (ns < 32 && lane >= ns) rowE[lane] = 0.0; // columns beyond the grid
+    const double2 *const tab = p.rtab + i0;
     auto steps = [&](auto masked) { // masked: the tile has occupied cells (or cells off the grid)
-#pragma unroll 4
+      double2 rn = __ldg(tab); // 1/i of the next step, fetched one step ahead
+#pragma unroll kStepUnroll
       for (int s = 0; s < ns; ++s) {
-        const double2 rr = __ldg(p.rtab + i0 + s);
+        const double2 rr = rn;
+        rn = __ldg(tab + s + 1);
         const double up = __shfl_up_sync(kAll, F, 1);
         const double b = lane ? up : wscr[s];
         const double c = __fma_rn(fd, rr.x, __dmul_rn(fd, rr.y));
         const double v = lerp_rn(F, b, c);
         F = (!decltype(masked)::value || ((wrow >> s) & 1u)) ? v : 0.0;
-        stage[lane * kStagePitch + s] = to_out<OutT>(F);
-        if (lane == wj - 1) wnew[s] = F;
+        stage[stage_at(lane, s)] = to_out<OutT>(F);
+        if (lane == wj - 1) rowE[s] = F;
       }
     };
     if (allfree && nvx == 32 && nvy == 32) steps(std::false_type{});
     else steps(std::true_type{});
-    __syncwarp();
-    rowE[lane] = wnew[lane];
     Lv = F;
     publish();
   } else {
@@ -366,11 +391,14 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
       // ---- row-octant tile: lanes along i, steps along j (wj == 32) --------------------
       double F = Bv;
       const int ns = rgrid + 1;
+      const double2 *const tab = p.rtab + j0;
       auto steps = [&](auto masked) {
         OutT *q = ptr;
-#pragma unroll 4
+        double2 rn = __ldg(tab);
+#pragma unroll kStepUnroll
         for (int s = 0; s < ns; ++s, q += rs) {
-          const double2 rr = __ldg(p.rtab + j0 + s);
+          const double2 rr = rn;
+          rn = __ldg(tab + s + 1);
           const double up = __shfl_up_sync(kAll, F, 1);
           const double b = lane ? up : lx[s];
           const double c = __fma_rn(fd, rr.x, __dmul_rn(fd, rr.y));
@@ -394,9 +422,12 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
     // ---- diagonal tile: both fronts and the diagonal cell (wi == wj) ---------------------
     double C = 0.0, R = 0.0; // C[l] = q(k-1, j0+l), R[l] = q(i0+l, k-1); set when lane l joins
     const int ns = min(wi, max(g.Ex, g.Ey) - i0 + 1);
-#pragma unroll 2
+    const double2 *const tab = p.rtab + i0;
+    double2 rn = __ldg(tab);
+#pragma unroll kDiagUnroll
     for (int k = 0; k < ns; ++k) {
-      const double2 rr = __ldg(p.rtab + i0 + k);
+      const double2 rr = rn;
+      rn = __ldg(tab + k + 1);
       const double c = __fma_rn(fd, rr.x, __dmul_rn(fd, rr.y));
       const double upC = __shfl_up_sync(kAll, C, 1);
       const double upR = __shfl_up_sync(kAll, R, 1);
@@ -406,8 +437,8 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
       if (lane < k) {
         C = ((wrow >> k) & 1u) ? vC : 0.0;
         R = ((wcol >> k) & 1u) ? vR : 0.0;
-        stage[lane * kStagePitch + k] = to_out<OutT>(C);
-        stage[k * kStagePitch + lane] = to_out<OutT>(R);
+        stage[stage_at(lane, k)] = to_out<OutT>(C);
+        stage[stage_at(k, lane)] = to_out<OutT>(R);
       }
       // diagonal cell q(k,k) = q(k,k-1) * occ: q(k,k-1) is lane k-1's new C (k == 0: B[0])
       const double dsrc = __shfl_up_sync(kAll, C, 1);
@@ -415,7 +446,7 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
         const double dv = ((wrow >> k) & 1u) ? (k ? dsrc : Bv) : 0.0;
         C = dv;
         R = dv;
-        stage[k * kStagePitch + k] = to_out<OutT>(dv);
+        stage[stage_at(k, k)] = to_out<OutT>(dv);
       }
     }
     __syncwarp();
@@ -428,8 +459,8 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
   __syncwarp();
   if (lane_st) {
     OutT *q = ptr + r0 * rs;
-#pragma unroll 4
-    for (int r = r0; r <= rlast; ++r, q += rs) __stcs(q, stage[r * kStagePitch + lane]);
+#pragma unroll kFillUnroll
+    for (int r = r0; r <= rlast; ++r, q += rs) __stcs(q, stage[stage_at(r, lane)]);
   }
 }
 
@@ -443,6 +474,8 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nx = p.nx, ny = p.ny;
   TQuad *quads = reinterpret_cast<TQuad *>(smem_raw);
+  int *next_row = reinterpret_cast<int *>(smem_raw + 240); // next tile row to hand out (NW > 1)
+  static_assert(4 * sizeof(TQuad) <= 240, "quadrant geometry overlaps the row counter");
   uint32_t *bsum = reinterpret_cast<uint32_t *>(smem_raw + 256);
   const int nsum = tile_sum_words(nx) * ((ny + 31) >> 5);
   const int lmcap = tile_lm_cap(ny);
@@ -453,9 +486,10 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
   unsigned char *wbase = reinterpret_cast<unsigned char *>(edges + nedge);
   double *wscr = reinterpret_cast<double *>(wbase) + warp * kWarpScratch;
   OutT *stage = reinterpret_cast<OutT *>(wbase + NW * kWarpScratch * sizeof(double)) +
-                warp * (kTile * kStagePitch);
+                warp * (kTile * kTile);
 
   if (tid == 0) {
+    *next_row = 0;
     const int WXb = 32 * ((nx + 31) >> 5), WYb = 32 * ((ny + 31) >> 5);
     int off = 0;
     for (int q = 0; q < 4; ++q) { // Q1 (+,+), Q2 (-,+), Q3 (-,-), Q4 (+,-): reference order
@@ -585,7 +619,7 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
         const int *flag = prog + q * lmcap + J - 1;
         while (ld_acquire_shared(flag) <= I) __nanosleep(40);
       }
-      process_tile<OutT>(p, g, rowpl, colpl, bsum, sx, sy, I, J, out, edges, stage, wscr, lane, Lv,
+      process_tile<OutT, NW>(p, g, rowpl, colpl, bsum, sx, sy, I, J, out, edges, stage, wscr, lane, Lv,
                          cor, prog + q * lmcap + J);
       __syncwarp();
     }
@@ -610,20 +644,22 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
       }
     }
   } else {
-    // dealt to the warps in (J, quadrant) order
+    // a warp that finishes a row takes the next one in (J, quadrant) order from a shared
+    // counter: a row only waits for the row below it, which was taken earlier
     int maxTY = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) maxTY = max(maxTY, quads[q].TY);
-    int cnt = 0;
-    for (int J = 0; J < maxTY; ++J) {
 #pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        if (J >= quads[q].TY || J < quads[q].Jlo || J > quads[q].Jhi) continue;
-        const int I0 = Lm[q * lmcap + J];
-        if (I0 >= quads[q].TX) continue; // the whole row is lit
-        if ((cnt++ & (NW - 1)) != warp) continue;
-        run_row(q, J, I0);
-      }
+    for (;;) {
+      int c = 0;
+      if (lane == 0) c = atomicAdd(next_row, 1);
+      c = __shfl_sync(kAll, c, 0);
+      if (c >= 4 * maxTY) break;
+      const int J = c >> 2, q = c & 3;
+      if (J >= quads[q].TY || J < quads[q].Jlo || J > quads[q].Jhi) continue;
+      const int I0 = Lm[q * lmcap + J];
+      if (I0 >= quads[q].TX) continue; // the whole row is lit
+      run_row(q, J, I0);
     }
   }
   __syncthreads();
