@@ -143,7 +143,7 @@ vhp_status run_dev(vhp_context *ctx, Op op, const uint8_t *d_occ, int nmaps, int
   }
   const size_t esz = dtype == VHP_F32 ? 4 : 8;
   if (ctx->sweep_impl == 0 && vhp_sweep_tile_supported(nx, ny)) {
-    vhp_status st = ensure_rcp2(ctx, std::max(nx, ny) + 8);
+    vhp_status st = ensure_rcp2(ctx, std::max(nx, ny) + 64);
     if (st != VHP_OK) return st;
     if ((st = pack_tile(ctx, d_occ, nmaps, nx, ny, false)) != VHP_OK) return st;
     VHP_CUDA(ctx, vhp_launch_sweep_tile(ctx->tile, nx, ny, d_xy, d_map, n, dtype, d_out,
@@ -250,7 +250,7 @@ vhp_status planner_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx
     return fail(ctx, VHP_ERR_UNSUPPORTED, "planner: grid too large for the single-CTA kernel");
   if (ls_cap < max_iter + 2 || max_iter < 0)
     return fail(ctx, VHP_ERR_INVALID_ARG, "planner: ls_cap must be >= max_iter + 2");
-  vhp_status st = ensure_rcp2(ctx, std::max(nx, ny) + 8);
+  vhp_status st = ensure_rcp2(ctx, std::max(nx, ny) + 64);
   if (st != VHP_OK) return st;
   if ((st = pack_tile(ctx, d_occ, nmaps, nx, ny, false)) != VHP_OK) return st;
   const size_t cells = (size_t)nx * ny;
@@ -459,7 +459,7 @@ vhp_status vhp_strip_sweep_dev(vhp_context *ctx, const uint8_t *d_occ, int nx, i
     if (rows[q] >= 0 && (!d_halo || !d_halo[q]))
       return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_strip_sweep_dev: missing halo row");
   VHP_CUDA(ctx, cudaSetDevice(ctx->device));
-  vhp_status st = ensure_rcp2(ctx, std::max(nx, ny) + 8);
+  vhp_status st = ensure_rcp2(ctx, std::max(nx, ny) + 64);
   if (st != VHP_OK) return st;
   if ((st = pack_tile(ctx, d_occ, 1, nx, ny, false)) != VHP_OK) return st;
   VHP_CUDA(ctx, vhp_launch_sweep_window(ctx->tile, nx, ny, sx, sy, y0, y1, d_halo, dtype,

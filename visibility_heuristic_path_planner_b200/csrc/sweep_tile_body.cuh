@@ -93,7 +93,8 @@ namespace {
 constexpr int kDiagUnroll = VHP_DIAG_UNROLL, kFillUnroll = VHP_FILL_UNROLL;
 constexpr int kTileWarps = 8;          // warps per CTA (default; small maps use fewer)
 constexpr int kTile = 32;              // tile side
-constexpr int kWarpScratch = 72;       // doubles per warp: bottom stream [33] (row-octant tiles: new left column), left stream [33]
+constexpr int kWarpScratch = 136;      // doubles per warp: bottom stream [34] (row-octant tiles: new left
+                                       // column), left stream [34], 1/k table of the tile [33 x double2]
 constexpr unsigned kAll = 0xffffffffu;
 
 struct TileArgs {
@@ -241,14 +242,53 @@ __device__ __forceinline__ void st_release_shared(int *a, int v) {
                :: "r"((uint32_t)__cvta_generic_to_shared(a)), "r"(v) : "memory");
 }
 
+// What a tile needs from global memory, fetched while the previous tile of the row is still
+// being computed (the loads are L2 hits of a few hundred cycles; issued at the head of the
+// tile they were the first thing on its critical path): the block-summary verdict and,
+// where the summary does not prove the tile free, the raw occupancy words of this lane's
+// row (bit plane along x) and column (bit plane along y; diagonal and row-octant tiles).
+struct TilePre {
+  uint32_t r0, r1, c0, c1;
+  int sumfree;
+};
+
+__device__ __forceinline__ TilePre tile_prefetch(const TileArgs &p, const TQuad &g,
+                                                 const uint32_t *__restrict__ rowpl,
+                                                 const uint32_t *__restrict__ colpl,
+                                                 const uint32_t *__restrict__ bsum, const int sx,
+                                                 const int sy, const int I, const int J,
+                                                 const int lane) {
+  TilePre t;
+  t.r0 = t.r1 = t.c0 = t.c1 = 0u;
+  t.sumfree = 0;
+  const int wi = I ? kTile : g.a, wj = J ? kTile : g.a;
+  const int i0 = tile_start(g.a, I), j0 = tile_start(g.a, J);
+  const int nvx = min(wi, g.Ex - (g.dirx < 0) - i0 + 1), nvy = min(wj, g.Ey - (g.diry < 0) - j0 + 1);
+  if (nvx > 0 && nvy > 0) {
+    t.sumfree = tile_sum_free(g, bsum, tile_sum_words(p.nx), sx, sy, I, J);
+    if (!t.sumfree) {
+      if (lane < nvy) { // row j0 + lane, bit b <-> local column i0 + b
+        const uint32_t *rp =
+            rowpl + (size_t)(sy + g.diry * (j0 + lane)) * p.pl.wx + ((g.psx + i0) >> 5);
+        t.r0 = __ldg(rp);
+        t.r1 = __ldg(rp + 1);
+      }
+      if (J >= I && lane < nvx) { // column i0 + lane, bit b <-> local row j0 + b
+        const uint32_t *cp =
+            colpl + (size_t)(sx + g.dirx * (i0 + lane)) * p.pl.wy + ((g.psy + j0) >> 5);
+        t.c0 = __ldg(cp);
+        t.c1 = __ldg(cp + 1);
+      }
+    }
+  }
+  return t;
+}
+
 // One tile (I, J) of quadrant g by one warp.  Lv (lane r: q(i0-1, j0+r)) and cor
 // (q(i0-1, j0-1)) are the left inputs; on return they hold the same for tile (I+1, J).
 template <typename OutT, int NW>
-__device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
-                                             const uint32_t *__restrict__ rowpl,
-                                             const uint32_t *__restrict__ colpl,
-                                             const uint32_t *__restrict__ bsum, const int sx,
-                                             const int sy, const int I, const int J,
+__device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, const TilePre &pre,
+                                             const int sx, const int sy, const int I, const int J,
                                              OutT *__restrict__ out, double *edges,
                                              OutT *stage, double *wscr, const int lane,
                                              double &Lv, double &cor, int *done_flag) {
@@ -270,22 +310,21 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
   const uint32_t rmask = nvy >= 32 ? ~0u : (nvy <= 0 ? 0u : (1u << nvy) - 1u);
   const bool colc = (cmask >> lane) & 1u, rowc = (rmask >> lane) & 1u;
   double *rowE = edges + g.rowOff + i0;
+  // 1/k of the 32 steps of this tile (k = i in column-octant and diagonal tiles, j in
+  // row-octant tiles): one coalesced load here, parked in shared memory if the tile computes
+  const double2 myr = __ldg(p.rtab + max(i0, j0) + lane);
 
   // ---- occupancy: block summary first, bit plane otherwise --------------------------
-  bool allfree = false, allocc = true, sumfree = false;
+  bool allfree = false, allocc = true;
+  const bool sumfree = pre.sumfree != 0;
   uint32_t wrow = 0;
   if (nvx > 0 && nvy > 0) {
-    sumfree = tile_sum_free(g, bsum, tile_sum_words(nx), sx, sy, I, J);
     if (sumfree) {
       wrow = rowc ? cmask : 0u;
       allfree = true;
       allocc = false;
     } else {
-      if (rowc) { // occupancy of row jr, bit b <-> local column i0 + b
-        const int p0 = g.psx + i0;
-        const uint32_t *rp = rowpl + (size_t)(sy + g.diry * jr) * p.pl.wx + (p0 >> 5);
-        wrow = __funnelshift_r(__ldg(rp), __ldg(rp + 1), p0 & 31) & cmask;
-      }
+      if (rowc) wrow = __funnelshift_r(pre.r0, pre.r1, (g.psx + i0) & 31) & cmask;
       allfree = __all_sync(kAll, wrow == (rowc ? cmask : 0u));
       allocc = __all_sync(kAll, wrow == 0u);
     }
@@ -339,10 +378,12 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
   const double fd = (double)(I > J ? jr : il); // offset along the front (i0 == j0 on the diagonal)
   double *lx = wscr + 34, *wnew = wscr; // wscr: bottom stream, lx: left stream; wnew (row-octant tiles
                                         // only, which never read wscr): the new left column
+  double2 *const rts = reinterpret_cast<double2 *>(wscr + 68); // 1/k of step s (entry 32: never used)
   const double cor_next = __shfl_sync(kAll, Bv, wi - 1);
   __syncwarp();
   wscr[1 + lane] = Bv;
   lx[1 + lane] = Lv;
+  rts[lane] = myr;
   if (lane == 0) {
     wscr[0] = cor;
     lx[0] = cor;
@@ -355,13 +396,12 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
     const int ns = min(32, g.Ex - i0 + 1);
     // this tile's bottom inputs are in wscr by now: its top row goes straight into rowE
     if (ns < 32 && lane >= ns) rowE[lane] = 0.0; // columns beyond the grid
-    const double2 *const tab = p.rtab + i0;
     auto steps = [&](auto masked) { // masked: the tile has occupied cells (or cells off the grid)
-      double2 rn = __ldg(tab); // 1/i of the next step, fetched one step ahead
+      double2 rn = rts[0]; // 1/i of the next step, read one step ahead
 #pragma unroll kStepUnroll
       for (int s = 0; s < ns; ++s) {
         const double2 rr = rn;
-        rn = __ldg(tab + s + 1);
+        rn = rts[s + 1];
         const double up = __shfl_up_sync(kAll, F, 1);
         const double b = lane ? up : wscr[s];
         const double c = __fma_rn(fd, rr.x, __dmul_rn(fd, rr.y));
@@ -379,26 +419,19 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
     // occupancy of column il, bit b <-> local row j0 + b
     uint32_t wcol = 0;
     if (colc) {
-      if (sumfree) {
-        wcol = rmask;
-      } else {
-        const int q0 = g.psy + j0;
-        const uint32_t *cp = colpl + (size_t)(sx + g.dirx * il) * p.pl.wy + (q0 >> 5);
-        wcol = __funnelshift_r(__ldg(cp), __ldg(cp + 1), q0 & 31) & rmask;
-      }
+      wcol = sumfree ? rmask : (__funnelshift_r(pre.c0, pre.c1, (g.psy + j0) & 31) & rmask);
     }
     if (J > I) {
       // ---- row-octant tile: lanes along i, steps along j (wj == 32) --------------------
       double F = Bv;
       const int ns = rgrid + 1;
-      const double2 *const tab = p.rtab + j0;
       auto steps = [&](auto masked) {
         OutT *q = ptr;
-        double2 rn = __ldg(tab);
+        double2 rn = rts[0];
 #pragma unroll kStepUnroll
         for (int s = 0; s < ns; ++s, q += rs) {
           const double2 rr = rn;
-          rn = __ldg(tab + s + 1);
+          rn = rts[s + 1];
           const double up = __shfl_up_sync(kAll, F, 1);
           const double b = lane ? up : lx[s];
           const double c = __fma_rn(fd, rr.x, __dmul_rn(fd, rr.y));
@@ -422,12 +455,11 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g,
     // ---- diagonal tile: both fronts and the diagonal cell (wi == wj) ---------------------
     double C = 0.0, R = 0.0; // C[l] = q(k-1, j0+l), R[l] = q(i0+l, k-1); set when lane l joins
     const int ns = min(wi, max(g.Ex, g.Ey) - i0 + 1);
-    const double2 *const tab = p.rtab + i0;
-    double2 rn = __ldg(tab);
+    double2 rn = rts[0];
 #pragma unroll kDiagUnroll
     for (int k = 0; k < ns; ++k) {
       const double2 rr = rn;
-      rn = __ldg(tab + k + 1);
+      rn = rts[k + 1];
       const double c = __fma_rn(fd, rr.x, __dmul_rn(fd, rr.y));
       const double upC = __shfl_up_sync(kAll, C, 1);
       const double upR = __shfl_up_sync(kAll, R, 1);
@@ -613,14 +645,17 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
     const uint32_t *rowpl = (g.dirx > 0 ? p.pl.rowF : p.pl.rowR) + (size_t)map * p.pl.row_plane;
     const uint32_t *colpl = (g.diry > 0 ? p.pl.colF : p.pl.colR) + (size_t)map * p.pl.col_plane;
     double Lv = 1.0, cor = 1.0; // left of the first tile: lit tiles or the virtual boundary
+    TilePre pre = tile_prefetch(p, g, rowpl, colpl, bsum, sx, sy, I0, J, lane);
 #pragma unroll 1
     for (int I = I0; I < g.TX; ++I) {
+      const TilePre cur = pre;
+      if (I + 1 < g.TX) pre = tile_prefetch(p, g, rowpl, colpl, bsum, sx, sy, I + 1, J, lane);
       if (NW > 1 && J > 0) { // tile (I, J-1) must be finished
         const int *flag = prog + q * lmcap + J - 1;
         while (ld_acquire_shared(flag) <= I) __nanosleep(40);
       }
-      process_tile<OutT, NW>(p, g, rowpl, colpl, bsum, sx, sy, I, J, out, edges, stage, wscr, lane, Lv,
-                         cor, prog + q * lmcap + J);
+      process_tile<OutT, NW>(p, g, cur, sx, sy, I, J, out, edges, stage, wscr, lane, Lv, cor,
+                             prog + q * lmcap + J);
       __syncwarp();
     }
   };
