@@ -165,7 +165,7 @@ int tile_warps_for(int nx, int ny, int64_t npairs) {
     const char *e = std::getenv("VHP_TILE_WARPS");
     return e ? std::atoi(e) : 0;
   }();
-  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced;
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 6 || forced == 8) return forced;
   if (std::max(nx, ny) > 512) return 8;
   return npairs >= 148 * 16 ? 1 : 4; // enough pairs to fill the SMs with single-warp CTAs?
 }
@@ -176,6 +176,7 @@ cudaError_t launch_tile(const TileArgs &p, int64_t npairs, cudaStream_t st) {
     case 1: return launch_tile_nw<OutT, 1, 32>(p, npairs, st);
     case 2: return launch_tile_nw<OutT, 2, 12>(p, npairs, st);
     case 4: return launch_tile_nw<OutT, 4, 8>(p, npairs, st);
+    case 6: return launch_tile_nw<OutT, 6, 4>(p, npairs, st);
     default: return launch_tile_nw<OutT, 8, VHP_NW8_MINB>(p, npairs, st);
   }
 }

@@ -81,6 +81,9 @@
 #ifndef VHP_STEP_UNROLL_1W
 #define VHP_STEP_UNROLL_1W 2
 #endif
+#ifndef VHP_POLL_BACKOFF
+#define VHP_POLL_BACKOFF 1
+#endif
 #ifndef VHP_DIAG_UNROLL
 #define VHP_DIAG_UNROLL 1
 #endif
@@ -93,6 +96,7 @@ namespace {
 constexpr int kDiagUnroll = VHP_DIAG_UNROLL, kFillUnroll = VHP_FILL_UNROLL;
 constexpr int kTileWarps = 8;          // warps per CTA (default; small maps use fewer)
 constexpr int kTile = 32;              // tile side
+constexpr int kStagePitch = 33;        // staging tile pitch (elements)
 constexpr int kWarpScratch = 136;      // doubles per warp: bottom stream [34] (row-octant tiles: new left
                                        // column), left stream [34], 1/k table of the tile [33 x double2]
 constexpr unsigned kAll = 0xffffffffu;
@@ -173,7 +177,7 @@ template <typename OutT>
 __host__ __device__ inline size_t tile_smem_bytes(int nx, int ny, int nwarps = kTileWarps) {
   return 256 + tile_sum_bytes(nx, ny) + 32 * (size_t)tile_lm_cap(ny) +
          sizeof(double) * (size_t)tile_edge_doubles(nx, nwarps) +
-         (size_t)nwarps * (kTile * kTile * sizeof(OutT) + kWarpScratch * sizeof(double));
+         (size_t)nwarps * (kTile * kStagePitch * sizeof(OutT) + kWarpScratch * sizeof(double));
 }
 
 // 16-byte streaming store of one value replicated
@@ -184,9 +188,9 @@ __device__ __forceinline__ void stg16_fill(double *q, double v) {
   __stcs(reinterpret_cast<double2 *>(q), make_double2(v, v));
 }
 
-// staging tile: element (row r, column c) of a 32 x 32 tile, XOR-swizzled so that both the
-// column-wise writes of the column-octant steps and the row-wise read-out are conflict-free
-__device__ __forceinline__ int stage_at(const int r, const int c) { return r * kTile + ((c ^ r) & 31); }
+// staging tile: element (row r, column c) of a 32 x 32 tile (odd pitch: column-wise writes
+// and the row-wise read-out are both conflict-free)
+__device__ __forceinline__ int stage_at(const int r, const int c) { return r * kStagePitch + c; }
 
 // first local index and extent of tile column / row T
 __device__ __forceinline__ int tile_start(const int a, const int T) {
@@ -407,6 +411,8 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
         const double c = __fma_rn(fd, rr.x, __dmul_rn(fd, rr.y));
         const double v = lerp_rn(F, b, c);
         F = (!decltype(masked)::value || ((wrow >> s) & 1u)) ? v : 0.0;
+        // (storing this lane's row straight from registers, 16 bytes every few steps, was
+        // measured slower than staging: 32 partial-sector requests per store instruction)
         stage[stage_at(lane, s)] = to_out<OutT>(F);
         if (lane == wj - 1) rowE[s] = F;
       }
@@ -518,7 +524,7 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
   unsigned char *wbase = reinterpret_cast<unsigned char *>(edges + nedge);
   double *wscr = reinterpret_cast<double *>(wbase) + warp * kWarpScratch;
   OutT *stage = reinterpret_cast<OutT *>(wbase + NW * kWarpScratch * sizeof(double)) +
-                warp * (kTile * kTile);
+                warp * (kTile * kStagePitch);
 
   if (tid == 0) {
     *next_row = 0;
@@ -652,7 +658,11 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
       if (I + 1 < g.TX) pre = tile_prefetch(p, g, rowpl, colpl, bsum, sx, sy, I + 1, J, lane);
       if (NW > 1 && J > 0) { // tile (I, J-1) must be finished
         const int *flag = prog + q * lmcap + J - 1;
+#if VHP_POLL_BACKOFF
+        for (unsigned ns = 32; ld_acquire_shared(flag) <= I; ns = min(2 * ns, 256u)) __nanosleep(ns);
+#else
         while (ld_acquire_shared(flag) <= I) __nanosleep(40);
+#endif
       }
       process_tile<OutT, NW>(p, g, cur, sx, sy, I, J, out, edges, stage, wscr, lane, Lv, cor,
                              prog + q * lmcap + J);
