@@ -191,8 +191,14 @@ vhp_status vhp_planner_batch_dev(vhp_context *ctx, const uint8_t *d_occ,
  *                         the ranks (an all-gather of 16 bytes per rank).
  * d_h_strip caches the heuristic per cell: initialise it to +inf, d_vg_strip to 0 and
  * d_came_strip to VHP_NO_PARENT.  visibility_heuristic_path_planner_b200/giant.py drives
- * these calls with torch.distributed (NCCL send/recv of the halo rows, all_gather of keys). */
+ * these calls with torch.distributed (NCCL send/recv of the halo rows, all_gather of keys).
+ * A strip sweep is one launch of ONE sweep: large windows (>= 2^20 cells) are spread over many
+ * CTAs ("grid mode": tile rows handed out from a global counter, boundary rows and progress
+ * flags in global memory), small ones run on a single CTA.  vhp_context_set_grid_sweep:
+ * 0 = never, 1 = by size (default; env VHP_GRID_SWEEP overrides at context creation),
+ * 2 = always (tests). */
 void vhp_strip_halo_rows(int nx, int ny, int sx, int sy, int y0, int y1, int32_t rows[4]);
+vhp_status vhp_context_set_grid_sweep(vhp_context *ctx, int mode);
 vhp_status vhp_strip_sweep_dev(vhp_context *ctx, const uint8_t *d_occ, int nx, int ny,
                                int sx, int sy, int y0, int y1,
                                const double *const d_halo[4], vhp_dtype dtype,

@@ -96,6 +96,7 @@ def load_library(build_if_missing: bool = True):
     lib.vhp_planner_batch_dev.argtypes = plan
     lib.vhp_strip_halo_rows.argtypes = [i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int32 * 4)]
     lib.vhp_strip_halo_rows.restype = None
+    lib.vhp_context_set_grid_sweep.argtypes = [vp, i32]
     lib.vhp_strip_sweep_dev.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, C.POINTER(vp * 4), i32, vp]
     lib.vhp_strip_epilogue_dev.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, C.c_double,
                                            C.c_int32, vp, vp, vp, vp, vp, vp]

@@ -349,6 +349,7 @@ vhp_status vhp_context_create(int device, void *cuda_stream, vhp_context **out) 
   const char *impl = std::getenv("VHP_SWEEP_IMPL");
   ctx->sweep_impl = 0;
   if (impl && std::strcmp(impl, "naive") == 0) ctx->sweep_impl = 1;
+  if (const char *e = std::getenv("VHP_GRID_SWEEP")) ctx->grid_sweep = std::atoi(e);
   *out = ctx;
   return VHP_OK;
 }
@@ -359,7 +360,7 @@ void vhp_context_destroy(vhp_context *ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
   VhpDevBuf *bufs[] = {&ctx->b_occ, &ctx->b_src, &ctx->b_map, &ctx->b_out[0], &ctx->b_out[1],
-                       &ctx->b_scratch, &ctx->b_planner, &ctx->b_misc};
+                       &ctx->b_scratch, &ctx->b_planner, &ctx->b_misc, &ctx->b_grid};
   for (VhpDevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->tile_buf) cudaFree(ctx->tile_buf);
@@ -439,6 +440,12 @@ vhp_status vhp_selftest_ratio(vhp_context *ctx, int kmax, int64_t *mismatches) {
   return VHP_OK;
 }
 
+vhp_status vhp_context_set_grid_sweep(vhp_context *ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 2) return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_context_set_grid_sweep: bad argument");
+  ctx->grid_sweep = mode;
+  return VHP_OK;
+}
+
 void vhp_strip_halo_rows(int nx, int ny, int sx, int sy, int y0, int y1, int32_t rows[4]) {
   vhp_window_halo_rows(nx, ny, sx, sy, y0, y1, rows);
 }
@@ -462,9 +469,19 @@ vhp_status vhp_strip_sweep_dev(vhp_context *ctx, const uint8_t *d_occ, int nx, i
   vhp_status st = ensure_rcp2(ctx, std::max(nx, ny) + 64);
   if (st != VHP_OK) return st;
   if ((st = pack_tile(ctx, d_occ, 1, nx, ny, false)) != VHP_OK) return st;
+  // Large windows are swept by many CTAs at once (grid mode): enough 8-warp CTAs for the tile
+  // rows of the window, at most two per SM.
+  const int grid_mode = ctx->grid_sweep;
+  int grid_ctas = 1;
+  if (grid_mode && (int64_t)nx * (y1 - y0) >= (grid_mode > 1 ? 0 : (1 << 20))) {
+    const int rows = 4 * ((y1 - y0) / 32 + 2);
+    grid_ctas = std::max(2, std::min(2 * ctx->sm_count, (rows + 7) / 8));
+    if ((st = ensure(ctx, ctx->b_grid, vhp_sweep_grid_ws_bytes(nx, ny))) != VHP_OK) return st;
+  }
   VHP_CUDA(ctx, vhp_launch_sweep_window(ctx->tile, nx, ny, sx, sy, y0, y1, d_halo, dtype,
-                                        d_vis_strip, ctx->rcp2_table, ctx->d_err, ctx->stream,
-                                        &ctx->launches));
+                                        d_vis_strip, ctx->rcp2_table, ctx->d_err,
+                                        grid_ctas > 1 ? ctx->b_grid.p : nullptr, grid_ctas,
+                                        ctx->stream, &ctx->launches));
   return VHP_OK;
 }
 

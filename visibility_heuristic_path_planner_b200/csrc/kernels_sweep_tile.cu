@@ -45,6 +45,18 @@ sweep_window_kernel(const TileArgs p, const int sx, const int sy) {
   tile_sweep_cta<OutT, kTileWarps>(p, 0, sx, sy, out, smem_raw);
 }
 
+// Grid mode of the same window sweep (giant maps): one sweep spread over many CTAs.  The init
+// kernel (one CTA) leaves the staircase, the boundary rows, the row progress flags and the row
+// counter in the global workspace; the work kernel, launched right after it on the same stream,
+// writes the lit region and runs the tile rows (see tile_sweep_cta).
+template <typename OutT, int MODE>
+__global__ void __launch_bounds__(kTileWarps * 32, MODE == kSweepGridWork ? 2 : 1)
+sweep_grid_kernel(const TileArgs p, const int sx, const int sy) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  OutT *out = reinterpret_cast<OutT *>(p.out) - (ptrdiff_t)p.win_y0 * p.nx;
+  tile_sweep_cta<OutT, kTileWarps, MODE>(p, 0, sx, sy, out, smem_raw);
+}
+
 // ---------------------------------------------------------------------------------
 // Bit planes.  wx = ceil(nx/32) + 1 words per row line, wy likewise per column line
 // (one zero word of padding so a 32-bit window may start in the last data word).
@@ -247,6 +259,8 @@ cudaError_t vhp_launch_sweep_tile(const VhpTilePlanes &pl, int nx, int ny, const
   p.win_y0 = 0;
   p.win_y1 = ny;
   for (int q = 0; q < 4; ++q) p.halo[q] = nullptr;
+  p.g_edges = nullptr;
+  p.g_lm = p.g_prog = p.g_next_row = nullptr;
   const cudaError_t e = dtype == VHP_F32 ? launch_tile<float>(p, npairs, st)
                                          : launch_tile<double>(p, npairs, st);
   if (launches) *launches += 1;
@@ -261,10 +275,54 @@ void vhp_window_halo_rows(int nx, int ny, int sx, int sy, int y0, int y1, int32_
   }
 }
 
+size_t vhp_sweep_grid_ws_bytes(int nx, int ny) {
+  return sizeof(double) * (size_t)tile_edge_doubles(nx, kTileWarps) +
+         sizeof(int) * (8 * (size_t)tile_lm_cap(ny) + 4);
+}
+
+namespace {
+
+template <typename OutT>
+cudaError_t launch_window(TileArgs &p, int sx, int sy, void *d_grid_ws, int grid_ctas,
+                          cudaStream_t st, int64_t *launches) {
+  if (d_grid_ws && grid_ctas > 1) {
+    const int lmcap = tile_lm_cap(p.ny);
+    p.g_edges = static_cast<double *>(d_grid_ws);
+    p.g_lm = reinterpret_cast<int *>(p.g_edges + tile_edge_doubles(p.nx, kTileWarps));
+    p.g_prog = p.g_lm + 4 * lmcap;
+    p.g_next_row = p.g_prog + 4 * lmcap;
+    const size_t smem = tile_smem_bytes_grid<OutT>(p.nx, p.ny);
+    auto init = sweep_grid_kernel<OutT, kSweepGridInit>;
+    auto work = sweep_grid_kernel<OutT, kSweepGridWork>;
+    cudaError_t e = cudaFuncSetAttribute(init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(work, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    init<<<1, kTileWarps * 32, smem, st>>>(p, sx, sy);
+    work<<<grid_ctas, kTileWarps * 32, smem, st>>>(p, sx, sy);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
+  }
+  p.g_edges = nullptr;
+  p.g_lm = p.g_prog = p.g_next_row = nullptr;
+  const size_t smem = tile_smem_bytes<OutT>(p.nx, p.ny);
+  cudaError_t e = cudaFuncSetAttribute(sweep_window_kernel<OutT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  sweep_window_kernel<OutT><<<1, kTileWarps * 32, smem, st>>>(p, sx, sy);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+} // namespace
+
+// d_grid_ws: vhp_sweep_grid_ws_bytes(nx, ny) bytes of device scratch, or null; grid_ctas > 1
+// spreads the sweep over that many CTAs (grid mode), else one CTA does it.
 cudaError_t vhp_launch_sweep_window(const VhpTilePlanes &pl, int nx, int ny, int sx, int sy, int y0,
                                     int y1, const double *const d_halo[4], vhp_dtype dtype,
                                     void *d_out_strip, const double *d_rcp2, int *d_err,
-                                    cudaStream_t st, int64_t *launches) {
+                                    void *d_grid_ws, int grid_ctas, cudaStream_t st,
+                                    int64_t *launches) {
   TileArgs p;
   p.pl = pl;
   p.nx = nx;
@@ -279,18 +337,6 @@ cudaError_t vhp_launch_sweep_window(const VhpTilePlanes &pl, int nx, int ny, int
   p.win_y0 = y0;
   p.win_y1 = y1;
   for (int q = 0; q < 4; ++q) p.halo[q] = d_halo ? d_halo[q] : nullptr;
-  cudaError_t e;
-  if (dtype == VHP_F32) {
-    const size_t smem = tile_smem_bytes<float>(nx, ny);
-    e = cudaFuncSetAttribute(sweep_window_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    sweep_window_kernel<float><<<1, kTileWarps * 32, smem, st>>>(p, sx, sy);
-  } else {
-    const size_t smem = tile_smem_bytes<double>(nx, ny);
-    e = cudaFuncSetAttribute(sweep_window_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    sweep_window_kernel<double><<<1, kTileWarps * 32, smem, st>>>(p, sx, sy);
-  }
-  if (launches) *launches += 1;
-  return cudaGetLastError();
+  return dtype == VHP_F32 ? launch_window<float>(p, sx, sy, d_grid_ws, grid_ctas, st, launches)
+                          : launch_window<double>(p, sx, sy, d_grid_ws, grid_ctas, st, launches);
 }

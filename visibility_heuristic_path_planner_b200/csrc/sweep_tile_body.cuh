@@ -113,7 +113,16 @@ struct TileArgs {
   // visibility row (indexed by x) just below the first tile row of quadrant q, or null
   int win_y0, win_y1;
   const double *halo[4];
+  // grid mode (one sweep spread over many CTAs): boundary rows, staircase, row progress and
+  // the row counter live in global memory (null otherwise)
+  double *g_edges;
+  int *g_lm, *g_prog, *g_next_row;
 };
+
+// how tile_sweep_cta is used
+constexpr int kSweepCta = 0;      // one CTA does the whole sweep (batches: one CTA per pair)
+constexpr int kSweepGridInit = 1; // grid mode, first kernel (one CTA): staircase, boundary rows, flags
+constexpr int kSweepGridWork = 2; // grid mode, second kernel (many CTAs): lit fill and tile rows
 
 // geometry of one quadrant (shared memory, written once per sweep)
 struct TQuad {
@@ -172,6 +181,13 @@ __host__ __device__ inline int tile_sum_bytes(int nx, int ny) {
 
 // lit staircase Lm[q][J] and row progress prog[q][J]: tile_lm_cap(ny) entries per quadrant each
 __host__ __device__ inline int tile_lm_cap(int ny) { return (ny - 1) / kTile + 4; }
+
+// grid mode keeps the boundary rows in global memory
+template <typename OutT>
+__host__ __device__ inline size_t tile_smem_bytes_grid(int nx, int ny, int nwarps = kTileWarps) {
+  return 256 + tile_sum_bytes(nx, ny) + 32 * (size_t)tile_lm_cap(ny) +
+         (size_t)nwarps * (kTile * kStagePitch * sizeof(OutT) + kWarpScratch * sizeof(double));
+}
 
 template <typename OutT>
 __host__ __device__ inline size_t tile_smem_bytes(int nx, int ny, int nwarps = kTileWarps) {
@@ -288,9 +304,20 @@ __device__ __forceinline__ TilePre tile_prefetch(const TileArgs &p, const TQuad 
   return t;
 }
 
+__device__ __forceinline__ int ld_acquire_gpu(const int *a) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int *a, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(a), "r"(v) : "memory");
+}
+
 // One tile (I, J) of quadrant g by one warp.  Lv (lane r: q(i0-1, j0+r)) and cor
 // (q(i0-1, j0-1)) are the left inputs; on return they hold the same for tile (I+1, J).
-template <typename OutT, int NW>
+// GE: the boundary rows (edges) and the progress flag are in global memory and shared with
+// warps of other CTAs (grid mode): boundary reads bypass L1, the flag is released at GPU scope.
+template <typename OutT, int NW, bool GE>
 __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, const TilePre &pre,
                                              const int sx, const int sy, const int I, const int J,
                                              OutT *__restrict__ out, double *edges,
@@ -300,8 +327,12 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
   // before the global stores
   constexpr int kStepUnroll = NW == 1 ? VHP_STEP_UNROLL_1W : VHP_STEP_UNROLL;
   auto publish = [&]() {
+    if (GE) __threadfence(); // this lane's boundary-row stores, before lane 0 raises the flag
     __syncwarp();
-    if (lane == 0) st_release_shared(done_flag, I + 1);
+    if (lane == 0) {
+      if (GE) st_release_gpu(done_flag, I + 1);
+      else st_release_shared(done_flag, I + 1);
+    }
   };
   const int nx = p.nx;
   const int wi = I ? kTile : g.a, wj = J ? kTile : g.a;          // tile extent
@@ -333,7 +364,7 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
       allocc = __all_sync(kAll, wrow == 0u);
     }
   }
-  const double Bv = rowE[lane];
+  const double Bv = GE ? __ldcg(rowE + lane) : rowE[lane];
   const bool inuni = __all_sync(kAll, (!colc || Bv == cor) && (!rowc || Lv == cor));
   const bool zero_in = inuni && cor == 0.0;
 
@@ -505,29 +536,40 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
 // One complete sweep from (sx, sy) by the whole CTA (NW warps, all threads must call).  Writes every cell of out[ny][nx] exactly once (cells on the never-
 // written border get 0).  smem_raw: tile_smem_bytes<OutT>(nx, ny, NW) bytes, 16-aligned.
 // Ends with a block barrier.
-template <typename OutT, int NW>
+//
+// Grid mode (MODE != kSweepCta; one sweep of a giant map by many CTAs): kSweepGridInit, run by
+// one CTA, computes the staircase and writes it with the boundary rows, the progress flags and
+// the row counter to global memory; kSweepGridWork, launched after it with any number of
+// CTAs, writes the lit region (grid rows dealt over all warps of the grid) and then takes tile
+// rows from the global counter.  A row only waits for a row handed out earlier, whose warp is
+// therefore running: no co-residency of the CTAs is needed.
+template <typename OutT, int NW, int MODE = kSweepCta>
 __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map, const int sx,
                                                const int sy, OutT *__restrict__ out,
                                                unsigned char *smem_raw) {
+  constexpr bool GE = MODE != kSweepCta;
+  static_assert(!GE || NW > 1, "grid mode uses the multi-warp boundary layout");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nx = p.nx, ny = p.ny;
   TQuad *quads = reinterpret_cast<TQuad *>(smem_raw);
-  int *next_row = reinterpret_cast<int *>(smem_raw + 240); // next tile row to hand out (NW > 1)
+  // next tile row to hand out (NW > 1)
+  int *next_row = GE ? p.g_next_row : reinterpret_cast<int *>(smem_raw + 240);
   static_assert(4 * sizeof(TQuad) <= 240, "quadrant geometry overlaps the row counter");
   uint32_t *bsum = reinterpret_cast<uint32_t *>(smem_raw + 256);
   const int nsum = tile_sum_words(nx) * ((ny + 31) >> 5);
   const int lmcap = tile_lm_cap(ny);
   int *Lm = reinterpret_cast<int *>(smem_raw + 256 + tile_sum_bytes(nx, ny));
-  int *prog = Lm + 4 * lmcap; // tiles finished (or lit) at the head of tile row (q, J)
-  double *edges = reinterpret_cast<double *>(smem_raw + 256 + tile_sum_bytes(nx, ny) + 32 * lmcap);
+  int *prog = GE ? p.g_prog : Lm + 4 * lmcap; // tiles finished (or lit) at the head of tile row (q, J)
+  double *const edges_s = reinterpret_cast<double *>(smem_raw + 256 + tile_sum_bytes(nx, ny) + 32 * lmcap);
+  double *edges = GE ? p.g_edges : edges_s;
   const int nedge = tile_edge_doubles(nx, NW);
-  unsigned char *wbase = reinterpret_cast<unsigned char *>(edges + nedge);
+  unsigned char *wbase = reinterpret_cast<unsigned char *>(GE ? edges_s : edges_s + nedge);
   double *wscr = reinterpret_cast<double *>(wbase) + warp * kWarpScratch;
   OutT *stage = reinterpret_cast<OutT *>(wbase + NW * kWarpScratch * sizeof(double)) +
                 warp * (kTile * kStagePitch);
 
   if (tid == 0) {
-    *next_row = 0;
+    if (MODE != kSweepGridWork) *next_row = 0;
     const int WXb = 32 * ((nx + 31) >> 5), WYb = 32 * ((ny + 31) >> 5);
     int off = 0;
     for (int q = 0; q < 4; ++q) { // Q1 (+,+), Q2 (-,+), Q3 (-,-), Q4 (+,-): reference order
@@ -553,11 +595,17 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
     }
   }
   for (int i = tid; i < nsum; i += blockDim.x) bsum[i] = __ldg(p.pl.bsum + (size_t)map * nsum + i);
-  for (int i = tid; i < nedge; i += blockDim.x) edges[i] = 1.0; // virtual boundary
+  if (MODE != kSweepGridWork)
+    for (int i = tid; i < nedge; i += blockDim.x) edges[i] = 1.0; // virtual boundary
   __syncthreads();
+  if (MODE == kSweepGridWork) { // the staircase was computed by the init kernel
+    for (int i = tid; i < 4 * lmcap; i += blockDim.x) Lm[i] = __ldg(p.g_lm + i);
+    __syncthreads();
+  }
 
   // ---- lit staircase: leading free tiles per tile row, then the running minimum ---------
   const int nbw = tile_sum_words(nx);
+  if (MODE != kSweepGridWork) {
   for (int q = 0; q < 4; ++q) {
     const TQuad &g = quads[q];
     for (int J = warp; J < g.TY; J += NW) {
@@ -580,6 +628,7 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
       m = min(m, Lm[tid * lmcap + J]);
       Lm[tid * lmcap + J] = m;
       prog[tid * lmcap + J] = J < g.Jlo ? g.TX : m; // rows below the window count as finished
+      if (GE) p.g_lm[tid * lmcap + J] = m;
     }
   }
   if (NW > 1) { // boundary row below the first tile row of the window = the neighbour's halo row
@@ -590,6 +639,8 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
           edges[g.rowOff + i] = __ldg(p.halo[q] + (sx + g.dirx * i));
     }
   }
+  }
+  if (MODE == kSweepGridInit) return; // boundary rows, flags, staircase and counter are set
   __syncthreads();
 
   // ---- write the lit region: one warp per grid row, -x and +x runs merged -----------------
@@ -623,7 +674,8 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
     }
     // rows below the source are j = 1 .. jl - 1, rows from the source upwards j = 0 .. jl - 1
     const int ylo = sy - max(max(jl[2], jl[3]) - 1, 0), yhi = sy + max(jl[0], jl[1]) - 1;
-    for (int y = max(ylo, p.win_y0) + warp; y <= min(yhi, p.win_y1 - 1); y += NW) {
+    const int wfirst = GE ? (int)blockIdx.x * NW + warp : warp, wstride = GE ? (int)gridDim.x * NW : NW;
+    for (int y = max(ylo, p.win_y0) + wfirst; y <= min(yhi, p.win_y1 - 1); y += wstride) {
       const bool upper = y >= sy;
       const int j = upper ? y - sy : sy - y;
       const int nR = upper ? lit_run(0, j) : lit_run(3, j);
@@ -659,12 +711,14 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
       if (NW > 1 && J > 0) { // tile (I, J-1) must be finished
         const int *flag = prog + q * lmcap + J - 1;
 #if VHP_POLL_BACKOFF
-        for (unsigned ns = 32; ld_acquire_shared(flag) <= I; ns = min(2 * ns, 256u)) __nanosleep(ns);
+        for (unsigned ns = 32; (GE ? ld_acquire_gpu(flag) : ld_acquire_shared(flag)) <= I;
+             ns = min(2 * ns, 256u))
+          __nanosleep(ns);
 #else
-        while (ld_acquire_shared(flag) <= I) __nanosleep(40);
+        while ((GE ? ld_acquire_gpu(flag) : ld_acquire_shared(flag)) <= I) __nanosleep(40);
 #endif
       }
-      process_tile<OutT, NW>(p, g, cur, sx, sy, I, J, out, edges, stage, wscr, lane, Lv, cor,
+      process_tile<OutT, NW, GE>(p, g, cur, sx, sy, I, J, out, edges, stage, wscr, lane, Lv, cor,
                              prog + q * lmcap + J);
       __syncwarp();
     }

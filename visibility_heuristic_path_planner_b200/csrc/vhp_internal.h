@@ -36,7 +36,7 @@ struct vhp_context {
   // device-side error word (bit 0: a source / start / end outside the grid)
   int *d_err = nullptr;
   // workspace buffers (grown on demand, reused across calls)
-  VhpDevBuf b_occ, b_src, b_map, b_out[2], b_scratch, b_planner, b_misc;
+  VhpDevBuf b_occ, b_src, b_map, b_out[2], b_scratch, b_planner, b_misc, b_grid;
   cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   // 1/k table {rh, rl} of the tile kernel (double-double reciprocal), device resident
   double *rcp2_table = nullptr;
@@ -52,6 +52,8 @@ struct vhp_context {
   // K1 implementation (env VHP_SWEEP_IMPL): 0 = tile wavefront kernel where its boundary
   // arrays fit shared memory, else the naive kernel; 1 = always the naive kernel
   int sweep_impl = 0;
+  // strip sweeps over many CTAs: 0 never, 1 for windows of >= 2^20 cells, 2 always
+  int grid_sweep = 1;
 };
 
 // ---- kernel launchers (all enqueue on `st`, return cudaGetLastError()) --------
@@ -80,10 +82,14 @@ cudaError_t vhp_launch_sweep_tile(const VhpTilePlanes &pl, int nx, int ny, const
 // giant-map path: one sweep of map 0 restricted to the rows [y0, y1) of a strip, and the
 // planner epilogue + arg-min over a strip (whole GPU)
 void vhp_window_halo_rows(int nx, int ny, int sx, int sy, int y0, int y1, int32_t rows[4]);
+// d_grid_ws (vhp_sweep_grid_ws_bytes bytes) with grid_ctas > 1: the sweep is spread over that
+// many CTAs (two launches), else a single CTA does it.
+size_t vhp_sweep_grid_ws_bytes(int nx, int ny);
 cudaError_t vhp_launch_sweep_window(const VhpTilePlanes &pl, int nx, int ny, int sx, int sy, int y0,
                                     int y1, const double *const d_halo[4], vhp_dtype dtype,
                                     void *d_out_strip, const double *d_rcp2, int *d_err,
-                                    cudaStream_t st, int64_t *launches);
+                                    void *d_grid_ws, int grid_ctas, cudaStream_t st,
+                                    int64_t *launches);
 int vhp_strip_epilogue_blocks(int sm_count);
 cudaError_t vhp_launch_strip_epilogue(int nx, int ny, int y0, int y1, int sx, int sy, int ex, int ey,
                                       double thr, int nb, const int32_t *d_ls, const double *d_vis,

@@ -72,12 +72,14 @@ class StripPlanner:
     nstrips  number of strips; strip k is owned by rank k % world (world = 1: all local)
     device   CUDA device index of this rank
     dist     torch.distributed (initialised) or None
+    grid_sweep  None: strips of >= 2^20 cells are swept by many CTAs at once, smaller ones by
+             one CTA (the library default); 0 / 2 force the single-CTA / the grid kernels
 
     All device work (the library's kernels, torch copies / fills, NCCL send/recv) is
     enqueued on one torch stream owned by the planner, so it is ordered without host syncs.
     """
 
-    def __init__(self, occ, nstrips, device=0, dist=None):
+    def __init__(self, occ, nstrips, device=0, dist=None, grid_sweep=None):
         import torch
         from . import torch_context
         self.torch, self.lib, self.dist = torch, load_library(), dist
@@ -86,6 +88,8 @@ class StripPlanner:
         self.dev = torch.device("cuda", device)
         self.stream = torch.cuda.Stream(self.dev)
         self.ctx = torch_context(device, self.stream)
+        if grid_sweep is not None:
+            self._check(self.lib.vhp_context_set_grid_sweep(self.ctx.h, int(grid_sweep)))
         with torch.cuda.stream(self.stream):
             self._alloc(occ, nstrips)
 
