@@ -22,9 +22,13 @@ def vhp():
     return m
 
 
-@pytest.fixture(scope="module")
-def ctx(vhp):
+@pytest.fixture(scope="module", params=["cta", "grid"])
+def ctx(vhp, request):
+    """Every test runs on both planner routes: one persistent CTA per problem (batches), and
+    one problem at a time on the whole GPU (grid-mode sweep + strip epilogue + control kernels,
+    what large single problems take by default; forced here for every size)."""
     c = vhp.Context(0)
+    c.set_grid_sweep(2 if request.param == "grid" else 0)
     yield c
     c.close()
 

@@ -147,6 +147,11 @@ class Context:
             raise VhpError(st, self.lib.vhp_last_error(self.h).decode())
         return st
 
+    def set_grid_sweep(self, mode: int):
+        """0: strip sweeps / large planner problems always on one CTA; 1: spread over many CTAs
+        by size (default); 2: always (tests)."""
+        self._check(self.lib.vhp_context_set_grid_sweep(self.h, int(mode)))
+
     def synchronize(self):
         self._check(self.lib.vhp_context_synchronize(self.h))
 

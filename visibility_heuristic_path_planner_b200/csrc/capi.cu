@@ -240,6 +240,55 @@ vhp_status run_host(vhp_context *ctx, Op op, const uint8_t *occ, int nmaps, int 
 }
 
 // ---- planner ------------------------------------------------------------------
+// Grid-mode strip sweep of rows [y0, y1) (see vhp_strip_sweep_dev): CTAs to spread one sweep over.
+int grid_sweep_ctas(const vhp_context *ctx, int rows) {
+  return std::max(2, std::min(2 * ctx->sm_count, (4 * (rows / 32 + 2) + 7) / 8));
+}
+
+// One LARGE problem on the whole GPU: solve() (src/visibilityBasedSolver.cpp:76-160) driven from
+// the host.  Per iteration: grid-mode sweep of the whole map (many CTAs), per-cell epilogue +
+// arg-min over the whole map (strip epilogue kernels with the strip = the map), next-source
+// selection on the device, 20 bytes of loop state back to the host.  Same results as the
+// persistent single-CTA planner kernel, which would leave all but one SM idle.
+vhp_status planner_grid_one(vhp_context *ctx, const VhpTilePlanes &pl, int nx, int ny,
+                            const int32_t se[4], double thr, int32_t max_iter, int32_t ls_cap,
+                            double *vis, double *vg, double *hc, int32_t *came, int32_t *status,
+                            int32_t *nb, int32_t *ls, double *plen, int32_t *pn, int32_t *path,
+                            float *vg32, float *vis32) {
+  const int nblocks = vhp_strip_epilogue_blocks(ctx->sm_count);
+  vhp_status st = ensure(ctx, ctx->b_misc, (size_t)nblocks * 16 + 128);
+  if (st != VHP_OK) return st;
+  if ((st = ensure(ctx, ctx->b_grid, vhp_sweep_grid_ws_bytes(nx, ny))) != VHP_OK) return st;
+  unsigned long long *d_partial = (unsigned long long *)ctx->b_misc.p;
+  unsigned long long *d_best = d_partial + 2 * (size_t)nblocks;
+  int *d_ctl = (int *)(d_best + 2);
+  const int stx = se[0], sty = se[1], ex = se[2], ey = se[3];
+  VHP_CUDA(ctx, vhp_launch_grid_planner_begin(pl, nx, ny, stx, sty, ex, ey, thr, vg, hc, came, ls,
+                                              d_ctl, ctx->stream, &ctx->launches));
+  int ctl[5];
+  auto read_ctl = [&]() -> cudaError_t {
+    cudaError_t e = cudaMemcpyAsync(ctl, d_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, ctx->stream);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(ctx->stream);
+  };
+  VHP_CUDA(ctx, read_ctl());
+  const int ctas = grid_sweep_ctas(ctx, ny);
+  while (!ctl[0]) {
+    VHP_CUDA(ctx, vhp_launch_sweep_window(pl, nx, ny, ctl[1], ctl[2], 0, ny, nullptr, VHP_F64, vis,
+                                          ctx->rcp2_table, ctx->d_err, ctx->b_grid.p, ctas,
+                                          ctx->stream, &ctx->launches));
+    VHP_CUDA(ctx, vhp_launch_strip_epilogue(nx, ny, 0, ny, ctl[1], ctl[2], ex, ey, thr, ctl[4], ls,
+                                            vis, vg, hc, came, d_partial, nblocks, d_best,
+                                            ctx->stream, &ctx->launches));
+    VHP_CUDA(ctx, vhp_launch_grid_planner_step(d_best, nx, ex, ey, thr, max_iter, vg, ls, d_ctl,
+                                               ctx->stream, &ctx->launches));
+    VHP_CUDA(ctx, read_ctl());
+  }
+  VHP_CUDA(ctx, vhp_launch_grid_planner_finish(d_ctl, nx, ny, ex, ey, ls_cap, ls, came, vis, vg,
+                                               status, nb, plen, pn, path, vg32, vis32,
+                                               ctx->stream, &ctx->launches));
+  return VHP_OK;
+}
+
 // device pointers in `o` (any may be null).  Fields the caller did not ask for in
 // fp64 live in the context workspace, so large batches run in chunks.
 vhp_status planner_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx, int ny,
@@ -276,6 +325,26 @@ vhp_status planner_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx
   double *plen = o.path_len ? o.path_len : (double *)take(8 * nprob);
   int32_t *pn = o.path_n ? o.path_n : (int32_t *)take(4 * nprob);
   int32_t *path = o.path ? o.path : (int32_t *)take(8 * (size_t)ls_cap * nprob);
+  // A few problems on a large map: one problem at a time on the whole GPU (grid mode) instead
+  // of one persistent CTA per problem.  grid_sweep 0: never, 1: by size, 2: always.
+  // Measured on B200 (tools/planner_routes.py, ms per iteration): single CTA 0.6 @256^2, 3.3 @1000^2,
+  // 48 @4096^2, 184 @8192^2; grid route 0.3, 0.7, 2.8, 7.5 -- but its problems run one after the
+  // other, so it only wins for a handful of problems, more of them the larger the map.
+  const int64_t grid_max_prob = std::max<int64_t>(1, std::min<int64_t>(24, (int64_t)(cells / 100000)));
+  const bool grid_route = ctx->grid_sweep == 2 || (ctx->grid_sweep == 1 && nprob <= grid_max_prob);
+  std::vector<int32_t> h_se, h_pmap;
+  if (grid_route) {
+    h_se.resize(4 * (size_t)nprob);
+    VHP_CUDA(ctx, cudaMemcpyAsync(h_se.data(), d_se, h_se.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_pmap) {
+      h_pmap.resize((size_t)nprob);
+      VHP_CUDA(ctx, cudaMemcpyAsync(h_pmap.data(), d_pmap, h_pmap.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    VHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int64_t k = 0; k < nprob; ++k)
+      if (d_pmap && (h_pmap[k] < 0 || h_pmap[k] >= nmaps))
+        return fail(ctx, VHP_ERR_INVALID_ARG, "planner: map index out of range");
+  }
   for (int64_t q0 = 0; q0 < nprob; q0 += chunk) {
     const int64_t n = std::min(chunk, nprob - q0);
     double *vis = vis_user ? (double *)o.vis + q0 * cells : ws_vis;
@@ -283,6 +352,25 @@ vhp_status planner_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx
     int32_t *came = o.came ? o.came + q0 * cells : ws_came;
     float *vg32 = (dtype == VHP_F32 && o.vg) ? (float *)o.vg + q0 * cells : nullptr;
     float *vis32 = (dtype == VHP_F32 && o.vis) ? (float *)o.vis + q0 * cells : nullptr;
+    if (grid_route) {
+      int wx, wy, nsum;
+      vhp_tile_plane_geometry(nx, ny, &wx, &wy, &nsum);
+      for (int64_t k = 0; k < n; ++k) {
+        const int64_t q = q0 + k;
+        const size_t m = d_pmap ? (size_t)h_pmap[q] : 0;
+        VhpTilePlanes pl = ctx->tile; // planes of map m (the grid kernels sweep "map 0")
+        pl.rowF += m * pl.row_plane; pl.rowR += m * pl.row_plane;
+        pl.colF += m * pl.col_plane; pl.colR += m * pl.col_plane;
+        pl.bsum += m * (size_t)nsum;
+        st = planner_grid_one(ctx, pl, nx, ny, &h_se[4 * q], thr, max_iter, ls_cap, vis + k * cells,
+                              vg + k * cells, ws_hc + k * cells, came + k * cells, status + q, nb + q,
+                              ls + 2 * (size_t)ls_cap * q, plen + q, pn + q,
+                              path + 2 * (size_t)ls_cap * q, vg32 ? vg32 + k * cells : nullptr,
+                              vis32 ? vis32 + k * cells : nullptr);
+        if (st != VHP_OK) return st;
+      }
+      continue;
+    }
     VHP_CUDA(ctx, vhp_launch_planner(ctx->tile, nx, ny, d_se + 4 * q0, d_pmap ? d_pmap + q0 : nullptr,
                                      n, thr, max_iter, ls_cap, ctx->rcp2_table, vis, vg, ws_hc, came,
                                      status + q0, nb + q0, ls + 2 * (size_t)ls_cap * q0, plen + q0,
@@ -474,8 +562,7 @@ vhp_status vhp_strip_sweep_dev(vhp_context *ctx, const uint8_t *d_occ, int nx, i
   const int grid_mode = ctx->grid_sweep;
   int grid_ctas = 1;
   if (grid_mode && (int64_t)nx * (y1 - y0) >= (grid_mode > 1 ? 0 : (1 << 20))) {
-    const int rows = 4 * ((y1 - y0) / 32 + 2);
-    grid_ctas = std::max(2, std::min(2 * ctx->sm_count, (rows + 7) / 8));
+    grid_ctas = grid_sweep_ctas(ctx, y1 - y0);
     if ((st = ensure(ctx, ctx->b_grid, vhp_sweep_grid_ws_bytes(nx, ny))) != VHP_OK) return st;
   }
   VHP_CUDA(ctx, vhp_launch_sweep_window(ctx->tile, nx, ny, sx, sy, y0, y1, d_halo, dtype,

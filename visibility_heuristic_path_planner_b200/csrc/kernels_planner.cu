@@ -84,15 +84,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) planner_kernel(const PlannerP
     came[c] = VHP_NO_PARENT;
   }
   if (tid == 0) {
-    auto free_cell = [&](int x, int y) {
-      return (rowbits[(size_t)y * p.fp.pl.wx + (x >> 5)] >> (x & 31)) & 1u;
-    };
-    int st = VHP_OK; // checks in the reference's order, :89-116
-    if ((unsigned)stx >= (unsigned)nx || (unsigned)sty >= (unsigned)ny) st = VHP_START_OOB;
-    else if ((unsigned)ex >= (unsigned)nx || (unsigned)ey >= (unsigned)ny) st = VHP_END_OOB;
-    else if (!free_cell(stx, sty)) st = VHP_START_OCCUPIED;
-    else if (!free_cell(ex, ey)) st = VHP_END_OCCUPIED;
-    s_ctl[3] = st;
+    s_ctl[3] = planner_validate(rowbits, p.fp.pl.wx, nx, ny, stx, sty, ex, ey);
     s_ctl[1] = stx;
     s_ctl[2] = sty;
     s_ctl[0] = 0;
@@ -147,27 +139,12 @@ __global__ void __launch_bounds__(kTileWarps * 32) planner_kernel(const PlannerP
         }
         if (lane == 0) {
           // ---- 3. heap_->top() -> next light source, :130-139
-          const int qd = (int)(b.key >> 40), i = (int)((b.key >> 20) & 0xFFFFF), j = (int)(b.key & 0xFFFFF);
-          const int tx = (qd == 0 || qd == 3) ? sx + i : sx - i;
-          const int ty = (qd < 2) ? sy + j : sy - j;
-          int nnb = nb + 1;
-          ls[2 * nnb] = tx;
-          ls[2 * nnb + 1] = ty;
+          int tx, ty, d, st = s_ctl[3];
+          const int nnb = planner_next_source(b, sx, sy, nb, p.max_iter, thr,
+                                              __ldcg(vg + (size_t)ey * nx + ex), ls, tx, ty, d, st);
           s_ctl[1] = tx;
           s_ctl[2] = ty;
-          int d = 0;
-          if (nnb > p.max_iter) { d = 1; s_ctl[3] = VHP_MAX_ITER; }
-          else if (!(__ldcg(vg + (size_t)ey * nx + ex) <= thr)) d = 1; // loop test :127
-          else if (tx == sx && ty == sy) {
-            // fixed point: the same source again -> every further iteration is identical
-            while (nnb <= p.max_iter) {
-              ++nnb;
-              ls[2 * nnb] = tx;
-              ls[2 * nnb + 1] = ty;
-            }
-            d = 1;
-            s_ctl[3] = VHP_MAX_ITER;
-          }
+          s_ctl[3] = st;
           s_ctl[0] = d;
           s_ctl[4] = nnb;
         }
@@ -188,28 +165,8 @@ __global__ void __launch_bounds__(kTileWarps * 32) planner_kernel(const PlannerP
     p.status[q] = status;
     p.nb[q] = nb;
     int32_t *path = p.path + q * (size_t)p.ls_cap * 2;
-    long n = 0;
-    double total = 0.0;
-    if (status == VHP_OK) {
-      ls[2 * nb] = ex; ls[2 * nb + 1] = ey; // lightSources_[nb] = end, :141
-      // reconstructPath, :1183-1213: walk end -> start, then reverse
-      int x = ex, y = ey;
-      int t = __ldcg(came + (size_t)y * nx + x), t_old = -2;
-      while (t != t_old && t >= 0 && n < p.ls_cap - 1) {
-        path[2 * n] = x; path[2 * n + 1] = y; ++n;
-        t_old = t;
-        x = ls[2 * t]; y = ls[2 * t + 1];
-        t = __ldcg(came + (size_t)y * nx + x);
-      }
-      path[2 * n] = x; path[2 * n + 1] = y; ++n;
-      for (long a = 0, b = n - 1; a < b; ++a, --b) {
-        const int tx = path[2 * a], ty = path[2 * a + 1];
-        path[2 * a] = path[2 * b]; path[2 * a + 1] = path[2 * b + 1];
-        path[2 * b] = tx; path[2 * b + 1] = ty;
-      }
-      for (long k = 0; k + 1 < n; ++k)
-        total = __dadd_rn(total, eval_d(path[2 * k], path[2 * k + 1], path[2 * k + 2], path[2 * k + 3]));
-    }
+    double total;
+    const long n = planner_reconstruct(status, nb, ex, ey, nx, p.ls_cap, ls, came, path, total);
     p.path_n[q] = (int32_t)n;
     p.path_len[q] = total;
   }
@@ -269,7 +226,100 @@ __global__ void __launch_bounds__(256) strip_best_kernel(const Best *partial, in
   }
 }
 
+// ---- one LARGE problem on the whole GPU ("grid planner"): the loop of solve() driven from
+// the host, one iteration = grid-mode sweep (kernels_sweep_tile.cu) + strip epilogue over the
+// whole map + the control kernels below.  ctl = {done, next x, next y, status, nb_of_sources}
+// is read back by the host after every iteration (20 bytes).
+__global__ void grid_planner_reset_kernel(double *vg, double *hc, int32_t *came, size_t cells) {
+  for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < cells;
+       c += (size_t)gridDim.x * blockDim.x) { // reset(), :42-60
+    vg[c] = 0.0;
+    hc[c] = __longlong_as_double(0x7ff0000000000000ll);
+    came[c] = VHP_NO_PARENT;
+  }
+}
+
+__global__ void grid_planner_begin_kernel(const uint32_t *rowbits, int wx, int nx, int ny, int stx,
+                                          int sty, int ex, int ey, double thr, int32_t *ls,
+                                          int32_t *came, int *ctl) {
+  const int st = planner_validate(rowbits, wx, nx, ny, stx, sty, ex, ey);
+  int done = 1;
+  if (st == VHP_OK) {
+    ls[0] = stx; ls[1] = sty;                 // lightSources_[0] = start, :121
+    came[(size_t)sty * nx + stx] = 0;         // :122
+    done = !(0.0 <= thr);                     // visibility_global_(end) = 0 (:123), loop test :127
+  }
+  ctl[0] = done; ctl[1] = stx; ctl[2] = sty; ctl[3] = st; ctl[4] = 0;
+}
+
+__global__ void grid_planner_step_kernel(const Best *best, int nx, int ex, int ey, double thr,
+                                         int max_iter, const double *vg, int32_t *ls, int *ctl) {
+  int tx, ty, d, st = ctl[3];
+  const int nnb = planner_next_source(*best, ctl[1], ctl[2], ctl[4], max_iter, thr,
+                                      __ldcg(vg + (size_t)ey * nx + ex), ls, tx, ty, d, st);
+  ctl[0] = d; ctl[1] = tx; ctl[2] = ty; ctl[3] = st; ctl[4] = nnb;
+}
+
+// tail of solve(): outputs of problem q; vis keeps the zeros of reset() if no sweep ran;
+// optional fp32 exports
+__global__ void grid_planner_finish_kernel(const int *ctl, int nx, int ny, int ex, int ey, int ls_cap,
+                                           int32_t *ls, const int32_t *came, double *vis,
+                                           const double *vg, int32_t *status, int32_t *nb_out,
+                                           double *path_len, int32_t *path_n, int32_t *path,
+                                           float *vg32, float *vis32) {
+  const size_t cells = (size_t)nx * ny;
+  const int st = ctl[3], nb = ctl[4];
+  const size_t gtid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, gn = (size_t)gridDim.x * blockDim.x;
+  if (gtid == 0) {
+    *status = st;
+    *nb_out = nb;
+    double total;
+    const long n = planner_reconstruct(st, nb, ex, ey, nx, ls_cap, ls, came, path, total);
+    *path_n = (int32_t)n;
+    *path_len = total;
+  }
+  for (size_t c = gtid; c < cells; c += gn) {
+    if (nb == 0) vis[c] = 0.0;
+    if (vg32) vg32[c] = __double2float_rn(__ldcg(vg + c));
+    if (vis32) vis32[c] = nb == 0 ? 0.0f : __double2float_rn(__ldcg(vis + c));
+  }
+}
+
 } // namespace
+
+cudaError_t vhp_launch_grid_planner_begin(const VhpTilePlanes &pl, int nx, int ny, int stx, int sty,
+                                          int ex, int ey, double thr, double *d_vg, double *d_hc,
+                                          int32_t *d_came, int32_t *d_ls, int *d_ctl,
+                                          cudaStream_t st, int64_t *launches) {
+  grid_planner_reset_kernel<<<148 * 8, 256, 0, st>>>(d_vg, d_hc, d_came, (size_t)nx * ny);
+  grid_planner_begin_kernel<<<1, 1, 0, st>>>(pl.rowF, pl.wx, nx, ny, stx, sty, ex, ey, thr, d_ls,
+                                             d_came, d_ctl);
+  if (launches) *launches += 2;
+  return cudaGetLastError();
+}
+
+cudaError_t vhp_launch_grid_planner_step(const unsigned long long *d_best, int nx, int ex, int ey,
+                                         double thr, int max_iter, const double *d_vg,
+                                         int32_t *d_ls, int *d_ctl, cudaStream_t st,
+                                         int64_t *launches) {
+  grid_planner_step_kernel<<<1, 1, 0, st>>>(reinterpret_cast<const Best *>(d_best), nx, ex, ey, thr,
+                                            max_iter, d_vg, d_ls, d_ctl);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t vhp_launch_grid_planner_finish(const int *d_ctl, int nx, int ny, int ex, int ey,
+                                           int ls_cap, int32_t *d_ls, const int32_t *d_came,
+                                           double *d_vis, const double *d_vg, int32_t *d_status,
+                                           int32_t *d_nb, double *d_path_len, int32_t *d_path_n,
+                                           int32_t *d_path, float *d_vg32, float *d_vis32,
+                                           cudaStream_t st, int64_t *launches) {
+  grid_planner_finish_kernel<<<148 * 8, 256, 0, st>>>(d_ctl, nx, ny, ex, ey, ls_cap, d_ls, d_came,
+                                                      d_vis, d_vg, d_status, d_nb, d_path_len,
+                                                      d_path_n, d_path, d_vg32, d_vis32);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
 
 int vhp_strip_epilogue_blocks(int sm_count) { return sm_count * 8; }
 
@@ -312,6 +362,8 @@ cudaError_t vhp_launch_planner(const VhpTilePlanes &pl, int nx, int ny, const in
   p.fp.win_y0 = 0;
   p.fp.win_y1 = ny;
   for (int q = 0; q < 4; ++q) p.fp.halo[q] = nullptr;
+  p.fp.g_edges = nullptr;
+  p.fp.g_lm = p.fp.g_prog = p.fp.g_next_row = nullptr;
   p.se_xy = d_se_xy; p.prob_map = d_prob_map;
   p.thr = threshold; p.max_iter = max_iter; p.ls_cap = ls_cap;
   p.vis = d_vis; p.vg = d_vg; p.hc = d_hc; p.came = d_came;

@@ -72,6 +72,80 @@ __device__ __forceinline__ void epilogue_cell(const int X, const int Y, const si
   }
 }
 
+// ---- loop control of solve(), shared by the single-CTA planner kernel (one thread of the
+// persistent CTA) and the control kernels of the many-CTA path for large single problems.
+
+// Validity checks in the reference's order (:89-116); rowbits = forward row bit plane of the map.
+__device__ __forceinline__ int planner_validate(const uint32_t *rowbits, const int wx, const int nx,
+                                                const int ny, const int stx, const int sty,
+                                                const int ex, const int ey) {
+  auto free_cell = [&](int x, int y) { return (rowbits[(size_t)y * wx + (x >> 5)] >> (x & 31)) & 1u; };
+  if ((unsigned)stx >= (unsigned)nx || (unsigned)sty >= (unsigned)ny) return VHP_START_OOB;
+  if ((unsigned)ex >= (unsigned)nx || (unsigned)ey >= (unsigned)ny) return VHP_END_OOB;
+  if (!free_cell(stx, sty)) return VHP_START_OCCUPIED;
+  if (!free_cell(ex, ey)) return VHP_END_OCCUPIED;
+  return VHP_OK;
+}
+
+// heap_->top() -> next light source (:130-139) after the sweep from (sx, sy) as source nb.
+// Appends to ls, returns the new nb_of_sources; tx/ty = the next source; done / status as the
+// loop test (:127), max_iter and the fixed point decide.
+__device__ __forceinline__ int planner_next_source(const Best b, const int sx, const int sy,
+                                                   const int nb, const int max_iter,
+                                                   const double thr, const double vg_end,
+                                                   int32_t *ls, int &tx, int &ty, int &done,
+                                                   int &status) {
+  const int qd = (int)(b.key >> 40), i = (int)((b.key >> 20) & 0xFFFFF), j = (int)(b.key & 0xFFFFF);
+  tx = (qd == 0 || qd == 3) ? sx + i : sx - i;
+  ty = (qd < 2) ? sy + j : sy - j;
+  int nnb = nb + 1;
+  ls[2 * nnb] = tx;
+  ls[2 * nnb + 1] = ty;
+  done = 0;
+  if (nnb > max_iter) { done = 1; status = VHP_MAX_ITER; }
+  else if (!(vg_end <= thr)) done = 1; // loop test :127
+  else if (tx == sx && ty == sy) {
+    // fixed point: the same source again -> every further iteration is identical
+    while (nnb <= max_iter) {
+      ++nnb;
+      ls[2 * nnb] = tx;
+      ls[2 * nnb + 1] = ty;
+    }
+    done = 1;
+    status = VHP_MAX_ITER;
+  }
+  return nnb;
+}
+
+// lightSources_[nb] = end (:141) and reconstructPath (:1183-1213): walk end -> start through
+// cameFrom_ / lightSources_, reverse, sum the segment lengths.  Returns the number of points.
+__device__ __forceinline__ long planner_reconstruct(const int status, const int nb, const int ex,
+                                                    const int ey, const int nx, const int ls_cap,
+                                                    int32_t *ls, const int32_t *came, int32_t *path,
+                                                    double &total) {
+  long n = 0;
+  total = 0.0;
+  if (status != VHP_OK) return 0;
+  ls[2 * nb] = ex; ls[2 * nb + 1] = ey;
+  int x = ex, y = ey;
+  int t = __ldcg(came + (size_t)y * nx + x), t_old = -2;
+  while (t != t_old && t >= 0 && n < ls_cap - 1) {
+    path[2 * n] = x; path[2 * n + 1] = y; ++n;
+    t_old = t;
+    x = ls[2 * t]; y = ls[2 * t + 1];
+    t = __ldcg(came + (size_t)y * nx + x);
+  }
+  path[2 * n] = x; path[2 * n + 1] = y; ++n;
+  for (long a = 0, b = n - 1; a < b; ++a, --b) {
+    const int tx = path[2 * a], ty = path[2 * a + 1];
+    path[2 * a] = path[2 * b]; path[2 * a + 1] = path[2 * b + 1];
+    path[2 * b] = tx; path[2 * b + 1] = ty;
+  }
+  for (long k = 0; k + 1 < n; ++k)
+    total = __dadd_rn(total, eval_d(path[2 * k], path[2 * k + 1], path[2 * k + 2], path[2 * k + 3]));
+  return n;
+}
+
 // lane 0 of the warp ends up with the warp's best
 __device__ __forceinline__ Best warp_best(Best b) {
 #pragma unroll

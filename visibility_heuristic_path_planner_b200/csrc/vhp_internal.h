@@ -90,6 +90,23 @@ cudaError_t vhp_launch_sweep_window(const VhpTilePlanes &pl, int nx, int ny, int
                                     void *d_out_strip, const double *d_rcp2, int *d_err,
                                     void *d_grid_ws, int grid_ctas, cudaStream_t st,
                                     int64_t *launches);
+// one LARGE planner problem on the whole GPU, host-driven loop (capi.cu: planner_grid_one):
+// reset + validity checks; next-source selection after each sweep + epilogue; outputs.
+// d_ctl = int[5] {done, next x, next y, status, nb_of_sources}
+cudaError_t vhp_launch_grid_planner_begin(const VhpTilePlanes &pl, int nx, int ny, int stx, int sty,
+                                          int ex, int ey, double thr, double *d_vg, double *d_hc,
+                                          int32_t *d_came, int32_t *d_ls, int *d_ctl,
+                                          cudaStream_t st, int64_t *launches);
+cudaError_t vhp_launch_grid_planner_step(const unsigned long long *d_best, int nx, int ex, int ey,
+                                         double thr, int max_iter, const double *d_vg,
+                                         int32_t *d_ls, int *d_ctl, cudaStream_t st,
+                                         int64_t *launches);
+cudaError_t vhp_launch_grid_planner_finish(const int *d_ctl, int nx, int ny, int ex, int ey,
+                                           int ls_cap, int32_t *d_ls, const int32_t *d_came,
+                                           double *d_vis, const double *d_vg, int32_t *d_status,
+                                           int32_t *d_nb, double *d_path_len, int32_t *d_path_n,
+                                           int32_t *d_path, float *d_vg32, float *d_vis32,
+                                           cudaStream_t st, int64_t *launches);
 int vhp_strip_epilogue_blocks(int sm_count);
 cudaError_t vhp_launch_strip_epilogue(int nx, int ny, int y0, int y1, int sx, int sy, int ex, int ey,
                                       double thr, int nb, const int32_t *d_ls, const double *d_vis,

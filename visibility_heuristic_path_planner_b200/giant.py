@@ -106,6 +106,8 @@ class StripPlanner:
         self.owner_of = [k % self.world for k in range(nstrips)]
         self.mine = [k for k in range(nstrips) if self.owner_of[k] == self.rank]
         self.occ = torch.from_numpy(occ).to(self.dev)
+        # the map never changes: pack its bit planes once instead of before every sweep
+        self._check(self.lib.vhp_prepare_maps_dev(self.ctx.h, self.occ.data_ptr(), 1, self.nx, self.ny))
         f = {}
         for k in self.mine:
             rows = self.strips[k][1] - self.strips[k][0]
