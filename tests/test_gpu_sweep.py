@@ -22,11 +22,14 @@ def vhp():
     return m
 
 
-@pytest.fixture(scope="module", params=["auto", "naive"])  # auto = the tile wavefront kernel
+# auto = the tile wavefront kernel, one CTA per pair; grid = the same tile body with every sweep
+# spread over many CTAs (what a few sweeps of a large map take by default; forced here)
+@pytest.fixture(scope="module", params=["auto", "naive", "grid"])
 def ctx(request, vhp):
-    os.environ["VHP_SWEEP_IMPL"] = request.param
+    os.environ["VHP_SWEEP_IMPL"] = "auto" if request.param == "grid" else request.param
     c = vhp.Context(0)
     os.environ.pop("VHP_SWEEP_IMPL")
+    c.set_grid_sweep(2 if request.param == "grid" else 0)
     yield c
     c.close()
 

@@ -130,6 +130,11 @@ vhp_status check_device_error(vhp_context *ctx) {
   return VHP_OK;
 }
 
+// Grid-mode strip sweep of rows [y0, y1) (see vhp_strip_sweep_dev): CTAs to spread one sweep over.
+int grid_sweep_ctas(const vhp_context *ctx, int rows) {
+  return std::max(2, std::min(2 * ctx->sm_count, (4 * (rows / 32 + 2) + 7) / 8));
+}
+
 enum class Op { Sweep, Raycast };
 
 vhp_status run_dev(vhp_context *ctx, Op op, const uint8_t *d_occ, int nmaps, int nx, int ny,
@@ -146,6 +151,38 @@ vhp_status run_dev(vhp_context *ctx, Op op, const uint8_t *d_occ, int nmaps, int
     vhp_status st = ensure_rcp2(ctx, std::max(nx, ny) + 64);
     if (st != VHP_OK) return st;
     if ((st = pack_tile(ctx, d_occ, nmaps, nx, ny, false)) != VHP_OK) return st;
+    // A few sweeps of a large map: one sweep at a time on the whole GPU (grid mode, see
+    // vhp_strip_sweep_dev) instead of one CTA per pair.  (1000^2: up to 4 pairs, 2048^2 and up: 16.)
+    const size_t cells = (size_t)nx * ny;
+    if (ctx->grid_sweep == 2 ||
+        (ctx->grid_sweep == 1 && n <= std::min<int64_t>(16, (int64_t)(cells / 250000)))) {
+      std::vector<int32_t> h_xy(2 * (size_t)n), h_map;
+      VHP_CUDA(ctx, cudaMemcpyAsync(h_xy.data(), d_xy, h_xy.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      if (d_map) {
+        h_map.resize((size_t)n);
+        VHP_CUDA(ctx, cudaMemcpyAsync(h_map.data(), d_map, h_map.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      }
+      VHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      if ((st = ensure(ctx, ctx->b_grid, vhp_sweep_grid_ws_bytes(nx, ny))) != VHP_OK) return st;
+      int wx, wy, nsum;
+      vhp_tile_plane_geometry(nx, ny, &wx, &wy, &nsum);
+      const int ctas = grid_sweep_ctas(ctx, ny);
+      for (int64_t k = 0; k < n; ++k) {
+        const int sx = h_xy[2 * k], sy = h_xy[2 * k + 1];
+        const int64_t m = d_map ? h_map[k] : 0;
+        if (sx < 0 || sx >= nx || sy < 0 || sy >= ny || m < 0 || m >= nmaps)
+          return fail(ctx, VHP_ERR_INVALID_ARG, "a source / start / end point lies outside the grid");
+        VhpTilePlanes pl = ctx->tile; // planes of map m (the grid kernels sweep "map 0")
+        pl.rowF += m * pl.row_plane; pl.rowR += m * pl.row_plane;
+        pl.colF += m * pl.col_plane; pl.colR += m * pl.col_plane;
+        pl.bsum += m * (size_t)nsum;
+        VHP_CUDA(ctx, vhp_launch_sweep_window(pl, nx, ny, sx, sy, 0, ny, nullptr, dtype,
+                                              (char *)d_out + (size_t)k * cells * esz,
+                                              ctx->rcp2_table, ctx->d_err, ctx->b_grid.p, ctas,
+                                              ctx->stream, &ctx->launches));
+      }
+      return VHP_OK;
+    }
     VHP_CUDA(ctx, vhp_launch_sweep_tile(ctx->tile, nx, ny, d_xy, d_map, n, dtype, d_out,
                                         ctx->rcp2_table, ctx->d_err, ctx->stream, &ctx->launches));
     return VHP_OK;
@@ -240,11 +277,6 @@ vhp_status run_host(vhp_context *ctx, Op op, const uint8_t *occ, int nmaps, int 
 }
 
 // ---- planner ------------------------------------------------------------------
-// Grid-mode strip sweep of rows [y0, y1) (see vhp_strip_sweep_dev): CTAs to spread one sweep over.
-int grid_sweep_ctas(const vhp_context *ctx, int rows) {
-  return std::max(2, std::min(2 * ctx->sm_count, (4 * (rows / 32 + 2) + 7) / 8));
-}
-
 // One LARGE problem on the whole GPU: solve() (src/visibilityBasedSolver.cpp:76-160) driven from
 // the host.  Per iteration: grid-mode sweep of the whole map (many CTAs), per-cell epilogue +
 // arg-min over the whole map (strip epilogue kernels with the strip = the map), next-source
