@@ -399,7 +399,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         host_ctx = vhp.Context(local_rank)
-        out_h = torch.empty((n, ny, nx), dtype=tdt).pin_memory()
+        out_h = torch.empty((n, ny, nx), dtype=tdt, pin_memory=True)  # (no pageable staging copy)
         out_np = out_h.numpy()
         lib, C = host_ctx.lib, __import__("ctypes")
         dt = vhp.F32 if args.store == "f32" else vhp.F64
