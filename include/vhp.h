@@ -242,6 +242,17 @@ vhp_status vhp_config_parse(const char *filename, vhp_config *cfg);
  * glibc srand/rand stream, into occ[ny][nx] (uint8).  Returns the seed used. */
 vhp_status vhp_environment_generate(const vhp_config *cfg, uint8_t *occ,
                                     int64_t *seed_used);
+/* The same rectangle rule (src/environment.cpp:57-79) for a BATCH of maps, generated on the
+ * device: d_occ[nmaps][ny][nx] (uint8, device memory), map k of the call is environment
+ * first_map + k of the family `seed`.  The reference's draws are one sequential glibc rand()
+ * stream per map; a batch needs independent ones, so draw d (0..3: col_1, width, row_1,
+ * height) of obstacle o of map m is vhp_environment_draw(seed, m, o, d): SplitMix64's finaliser
+ * over seed + 0x9E3779B97F4A7C15 * (m * 0x100000001B3 + 4 * o + d + 1), top 31 bits.  Uses
+ * cfg->ncols, nrows, nb_of_obstacles, min/max_width, min/max_height only.  Asynchronous. */
+uint32_t vhp_environment_draw(uint64_t seed, uint64_t map, uint64_t obstacle, uint32_t d);
+vhp_status vhp_environment_generate_batch_dev(vhp_context *ctx, const vhp_config *cfg,
+                                              uint64_t seed, int64_t first_map, int nmaps,
+                                              uint8_t *d_occ);
 /* environment::loadImage (src/environment.cpp:183-214): red channel == 255 ->
  * free.  Reads PNG (8-bit gray/RGB/RGBA/palette, non-interlaced) and binary
  * PGM/PPM.  First call with occ == NULL to get nx, ny. */

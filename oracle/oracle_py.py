@@ -108,12 +108,25 @@ class _Base:
 class Oracle(_Base):
     prefix = "vhp_oracle_"
 
+    def generate_environment_counter(self, nx, ny, nb_of_obstacles, min_w, max_w, min_h, max_h,
+                                     seed, map_index):
+        """Map `map_index` of the family `seed` of the batch generator (counter-based draws)."""
+        f = self.lib.vhp_oracle_generate_environment_counter
+        f.argtypes = [_dp, C.c_int, C.c_int, C.c_long, C.c_long, C.c_long, C.c_long, C.c_long,
+                      C.c_ulonglong, C.c_ulonglong]
+        f.restype = None
+        occ = np.empty((ny, nx))
+        f(occ, nx, ny, nb_of_obstacles, min_w, max_w, min_h, max_h, seed, map_index)
+        return occ
+
     def __init__(self):
         path = os.path.join(HERE, "_build", "libvhp_oracle.so")
         if not os.path.exists(path):
             build(ref=False)
         self.lib = C.CDLL(path)
         self._bind_common()
+        self.lib.vhp_oracle_env_draw.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, C.c_uint]
+        self.lib.vhp_oracle_env_draw.restype = C.c_uint
         f = self.lib.vhp_oracle_solve
         f.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                       C.c_double, C.c_long, _dp, _dp, _u64p, _ip,

@@ -289,3 +289,39 @@ void vhp_oracle_generate_environment(double *occ, int nx, int ny,
       for (int y = row_1; y < row_2; ++y) occ[IDX(x, y)] = 0.0;
   }
 }
+
+unsigned vhp_oracle_env_draw(unsigned long long seed, unsigned long long map,
+                             unsigned long long obstacle, unsigned d) {
+  unsigned long long z =
+      seed + 0x9E3779B97F4A7C15ull * (map * 0x100000001B3ull + obstacle * 4ull + d + 1ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (unsigned)(z >> 33);
+}
+
+void vhp_oracle_generate_environment_counter(double *occ, int nx, int ny,
+                                             long nb_of_obstacles, long min_w,
+                                             long max_w, long min_h, long max_h,
+                                             unsigned long long seed,
+                                             unsigned long long map) {
+  /* rectangle rule of src/environment.cpp:57-79, draws as documented in the header */
+  const size_t n = (size_t)nx * (size_t)ny;
+  for (size_t k = 0; k < n; ++k) occ[k] = 1.0;
+  for (long o = 0; o < nb_of_obstacles; ++o) {
+    long col_1 = 1 + (long)(vhp_oracle_env_draw(seed, map, (unsigned long long)o, 0) %
+                            ((unsigned long)nx + 1));
+    long col_2 = col_1 + min_w + (long)(vhp_oracle_env_draw(seed, map, (unsigned long long)o, 1) %
+                                        ((unsigned long)max_w - (unsigned long)min_w + 1));
+    long row_1 = 1 + (long)(vhp_oracle_env_draw(seed, map, (unsigned long long)o, 2) %
+                            ((unsigned long)ny + 1));
+    long row_2 = row_1 + min_h + (long)(vhp_oracle_env_draw(seed, map, (unsigned long long)o, 3) %
+                                        ((unsigned long)max_h - (unsigned long)min_h + 1));
+    if (col_1 > nx - 1) col_1 = nx - 1;
+    if (col_2 > nx - 1) col_2 = nx - 1;
+    if (row_1 > ny - 1) row_1 = ny - 1;
+    if (row_2 > ny - 1) row_2 = ny - 1;
+    for (long x = col_1; x < col_2; ++x)
+      for (long y = row_1; y < row_2; ++y) occ[IDX(x, y)] = 0.0;
+  }
+}

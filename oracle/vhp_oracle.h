@@ -92,6 +92,20 @@ void vhp_oracle_generate_environment(double *occ, int nx, int ny,
                                      long max_w, long min_h, long max_h,
                                      int seed);
 
+/* The same rectangle rule (src/environment.cpp:57-79) with the counter-based draws of the
+ * device-side batch generator (include/vhp.h, vhp_environment_generate_batch_dev): draw d of
+ * obstacle o of map `map` = top 31 bits of SplitMix64's finaliser over
+ * seed + 0x9E3779B97F4A7C15 * (map * 0x100000001B3 + 4 * o + d + 1).  Not reference code: the
+ * reference draws from one sequential rand() stream; this restates the generator this
+ * repository defines for batches so that the CUDA kernel can be checked. */
+unsigned vhp_oracle_env_draw(unsigned long long seed, unsigned long long map,
+                             unsigned long long obstacle, unsigned d);
+void vhp_oracle_generate_environment_counter(double *occ, int nx, int ny,
+                                             long nb_of_obstacles, long min_w,
+                                             long max_w, long min_h, long max_h,
+                                             unsigned long long seed,
+                                             unsigned long long map);
+
 /* eval_d(), include/solver/visibilityBasedSolver.h:112-115 */
 double vhp_oracle_eval_d(int sx, int sy, int tx, int ty);
 

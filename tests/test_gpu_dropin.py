@@ -146,3 +146,43 @@ def test_solver_handle_fields(tmp_path):
     lib.vhp_solver_destroy.argtypes = [C.c_void_p]
     lib.vhp_solver_destroy(h)
     ctx.close()
+
+
+def test_device_environment_batch_matches_oracle(oracle):
+    """a batch of random-rectangle maps generated on the device equals the CPU
+    restatement of the same counter-based generator, map by map; the maps feed a sweep without
+    ever touching the host."""
+    import torch
+    import visibility_heuristic_path_planner_b200 as vhp
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(dev)
+    ctx = vhp.torch_context(0, stream)
+    lib = ctx.lib
+    for (nx, ny, nb, lo_w, hi_w, lo_h, hi_h, seed, first, nmaps) in (
+            (256, 256, 12, 8, 40, 8, 40, 4321, 0, 40), (101, 77, 10, 10, 20, 5, 9, 7, 1000, 9),
+            (33, 200, 0, 1, 1, 1, 1, 1, 5, 3), (64, 64, 50, 0, 70, 0, 3, 99, 2**33, 4)):
+        occ_t = torch.zeros((nmaps, ny, nx), dtype=torch.uint8, device=dev)
+        with torch.cuda.stream(stream):
+            ctx.generate_environments_dev(occ_t, nb, lo_w, hi_w, lo_h, hi_h, seed, first)
+        stream.synchronize()
+        occ = occ_t.cpu().numpy()
+        for k in range(nmaps):
+            ref = oracle.generate_environment_counter(nx, ny, nb, lo_w, hi_w, lo_h, hi_h, seed, first + k)
+            assert np.array_equal(occ[k], ref.astype(np.uint8)), (nx, ny, k)
+        assert set(np.unique(occ)) <= {0, 1}
+    assert lib.vhp_environment_draw(4321, 3, 2, 1) == oracle.lib.vhp_oracle_env_draw(4321, 3, 2, 1)
+    # device-resident maps straight into a sweep: equal to the oracle on the downloaded map
+    nx = ny = 256
+    occ_t = torch.empty((8, ny, nx), dtype=torch.uint8, device=dev)
+    src = torch.tensor([[5, 5]] * 8, dtype=torch.int32, device=dev)
+    smap = torch.arange(8, dtype=torch.int32, device=dev)
+    out = torch.empty((8, ny, nx), dtype=torch.float64, device=dev)
+    with torch.cuda.stream(stream):
+        ctx.generate_environments_dev(occ_t, 12, 8, 40, 8, 40, 11)
+        occ_t[:, 5, 5] = 1
+        ctx.visibility_batch_dev(occ_t, src, out, smap)
+    stream.synchronize()
+    occ = occ_t.cpu().numpy()
+    for k in (0, 7):
+        assert np.array_equal(out[k].cpu().numpy(), oracle.compute_visibility(occ[k].astype(np.float64), 5, 5))
+    ctx.close()

@@ -154,3 +154,29 @@ def test_environment_generator_vs_reference(oracle, ref_strict):
                  (1000, 1000, 15, 100, 200, 100, 200, 25)]:
         assert np.array_equal(oracle.generate_environment(*args),
                               ref_strict.generate_environment(*args))
+
+
+def test_counter_environment_generator(oracle):
+    """The batch generator's definition (include/vhp.h: SplitMix64 finaliser over a counter,
+    rectangle rule of src/environment.cpp:57-79), restated here with Python integers, equals the
+    C restatement the GPU test checks the device kernel against."""
+    M = (1 << 64) - 1
+
+    def draw(seed, m, o, d):
+        z = (seed + 0x9E3779B97F4A7C15 * ((m * 0x100000001B3 + o * 4 + d + 1) & M)) & M
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        return ((z ^ (z >> 31)) >> 33)
+
+    for seed, m, o, d in ((0, 0, 0, 0), (4321, 3, 2, 1), (2**63 + 5, 2**40, 77, 3), (7, 16383, 5999, 2)):
+        assert oracle.lib.vhp_oracle_env_draw(seed, m, o, d) == draw(seed, m, o, d) < 2**31
+    for (nx, ny, nb, lw, hw, lh, hh, seed, m) in ((64, 48, 12, 3, 9, 2, 11, 5, 9), (101, 101, 10, 10, 20, 10, 20, 2, 0)):
+        occ = np.ones((ny, nx))
+        for o in range(nb):
+            c1 = 1 + draw(seed, m, o, 0) % (nx + 1)
+            c2 = c1 + lw + draw(seed, m, o, 1) % (hw - lw + 1)
+            r1 = 1 + draw(seed, m, o, 2) % (ny + 1)
+            r2 = r1 + lh + draw(seed, m, o, 3) % (hh - lh + 1)
+            c1, c2, r1, r2 = min(c1, nx - 1), min(c2, nx - 1), min(r1, ny - 1), min(r2, ny - 1)
+            occ[r1:r2, c1:c2] = 0
+        assert np.array_equal(occ, oracle.generate_environment_counter(nx, ny, nb, lw, hw, lh, hh, seed, m))

@@ -97,6 +97,9 @@ def load_library(build_if_missing: bool = True):
     lib.vhp_strip_halo_rows.argtypes = [i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int32 * 4)]
     lib.vhp_strip_halo_rows.restype = None
     lib.vhp_context_set_grid_sweep.argtypes = [vp, i32]
+    lib.vhp_environment_draw.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]
+    lib.vhp_environment_draw.restype = C.c_uint32
+    lib.vhp_environment_generate_batch_dev.argtypes = [vp, vp, C.c_uint64, i64, i32, vp]
     lib.vhp_strip_sweep_dev.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, C.POINTER(vp * 4), i32, vp]
     lib.vhp_strip_epilogue_dev.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, C.c_double,
                                            C.c_int32, vp, vp, vp, vp, vp, vp]
@@ -227,6 +230,18 @@ class Context:
             self.h, occ_t.data_ptr(), nmaps, nx, ny, src_xy_t.data_ptr(),
             None if src_map_t is None else src_map_t.data_ptr(), src_xy_t.shape[0], dtype,
             out_t.data_ptr()))
+
+    def generate_environments_dev(self, occ_t, nb_of_obstacles, min_w, max_w, min_h, max_h, seed,
+                                  first_map=0):
+        """Fill occ_t (uint8 CUDA tensor (nmaps, ny, nx)) with random-rectangle environments
+        first_map .. first_map + nmaps - 1 of the family `seed` (vhp_environment_generate_batch_dev)."""
+        nmaps, ny, nx = occ_t.shape
+        cfg = Config()
+        self.lib.vhp_config_default(C.byref(cfg))
+        cfg.ncols, cfg.nrows, cfg.nb_of_obstacles = nx, ny, int(nb_of_obstacles)
+        cfg.min_width, cfg.max_width, cfg.min_height, cfg.max_height = int(min_w), int(max_w), int(min_h), int(max_h)
+        self._check(self.lib.vhp_environment_generate_batch_dev(self.h, C.byref(cfg), int(seed),
+                                                                int(first_map), nmaps, occ_t.data_ptr()))
 
     def prepare_maps_dev(self, occ_t):
         nmaps, ny, nx = occ_t.shape

@@ -560,6 +560,31 @@ vhp_status vhp_selftest_ratio(vhp_context *ctx, int kmax, int64_t *mismatches) {
   return VHP_OK;
 }
 
+uint32_t vhp_environment_draw(uint64_t seed, uint64_t map, uint64_t obstacle, uint32_t d) {
+  return vhp_env_draw(seed, map, obstacle, d);
+}
+
+vhp_status vhp_environment_generate_batch_dev(vhp_context *ctx, const vhp_config *cfg,
+                                              uint64_t seed, int64_t first_map, int nmaps,
+                                              uint8_t *d_occ) {
+  if (!ctx || !cfg || !d_occ || nmaps < 1 || first_map < 0)
+    return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_environment_generate_batch_dev: bad argument");
+  if (cfg->ncols < 1 || cfg->nrows < 1 || cfg->ncols > 16384 || cfg->nrows > 16384 ||
+      cfg->nb_of_obstacles < 0 || cfg->nb_of_obstacles > 0x7fffffff || cfg->min_width < 0 ||
+      cfg->min_height < 0 || cfg->max_width < cfg->min_width || cfg->max_height < cfg->min_height)
+    return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_environment_generate_batch_dev: bad environment settings");
+  VHP_CUDA(ctx, cudaSetDevice(ctx->device));
+  VHP_CUDA(ctx, vhp_launch_env_generate(d_occ, nmaps, (int)cfg->ncols, (int)cfg->nrows, first_map,
+                                        seed, cfg->nb_of_obstacles, cfg->min_width, cfg->max_width,
+                                        cfg->min_height, cfg->max_height, ctx->stream,
+                                        &ctx->launches));
+  if (ctx->tile_src == d_occ) { // bit planes of an older content of this buffer
+    ctx->planes_sticky = false;
+    ctx->tile_src = nullptr;
+  }
+  return VHP_OK;
+}
+
 vhp_status vhp_context_set_grid_sweep(vhp_context *ctx, int mode) {
   if (!ctx || mode < 0 || mode > 2) return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_context_set_grid_sweep: bad argument");
   ctx->grid_sweep = mode;

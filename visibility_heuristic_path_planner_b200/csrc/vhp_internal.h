@@ -120,6 +120,13 @@ cudaError_t vhp_launch_ratio2_selftest(const double *d_rcp2, int kmax,
                                        unsigned long long *d_mismatches, cudaStream_t st,
                                        int64_t *launches);
 
+// random-rectangle environments on the device (kernels_env.cu); vhp_env_draw = its generator
+uint32_t vhp_env_draw(uint64_t seed, uint64_t map, uint64_t obstacle, uint32_t d);
+cudaError_t vhp_launch_env_generate(uint8_t *d_occ, int nmaps, int nx, int ny, int64_t first_map,
+                                    uint64_t seed, int64_t nb_of_obstacles, int64_t min_w,
+                                    int64_t max_w, int64_t min_h, int64_t max_h, cudaStream_t st,
+                                    int64_t *launches);
+
 // K4 ray casting
 cudaError_t vhp_launch_raycast(const uint8_t *d_occ, int nx, int ny,
                                const int32_t *d_src_xy, const int32_t *d_src_map,
