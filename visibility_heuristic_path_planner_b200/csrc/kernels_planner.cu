@@ -36,7 +36,9 @@
 //
 // Cells the reference never visits (column 0 / row 0 unless the source lies on
 // them, loop bounds :434-438,:478-483,:522-527) get no epilogue.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstdint>
 
 #include "planner_common.cuh"
@@ -60,7 +62,11 @@ struct PlannerParams {
   float *vg32, *vis32;
 };
 
-__global__ void __launch_bounds__(kTileWarps * 32) planner_kernel(const PlannerParams p) {
+// NWK warps per CTA: 8 for large maps (their boundary rows take tens of KB of shared memory and
+// one problem must bring its own parallelism); batches of small maps run 4- or 2-warp CTAs so
+// that more problems are resident per SM (a 256 x 256 sweep has too few tile rows for 8 warps).
+template <int NWK>
+__global__ void __launch_bounds__(NWK * 32) planner_kernel(const PlannerParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_ctl[5];              // {done, next x, next y, status, nb_of_sources}
   __shared__ Best s_best[32];
@@ -106,17 +112,39 @@ __global__ void __launch_bounds__(kTileWarps * 32) planner_kernel(const PlannerP
     bool done = s_ctl[0] != 0;
     while (!done) {
       // ---- 1. sweep (visibility_.reset() + the DP of updateVisibility)
-      tile_sweep_cta<double, kTileWarps>(p.fp, map, sx, sy, vis, smem_raw);
+      tile_sweep_cta<double, NWK>(p.fp, map, sx, sy, vis, smem_raw);
       // ---- 2. per-cell epilogue + arg-min
       Best best{~0ull, ~0ull};
       {
-        int X = tid % nx, Y = tid / nx; // cell c = tid + k * blockDim.x, walked incrementally
+        // cell c = tid + k * blockDim.x, walked incrementally, kEpiU cells per round: all their
+        // field loads are issued before the first is used (one CTA has few threads for a whole
+        // map; with one cell in flight per thread the pass was latency-bound at ~1 TB/s in total)
+        constexpr int kEpiU = 4;
+        int X = tid % nx, Y = tid / nx;
         const int bdx = blockDim.x % nx, bdy = blockDim.x / nx;
-        for (size_t c = tid; c < cells; c += blockDim.x) {
-          epilogue_cell(X, Y, c, sx, sy, ex, ey, thr, scale, nb, ls, vis, vg, hc, came, best);
-          X += bdx;
-          Y += bdy;
-          if (X >= nx) { X -= nx; ++Y; }
+        for (size_t c0 = tid; c0 < cells; c0 += (size_t)kEpiU * blockDim.x) {
+          double v[kEpiU], h[kEpiU], g0[kEpiU];
+          int cf[kEpiU];
+#pragma unroll
+          for (int u = 0; u < kEpiU; ++u) {
+            const size_t c = c0 + (size_t)u * blockDim.x;
+            if (c < cells) {
+              v[u] = __ldcg(vis + c);
+              h[u] = __ldcg(hc + c);
+              g0[u] = __ldcg(vg + c);
+              cf[u] = __ldcg(came + c);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kEpiU; ++u) {
+            const size_t c = c0 + (size_t)u * blockDim.x;
+            if (c < cells)
+              epilogue_cell_loaded(X, Y, c, v[u], h[u], g0[u], cf[u], sx, sy, ex, ey, thr, scale, nb,
+                                   ls, vg, hc, came, best);
+            X += bdx;
+            Y += bdy;
+            if (X >= nx) { X -= nx; ++Y; }
+          }
         }
       }
 #pragma unroll
@@ -370,11 +398,22 @@ cudaError_t vhp_launch_planner(const VhpTilePlanes &pl, int nx, int ny, const in
   p.status = d_status; p.nb = d_nb; p.ls = d_ls;
   p.path_len = d_path_len; p.path_n = d_path_n; p.path = d_path;
   p.vg32 = d_vg32; p.vis32 = d_vis32;
-  const size_t smem = tile_smem_bytes<double>(nx, ny);
-  cudaError_t e = cudaFuncSetAttribute(planner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem);
-  if (e != cudaSuccess) return e;
-  planner_kernel<<<(unsigned)nprob, kTileWarps * 32, smem, st>>>(p);
-  if (launches) *launches += 1;
-  return cudaGetLastError();
+  static const int forced = [] {
+    const char *e = std::getenv("VHP_PLANNER_WARPS");
+    return e ? std::atoi(e) : 0;
+  }();
+  int nw = 8;
+  if (std::max(nx, ny) <= 512 && nprob >= 148 * 4) nw = std::max(nx, ny) <= 128 ? 2 : 4;
+  if (forced == 2 || forced == 4 || forced == 8) nw = forced;
+  auto go = [&](auto kern, int nwarps) -> cudaError_t {
+    const size_t smem = tile_smem_bytes<double>(nx, ny, nwarps);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)nprob, nwarps * 32, smem, st>>>(p);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+  };
+  if (nw == 2) return go(planner_kernel<2>, 2);
+  if (nw == 4) return go(planner_kernel<4>, 4);
+  return go(planner_kernel<8>, 8);
 }

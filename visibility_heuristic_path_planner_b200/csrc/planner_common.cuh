@@ -34,6 +34,44 @@ constexpr unsigned long long kHInf = 0x7ff0000000000000ull; // +inf: the cell ha
 // (:424-430, un-contracted), and the running arg-min on (h bits, push order).  The push
 // order is quadrant Q1..Q4, i outer, j inner, of the FIRST quadrant that visits the cell
 // (axis cells are visited twice with the same h; the earlier push wins).
+// The arithmetic of one visited cell with its four field values already loaded (v = vis, h = hc,
+// g0 = vg, cf = came): callers that walk many cells per thread issue the loads of several
+// cells first (memory-level parallelism), then call this.
+__device__ __forceinline__ void epilogue_cell_loaded(const int X, const int Y, const size_t c,
+                                                     const double v, double h, const double g0,
+                                                     int cf, const int sx, const int sy,
+                                                     const int ex, const int ey, const double thr,
+                                                     const double scale, const int nb,
+                                                     const int32_t *__restrict__ ls, double *vg,
+                                                     double *hc, int32_t *came, Best &best) {
+  if ((X == 0 && sx > 0) || (Y == 0 && sy > 0)) return; // never visited (loop bounds :434-527)
+  if (v > 0.0 || thr <= 0.0) { // a dark cell cannot raise vg or gain a parent (thr > 0)
+    const double g = v > g0 ? v : g0; // std::max(v, vg)
+    if (g != g0) vg[c] = g;
+    const bool fresh = v >= thr && cf == VHP_NO_PARENT;
+    if (fresh) {
+      cf = nb;
+      came[c] = nb;
+    }
+    if (cf != VHP_NO_PARENT && (fresh || g != g0)) { // (a parent implies vg >= thr)
+      const int px = __ldcg(ls + 2 * cf), py = __ldcg(ls + 2 * cf + 1);
+      h = __dadd_rn(__dmul_rn(scale, g), __dadd_rn(eval_d(X, Y, ex, ey), eval_d(X, Y, px, py)));
+      hc[c] = h;
+    }
+  }
+  const unsigned long long hb = (unsigned long long)__double_as_longlong(h);
+  if (hb <= best.h && hb != kHInf) {
+    const int dx = X - sx, dy = Y - sy;
+    unsigned long long qd, i, j;
+    if (dx >= 0 && dy >= 0) { qd = 0; i = dx; j = dy; }
+    else if (dx < 0 && dy >= 0) { qd = 1; i = -dx; j = dy; }
+    else if (dx <= 0 && (dx < 0 || sx >= 1)) { qd = 2; i = -dx; j = -dy; }
+    else { qd = 3; i = dx; j = -dy; }
+    const Best cand{hb, (qd << 40) | (i << 20) | j};
+    if (better(cand, best)) best = cand;
+  }
+}
+
 __device__ __forceinline__ void epilogue_cell(const int X, const int Y, const size_t c, const int sx,
                                               const int sy, const int ex, const int ey,
                                               const double thr, const double scale, const int nb,
