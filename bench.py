@@ -309,6 +309,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-planner", action="store_true")
+    ap.add_argument("--no-penumbra", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -431,6 +432,33 @@ def main():
         host_ctx.close()
         del out_h
 
+    # ---- the same grid and batch size with obstacles (kernel-only, rank-local): how the
+    # headline kernel does once the sweep is more than a fill -- reported beside the headline
+    penumbra = None
+    if args.workload == "c2" and not args.no_penumbra and not args.pairs:
+        penumbra = {}
+        for wl in ("c2s", "c4"):
+            m2, s2, sm2, d2 = workload(wl, rank, world)
+            n2, (ny2, nx2) = len(s2), m2.shape[1:]
+            o2 = torch.empty((n2, ny2, nx2), dtype=tdt, device=dev)
+            occ2, src2 = torch.from_numpy(m2).to(dev), torch.from_numpy(s2).to(dev)
+            smap2 = None if sm2 is None else torch.from_numpy(sm2).to(dev)
+            with torch.cuda.stream(stream):
+                for _ in range(3):
+                    ctx.visibility_batch_dev(occ2, src2, o2, smap2)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(10):
+                    ctx.visibility_batch_dev(occ2, src2, o2, smap2)
+                e1.record(stream)
+            stream.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            byts = n2 * nx2 * ny2 * esz + m2.shape[0] * nx2 * ny2
+            penumbra[wl] = {"workload": d2, "ms_per_step": ms, "value": n2 * nx2 * ny2 / ms / 1e6,
+                            "unit": "Gcells/s", "achieved_gbs": byts / ms / 1e6,
+                            "frac_of_hbm_peak": byts / ms / 1e6 / measured_peak()[0], "steps": 10}
+            del o2, occ2, src2
+
     planner = None
     if not args.no_planner:
         planner = planner_leg(vhp, local_rank, rank, world, dist if world > 1 else None, dev,
@@ -464,7 +492,7 @@ def main():
                        "pairs_per_gpu": n, "store": args.store, "parallelism": f"batch-shard x{world}, no collective",
                        "l2": "outputs (%.1f GB per step) exceed the 126 MB L2; the shared map is L2-resident by design" % (n * nx * ny * esz / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": int(launches), "planner": planner}
+            "gpu_launches": int(launches), "planner": planner, "penumbra": penumbra}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
