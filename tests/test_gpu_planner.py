@@ -185,3 +185,25 @@ def test_f32_export(ctx, vhp, oracle):
     assert np.array_equal(r32["vg"][0], r64["vg"][0].astype(np.float32))
     assert np.array_equal(r32["vis"][0], r64["vis"][0].astype(np.float32))
     assert np.array_equal(r32["came"], r64["came"]) and r32["path_len"][0] == r64["path_len"][0]
+
+
+def test_stalling_problems_of_the_bench_batch(ctx, vhp, oracle):
+    """The problems of bench.py's planner batch that stall until max_iter (the reference has no
+    closed set: once the heap's pick is the current source it is picked again forever) and a
+    few that solve: the fast-forward must be invisible in every output -- statuses, the full
+    light-source list, parents, fields and the LAST sweep's visibility -- for two values of
+    max_iter."""
+    import sys
+    sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parents[1]))
+    from bench import planner_workload
+    maps, se, pmap = planner_workload(0)
+    r = ctx.planner_batch(maps, se, prob_map=pmap, threshold=0.5, max_iter=100, fields=False)
+    stall = [int(k) for k in np.flatnonzero(r["status"] == 5)][:4]
+    assert stall, "the batch is expected to contain problems that hit max_iter"
+    picks = stall + [int(k) for k in np.flatnonzero(r["status"] == 0)[:2]]
+    for max_iter in (100, 37):
+        sel = np.array(picks)
+        rr = ctx.planner_batch(maps, se[sel], prob_map=pmap[sel], threshold=0.5, max_iter=max_iter)
+        for i, k in enumerate(picks):
+            ref = oracle.solve(maps[pmap[k]].astype(np.float64), se[k][:2], se[k][2:], 0.5, max_iter)
+            check(rr, i, ref)
