@@ -62,9 +62,9 @@ struct PlannerParams {
   float *vg32, *vis32;
 };
 
-// NWK warps per CTA: 8 for large maps (their boundary rows take tens of KB of shared memory and
-// one problem must bring its own parallelism); batches of small maps run 4- or 2-warp CTAs so
-// that more problems are resident per SM (a 256 x 256 sweep has too few tile rows for 8 warps).
+// NWK warps per CTA: 8 by default.  4- and 2-warp CTAs (more problems resident per SM) were
+// measured slower even on batches of 256 x 256 maps -- the epilogue pass wants the threads --
+// and stay selectable with VHP_PLANNER_WARPS for experiments.
 template <int NWK>
 __global__ void __launch_bounds__(NWK * 32) planner_kernel(const PlannerParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -402,8 +402,7 @@ cudaError_t vhp_launch_planner(const VhpTilePlanes &pl, int nx, int ny, const in
     const char *e = std::getenv("VHP_PLANNER_WARPS");
     return e ? std::atoi(e) : 0;
   }();
-  int nw = 8;
-  if (std::max(nx, ny) <= 512 && nprob >= 148 * 4) nw = std::max(nx, ny) <= 128 ? 2 : 4;
+  int nw = 8; // measured on the 1024 x 256^2 batch: 8 warps 240k solves/s, 4 warps 206k, 2 warps slower still
   if (forced == 2 || forced == 4 || forced == 8) nw = forced;
   auto go = [&](auto kern, int nwarps) -> cudaError_t {
     const size_t smem = tile_smem_bytes<double>(nx, ny, nwarps);
