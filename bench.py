@@ -139,6 +139,37 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Run this rank on the CPUs of its GPU's NUMA node, so that the pinned host buffers of the
+    end-to-end leg are allocated next to the GPU's PCIe root (ranks launched by torchrun are not
+    bound; with several ranks the D2H streams otherwise cross the socket interconnect).
+    Best effort: silently does nothing where sysfs does not expose the topology."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(gpu_index)
+        if hasattr(pr, "pci_bus_id"):
+            dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        else:
+            bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i",
+                                  str(gpu_index)], capture_output=True, text=True, timeout=20).stdout.strip()
+            dom, rest = bus.split(":", 1)
+            dev = f"{dom[-4:].lower()}:{rest.lower()}"
+        node = int(open(f"/sys/bus/pci/devices/{dev}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -328,6 +359,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -489,7 +521,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "grid": [nx, ny],
-                       "pairs_per_gpu": n, "store": args.store, "parallelism": f"batch-shard x{world}, no collective",
+                       "pairs_per_gpu": n, "store": args.store, "parallelism": f"batch-shard x{world}, no collective", "rank0_numa_node": numa_node,
                        "l2": "outputs (%.1f GB per step) exceed the 126 MB L2; the shared map is L2-resident by design" % (n * nx * ny * esz / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches), "planner": planner, "penumbra": penumbra}
