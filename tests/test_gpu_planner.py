@@ -207,3 +207,21 @@ def test_stalling_problems_of_the_bench_batch(ctx, vhp, oracle):
         for i, k in enumerate(picks):
             ref = oracle.solve(maps[pmap[k]].astype(np.float64), se[k][:2], se[k][2:], 0.5, max_iter)
             check(rr, i, ref)
+
+
+def test_wide_map_takes_the_grid_route(vhp, oracle):
+    """A map too wide for the persistent single-CTA kernel (its boundary rows do not fit shared
+    memory) is solved on the many-CTA route by default, and refused only if that route is
+    switched off."""
+    nx, ny = 12000, 48
+    occ = rect_map(nx, ny, 300, 12, 4, 30)
+    occ[5, 5] = occ[40, 11990] = occ[20, 6000] = 1
+    se = np.array([[5, 5, 11990, 40], [6000, 20, 5, 5]], np.int32)
+    c = vhp.Context(0)
+    r = c.planner_batch(occ, se, threshold=0.3, max_iter=12)
+    for k in range(2):
+        check(r, k, oracle.solve(occ, se[k][:2], se[k][2:], 0.3, 12))
+    c.set_grid_sweep(0)
+    with pytest.raises(vhp.VhpError):
+        c.planner_batch(occ, se, threshold=0.3, max_iter=12)
+    c.close()

@@ -66,7 +66,8 @@ def test_golden_sweeps(ctx, vhp):
 
 @pytest.mark.parametrize("shape", [(1, 1), (1, 9), (9, 1), (2, 2), (3, 5), (31, 33), (64, 64),
                                    (127, 129), (130, 61), (257, 255), (256, 256), (300, 200),
-                                   (513, 40), (40, 517)])
+                                   (513, 40), (40, 517), (12000, 40)])  # the last: too wide for the
+                                                                        # one-CTA kernel (naive / grid only)
 def test_random_maps_all_source_positions(ctx, vhp, oracle, shape):
     nx, ny = shape
     g = np.random.default_rng(nx * 1000 + ny)

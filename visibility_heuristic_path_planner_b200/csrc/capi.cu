@@ -147,15 +147,20 @@ vhp_status run_dev(vhp_context *ctx, Op op, const uint8_t *d_occ, int nmaps, int
     return VHP_OK;
   }
   const size_t esz = dtype == VHP_F32 ? 4 : 8;
-  if (ctx->sweep_impl == 0 && vhp_sweep_tile_supported(nx, ny)) {
+  const size_t cells = (size_t)nx * ny;
+  // A few sweeps of a large map: one sweep at a time on the whole GPU (grid mode, see
+  // vhp_strip_sweep_dev) instead of one CTA per pair.  (1000^2: up to 4 pairs, 2048^2 and up: 16;
+  // maps too wide for the one-CTA kernel's shared memory: up to 16 pairs whatever the size.)
+  const bool tile_ok = vhp_sweep_tile_supported(nx, ny);
+  const bool use_grid =
+      ctx->sweep_impl == 0 && vhp_sweep_grid_supported(nx, ny) &&
+      (ctx->grid_sweep == 2 ||
+       (ctx->grid_sweep == 1 && n <= (tile_ok ? std::min<int64_t>(16, (int64_t)(cells / 250000)) : 16)));
+  if (ctx->sweep_impl == 0 && (tile_ok || use_grid)) {
     vhp_status st = ensure_rcp2(ctx, std::max(nx, ny) + 64);
     if (st != VHP_OK) return st;
     if ((st = pack_tile(ctx, d_occ, nmaps, nx, ny, false)) != VHP_OK) return st;
-    // A few sweeps of a large map: one sweep at a time on the whole GPU (grid mode, see
-    // vhp_strip_sweep_dev) instead of one CTA per pair.  (1000^2: up to 4 pairs, 2048^2 and up: 16.)
-    const size_t cells = (size_t)nx * ny;
-    if (ctx->grid_sweep == 2 ||
-        (ctx->grid_sweep == 1 && n <= std::min<int64_t>(16, (int64_t)(cells / 250000)))) {
+    if (use_grid) {
       std::vector<int32_t> h_xy(2 * (size_t)n), h_map;
       VHP_CUDA(ctx, cudaMemcpyAsync(h_xy.data(), d_xy, h_xy.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
       if (d_map) {
@@ -226,7 +231,8 @@ vhp_status run_host(vhp_context *ctx, Op op, const uint8_t *occ, int nmaps, int 
                                   cudaMemcpyHostToDevice, ctx->stream));
   ctx->planes_sticky = false; // b_occ content changed
   ctx->tile_src = nullptr;
-  if (op == Op::Sweep && ctx->sweep_impl == 0 && vhp_sweep_tile_supported(nx, ny)) {
+  if (op == Op::Sweep && ctx->sweep_impl == 0 &&
+      (vhp_sweep_tile_supported(nx, ny) || vhp_sweep_grid_supported(nx, ny))) {
     // pack once for all chunks
     if ((st = pack_tile(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, true)) != VHP_OK)
       return st;
@@ -327,7 +333,9 @@ vhp_status planner_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx
                        const int32_t *d_se, const int32_t *d_pmap, int64_t nprob, double thr,
                        int32_t max_iter, int32_t ls_cap, vhp_dtype dtype, const vhp_planner_out &o) {
   if (nprob == 0) return VHP_OK;
-  if (!vhp_planner_supported(nx, ny))
+  // maps too wide for the persistent single-CTA kernel still run on the grid route
+  const bool cta_ok = vhp_planner_supported(nx, ny);
+  if (!cta_ok && !(ctx->grid_sweep != 0 && vhp_sweep_grid_supported(nx, ny)))
     return fail(ctx, VHP_ERR_UNSUPPORTED, "planner: grid too large for the single-CTA kernel");
   if (ls_cap < max_iter + 2 || max_iter < 0)
     return fail(ctx, VHP_ERR_INVALID_ARG, "planner: ls_cap must be >= max_iter + 2");
@@ -363,7 +371,8 @@ vhp_status planner_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx
   // 48 @4096^2, 184 @8192^2; grid route 0.3, 0.7, 2.8, 7.5 -- but its problems run one after the
   // other, so it only wins for a handful of problems, more of them the larger the map.
   const int64_t grid_max_prob = std::max<int64_t>(1, std::min<int64_t>(24, (int64_t)(cells / 100000)));
-  const bool grid_route = ctx->grid_sweep == 2 || (ctx->grid_sweep == 1 && nprob <= grid_max_prob);
+  const bool grid_route = !cta_ok || ctx->grid_sweep == 2 ||
+                          (ctx->grid_sweep == 1 && nprob <= grid_max_prob && vhp_sweep_grid_supported(nx, ny));
   std::vector<int32_t> h_se, h_pmap;
   if (grid_route) {
     h_se.resize(4 * (size_t)nprob);
@@ -505,7 +514,8 @@ vhp_status vhp_prepare_maps_dev(vhp_context *ctx, const uint8_t *d_occ, int nmap
   if (!ctx || !d_occ || nmaps < 1 || nx < 1 || ny < 1)
     return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_prepare_maps_dev: bad argument");
   VHP_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (!vhp_sweep_tile_supported(nx, ny)) return VHP_OK; // the naive kernel reads the byte maps
+  if (!vhp_sweep_tile_supported(nx, ny) && !vhp_sweep_grid_supported(nx, ny))
+    return VHP_OK; // the naive kernel reads the byte maps
   const vhp_status st = pack_tile(ctx, d_occ, nmaps, nx, ny, true);
   if (st == VHP_OK) ctx->planes_sticky = true;
   return st;
@@ -603,7 +613,8 @@ vhp_status vhp_strip_sweep_dev(vhp_context *ctx, const uint8_t *d_occ, int nx, i
   if (sx < 0 || sx >= nx || sy < 0 || sy >= ny)
     return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_strip_sweep_dev: source outside the grid");
   if (dtype != VHP_F32 && dtype != VHP_F64) return fail(ctx, VHP_ERR_INVALID_ARG, "bad dtype");
-  if (!vhp_sweep_tile_supported(nx, ny))
+  const bool cta_ok = vhp_sweep_tile_supported(nx, ny);
+  if (!cta_ok && !(ctx->grid_sweep != 0 && vhp_sweep_grid_supported(nx, ny)))
     return fail(ctx, VHP_ERR_UNSUPPORTED, "vhp_strip_sweep_dev: grid too wide for the tile kernel");
   int32_t rows[4];
   vhp_window_halo_rows(nx, ny, sx, sy, y0, y1, rows);
@@ -618,7 +629,8 @@ vhp_status vhp_strip_sweep_dev(vhp_context *ctx, const uint8_t *d_occ, int nx, i
   // rows of the window, at most two per SM.
   const int grid_mode = ctx->grid_sweep;
   int grid_ctas = 1;
-  if (grid_mode && (int64_t)nx * (y1 - y0) >= (grid_mode > 1 ? 0 : (1 << 20))) {
+  if (!cta_ok || (grid_mode && vhp_sweep_grid_supported(nx, ny) &&
+                  (int64_t)nx * (y1 - y0) >= (grid_mode > 1 ? 0 : (1 << 20)))) {
     grid_ctas = grid_sweep_ctas(ctx, y1 - y0);
     if ((st = ensure(ctx, ctx->b_grid, vhp_sweep_grid_ws_bytes(nx, ny))) != VHP_OK) return st;
   }

@@ -200,6 +200,12 @@ bool vhp_sweep_tile_supported(int nx, int ny) {
          tile_smem_bytes<double>(nx, ny) <= 227u * 1024u;
 }
 
+// grid mode keeps the boundary rows in global memory: wider maps than the one-CTA kernel
+bool vhp_sweep_grid_supported(int nx, int ny) {
+  return nx >= 1 && ny >= 1 && std::max(nx, ny) <= 16384 &&
+         tile_smem_bytes_grid<double>(nx, ny) <= 227u * 1024u;
+}
+
 void vhp_tile_plane_geometry(int nx, int ny, int *wx, int *wy, int *sum_words_per_map) {
   *wx = ((nx + 31) >> 5) + 1;
   *wy = ((ny + 31) >> 5) + 1;

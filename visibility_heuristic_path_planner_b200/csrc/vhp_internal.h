@@ -70,6 +70,7 @@ size_t vhp_sweep_naive_scratch_bytes(int nx, int ny, int64_t npairs);
 
 // K1, tile wavefront (32 x 32 tiles, uniform tiles are plain fills): the default.
 bool vhp_sweep_tile_supported(int nx, int ny);
+bool vhp_sweep_grid_supported(int nx, int ny); // many-CTA grid mode (boundary rows in global memory)
 void vhp_tile_plane_geometry(int nx, int ny, int *wx, int *wy, int *sum_words_per_map);
 cudaError_t vhp_launch_pack_tile(const uint8_t *d_occ, int nmaps, int nx, int ny, uint32_t *rowF,
                                  uint32_t *rowR, uint32_t *colF, uint32_t *colR, uint32_t *bsum,
