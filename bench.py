@@ -341,6 +341,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-planner", action="store_true")
     ap.add_argument("--no-penumbra", action="store_true")
+    ap.add_argument("--no-giant", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -491,6 +492,35 @@ def main():
                             "frac_of_hbm_peak": byts / ms / 1e6 / measured_peak()[0], "steps": 10}
             del o2, occ2, src2
 
+    # ---- BASELINE configs[4] shape on ONE GPU: one planner problem on a dense 8192 x 8192 map
+    # (grid route: every sweep spread over the whole GPU); rank 0 only, not part of `value`
+    giant = None
+    if args.workload == "c2" and not args.no_giant and not args.pairs and rank == 0:
+        ng = 8192
+        g = np.random.default_rng(8192)
+        occ_g = np.ones((ng, ng), dtype=np.uint8)
+        for _ in range(6000):
+            x, y = int(g.integers(1, ng)), int(g.integers(1, ng))
+            w, h = int(g.integers(8, 65)), int(g.integers(8, 65))
+            occ_g[y:y + h, x:x + w] = 0
+        free = np.argwhere(occ_g != 0)
+        a, b = free[len(free) // 7], free[-len(free) // 9]
+        se_g = np.array([[a[1], a[0], b[1], b[0]]], np.int32)
+        gctx = vhp.Context(local_rank)
+        gctx.planner_batch(occ_g, se_g, threshold=0.3, max_iter=60, fields=False)  # warm-up
+        gctx.synchronize()
+        t0 = time.perf_counter()
+        rg = gctx.planner_batch(occ_g, se_g, threshold=0.3, max_iter=60, fields=False)
+        gctx.synchronize()
+        tg = time.perf_counter() - t0
+        gctx.close()
+        nbg = int(rg["nb_sources"][0])
+        giant = {"workload": "one planner problem on a dense random-obstacle 8192x8192 map (6000 rectangles 8-64), "
+                             "threshold 0.3, host-buffer vhp_planner_batch incl. the 67 MB map upload",
+                 "ms_per_solve": tg * 1e3, "sources": nbg, "status": int(rg["status"][0]),
+                 "ms_per_iteration": tg * 1e3 / max(nbg, 1), "path_length": float(rg["path_len"][0])}
+        del occ_g, free
+
     planner = None
     if not args.no_planner:
         planner = planner_leg(vhp, local_rank, rank, world, dist if world > 1 else None, dev,
@@ -524,7 +554,7 @@ def main():
                        "pairs_per_gpu": n, "store": args.store, "parallelism": f"batch-shard x{world}, no collective", "rank0_numa_node": numa_node,
                        "l2": "outputs (%.1f GB per step) exceed the 126 MB L2; the shared map is L2-resident by design" % (n * nx * ny * esz / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": int(launches), "planner": planner, "penumbra": penumbra}
+            "gpu_launches": int(launches), "planner": planner, "penumbra": penumbra, "giant": giant}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

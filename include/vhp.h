@@ -227,6 +227,8 @@ typedef struct vhp_config {
   int64_t max_iter;
   double visibility_threshold;
   float light_strength;     /* parsed, unused (reference: lightStrength_ = 1.0) */
+  /* save_results: 0 no; 1 yes; 2 yes, but vhp_solver_create does not write visibilityField.txt
+   * again (the drop-in class rebuilds its handle before every solve()) */
   int32_t timer, save_results, save_local_visibility, save_came_from,
       save_light_sources, save_global_visibility, save_visibility_field, silent;
   int32_t ball_radius;

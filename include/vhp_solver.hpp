@@ -192,7 +192,9 @@ private:
     std::vector<uint8_t> occ(nx * ny);
     for (size_t k = 0; k < occ.size(); ++k) occ[k] = occupancyComplement_->data()[k] != 0.0;
     vhp_config c = toC(*sharedConfig_);
-    if (built_) c.save_results = 0; // visibilityField.txt is written once, by the environment
+    // visibilityField.txt is written once, when the environment is built: 2 = "save results,
+    // the environment file exists already" (vhp.h)
+    if (built_ && c.save_results) c.save_results = 2;
     if (vhp_solver_create(ctx_, &c, occ.data(), (int)nx, (int)ny, &solver_) != VHP_OK)
       throw std::runtime_error("vhp_solver_create failed");
     built_ = true;

@@ -67,6 +67,14 @@ def test_cli_outputs_match_reference_executable(tmp_path, seed, thr):
     for pat in (r"Path length: (\S+)", r"Density of the occupancy grid: (\S+)"):
         assert re.search(pat, out_a).group(1) == re.search(pat, out_b).group(1)
     assert "Visibility computation time in us:" in out_a and "Raycasting computation time in us:" in out_a
+    # the renderings: ours are PNGs, the reference build writes binary PPMs under the same names
+    # (SFML stub); every pixel must agree
+    from PIL import Image
+    for f in ("ResultingPath.png", "standAloneVisibility.png", "rayCastingVisibility.png"):
+        ours = np.asarray(Image.open(os.path.join(a, "output", f)).convert("RGB"))
+        ref = np.asarray(Image.open(os.path.join(b, "output", f)).convert("RGB"))
+        assert ours.shape == ref.shape == (101, 101, 3), f
+        assert np.array_equal(ours, ref), (f, np.argwhere((ours != ref).any(axis=2))[:5].tolist())
 
 
 def test_cli_error_messages(tmp_path):

@@ -9,8 +9,11 @@
 //   saveResults()           :1022-1178                             -> vhp_solver_save_results
 // with the same stdout lines and the same ./output/*.txt formats, so interface.m
 // style consumers keep working.  The compute runs on the GPU (K1/K2-K5/K4); this
-// file only validates, prints and writes files.  PNG renderings
-// (saveStandAloneVisibility, saveImageWithPath) are cosmetic and not reproduced.
+// file only validates, prints and writes files.  The PNG renderings
+//   saveStandAloneVisibility() :898-955, saveRayCastingVisibility() :960-1017,
+//   saveImageWithPath()        :1218-1292
+// are reproduced pixel for pixel (same base image, same drawing order) and written as 8-bit
+// RGBA PNGs with zlib (the reference writes them through SFML).
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -22,6 +25,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <zlib.h>
 
 #include "vhp.h"
 
@@ -47,6 +51,129 @@ const char *kBanner =
 bool in_grid(const vhp_solver *s, int x, int y) {
   // isValid() compares as size_t (.h:101-103): negative coordinates fail
   return (size_t)x < (size_t)s->nx && (size_t)y < (size_t)s->ny;
+}
+
+bool ensure_dir(const std::string &dir);
+
+// ---- PNG renderings --------------------------------------------------------------
+struct Rgb { unsigned char r, g, b; };
+constexpr Rgb kBlack{0, 0, 0}, kWhite{255, 255, 255}, kRed{255, 0, 0}, kGreen{0, 255, 0},
+    kYellow{255, 255, 0}, kMagenta{255, 0, 255}, kCyan{0, 255, 255};
+
+struct Canvas {
+  int w = 0, h = 0;
+  std::vector<Rgb> px;
+  void set(int x, int y, Rgb c) { px[(size_t)y * w + x] = c; }
+};
+
+// the solver's environment image (constructor, :20-33): created black, then rows j = ny-1 .. 1
+// white where free -- image row ny-1-j; the row of j == 0 keeps the creation colour
+Canvas base_image(const vhp_solver *s) {
+  Canvas im;
+  im.w = s->nx; im.h = s->ny;
+  im.px.assign((size_t)s->nx * s->ny, kBlack);
+  for (int j = s->ny - 1; j > 0; --j)
+    for (int i = 0; i < s->nx; ++i)
+      im.set(i, s->ny - 1 - j, s->occ[(size_t)j * s->nx + i] < 1 ? kBlack : kWhite);
+  return im;
+}
+
+void draw_ball(Canvas &im, const vhp_solver *s, int x0, int y0, int radius, Rgb c) {
+  for (int j = -radius; j <= radius; ++j)
+    for (int k = -radius; k <= radius; ++k)
+      if (in_grid(s, x0 + j, y0 + k) && j * j + k * k <= radius * radius) im.set(x0 + j, y0 + k, c);
+}
+
+void png_chunk(std::ofstream &f, const char type[4], const std::vector<unsigned char> &data) {
+  auto be32 = [&](uint32_t v) {
+    const unsigned char b[4] = {(unsigned char)(v >> 24), (unsigned char)(v >> 16), (unsigned char)(v >> 8),
+                                (unsigned char)v};
+    f.write((const char *)b, 4);
+  };
+  be32((uint32_t)data.size());
+  f.write(type, 4);
+  if (!data.empty()) f.write((const char *)data.data(), (std::streamsize)data.size());
+  uLong crc = crc32(0L, (const Bytef *)type, 4);
+  if (!data.empty()) crc = crc32(crc, data.data(), (uInt)data.size());
+  be32((uint32_t)crc);
+}
+
+bool write_png(const std::string &path, const Canvas &im) {
+  std::vector<unsigned char> raw((size_t)im.h * (1 + 4 * (size_t)im.w));
+  size_t o = 0;
+  for (int y = 0; y < im.h; ++y) {
+    raw[o++] = 0; // filter type None
+    for (int x = 0; x < im.w; ++x) {
+      const Rgb c = im.px[(size_t)y * im.w + x];
+      raw[o++] = c.r; raw[o++] = c.g; raw[o++] = c.b; raw[o++] = 255;
+    }
+  }
+  uLongf zlen = compressBound((uLong)raw.size());
+  std::vector<unsigned char> z(zlen);
+  if (compress2(z.data(), &zlen, raw.data(), (uLong)raw.size(), 6) != Z_OK) return false;
+  z.resize(zlen);
+  std::ofstream f(path, std::ios::binary);
+  if (!f) return false;
+  const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+  f.write((const char *)sig, 8);
+  std::vector<unsigned char> ihdr(13);
+  const uint32_t w = (uint32_t)im.w, h = (uint32_t)im.h;
+  for (int b = 0; b < 4; ++b) { ihdr[b] = (unsigned char)(w >> (24 - 8 * b)); ihdr[4 + b] = (unsigned char)(h >> (24 - 8 * b)); }
+  ihdr[8] = 8; ihdr[9] = 6; ihdr[10] = 0; ihdr[11] = 0; ihdr[12] = 0; // 8-bit RGBA, no interlace
+  png_chunk(f, "IHDR", ihdr);
+  png_chunk(f, "IDAT", z);
+  png_chunk(f, "IEND", {});
+  return (bool)f;
+}
+
+// saveStandAloneVisibility (:898-955) / saveRayCastingVisibility (:960-1017): grey levels of
+// the field (rows j >= 1), the light source as a yellow ball with a black ring, occupied
+// cells red
+void save_visibility_image(const vhp_solver *s, const std::vector<double> &field, const char *name) {
+  Canvas im = base_image(s);
+  const int nx = s->nx, ny = s->ny;
+  for (int j = ny - 1; j > 0; --j)
+    for (int i = 0; i < nx; ++i) {
+      const unsigned char v = (unsigned char)(255 * field[(size_t)j * nx + i]); // sf::Color(Uint8...)
+      im.set(i, ny - 1 - j, Rgb{v, v, v});
+    }
+  const int r = s->cfg.ball_radius, x0 = s->ls_x, y0 = ny - 1 - s->ls_y;
+  draw_ball(im, s, x0, y0, r, kYellow);
+  for (int j = -r - 1; j <= r + 1; ++j)
+    for (int k = -r - 1; k <= r + 1; ++k)
+      if (in_grid(s, x0 + j, y0 + k) && j * j + k * k > r * r && j * j + k * k <= (r + 1) * (r + 1))
+        im.set(x0 + j, y0 + k, kBlack);
+  for (int j = ny - 1; j > 0; --j)
+    for (int i = 0; i < nx; ++i)
+      if (s->occ[(size_t)j * nx + i] == 0) im.set(i, ny - 1 - j, kRed);
+  if (ensure_dir("output")) write_png(std::string("output/") + name, im);
+}
+
+// saveImageWithPath (:1218-1292): magenta Bresenham segments, a cyan ball per way point,
+// the start green, the end red
+void save_path_image(const vhp_solver *s) {
+  const size_t n = s->path.size() / 2;
+  if (n == 0) return;
+  Canvas im = base_image(s);
+  const int ny = s->ny;
+  for (size_t i = 0; i + 1 < n; ++i) {
+    int x0 = s->path[2 * i], y0 = ny - 1 - s->path[2 * i + 1];
+    const int x1 = s->path[2 * i + 2], y1 = ny - 1 - s->path[2 * i + 3];
+    const int dx = std::abs(x1 - x0), dy = std::abs(y1 - y0);
+    const int sx = x0 < x1 ? 1 : -1, sy = y0 < y1 ? 1 : -1;
+    int err = dx - dy;
+    while (x0 != x1 || y0 != y1) {
+      im.set(x0, y0, kMagenta);
+      const int e2 = 2 * err;
+      if (e2 > -dy) { err -= dy; x0 += sx; }
+      if (e2 < dx) { err += dx; y0 += sy; }
+    }
+  }
+  const int r = s->cfg.ball_radius;
+  for (size_t i = 0; i < n; ++i) draw_ball(im, s, s->path[2 * i], ny - 1 - s->path[2 * i + 1], r, kCyan);
+  draw_ball(im, s, s->path[0], ny - 1 - s->path[1], r, kGreen);
+  draw_ball(im, s, s->path[2 * (n - 1)], ny - 1 - s->path[2 * (n - 1) + 1], r, kRed);
+  if (ensure_dir("output")) write_png("output/ResultingPath.png", im);
 }
 
 template <typename T, typename F>
@@ -157,7 +284,7 @@ vhp_status vhp_solver_create(vhp_context *ctx, const vhp_config *cfg, const uint
   s->ray.assign(cells, 1.0);
   s->came.assign(cells, VHP_NO_PARENT);
   // the reference's environment writes visibilityField.txt when it is built
-  if (cfg->save_results) save_environment(s, "./output");
+  if (cfg->save_results == 1) save_environment(s, "./output"); // (2: written by an earlier instance)
   *out = s;
   return VHP_OK;
 }
@@ -206,6 +333,7 @@ vhp_status vhp_solver_solve(vhp_solver *s) {
     std::cout << kBanner << "\n" << "Execution time in us: " << duration.count() << "us" << std::endl;
   vhp_solver_save_results(s, "./output");
   if (!s->cfg.silent) std::cout << "Path length: " << s->path_len << std::endl;
+  if (s->cfg.save_results) save_path_image(s); // :1209-1211
   return VHP_OK;
 }
 
@@ -231,7 +359,9 @@ vhp_status vhp_solver_stand_alone_visibility(vhp_solver *s) {
   o.vg = s->vg.data(); o.came = s->came.data(); o.vis = s->vis.data();
   const vhp_status rc = vhp_planner_batch(s->ctx, s->occ.data(), 1, s->nx, s->ny, se, nullptr, 1,
                                           s->cfg.visibility_threshold, 0, 2, VHP_F64, &o);
-  return rc < 0 ? rc : VHP_OK;
+  if (rc < 0) return rc;
+  save_visibility_image(s, s->vis, "standAloneVisibility.png"); // :188
+  return VHP_OK;
 }
 
 vhp_status vhp_solver_benchmark(vhp_solver *s) {
@@ -250,6 +380,8 @@ vhp_status vhp_solver_benchmark(vhp_solver *s) {
   const vhp_status rc = time_sweep_and_raycast(s, s->occ.data(), s->nx, s->ny, sx, sy, s->vis.data(),
                                                s->ray.data(), &us_vis, &us_ray);
   if (rc != VHP_OK) return rc;
+  save_visibility_image(s, s->vis, "standAloneVisibility.png");  // :224
+  save_visibility_image(s, s->ray, "rayCastingVisibility.png");  // :237
   if (!s->cfg.silent) {
     std::cout << kBanner << "\n" << "Visibility computation time in us: " << us_vis << "us" << std::endl;
     std::cout << "Raycasting computation time in us: " << us_ray << "us" << std::endl;
