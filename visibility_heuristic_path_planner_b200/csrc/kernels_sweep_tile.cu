@@ -177,7 +177,9 @@ int tile_warps_for(int nx, int ny, int64_t npairs) {
     const char *e = std::getenv("VHP_TILE_WARPS");
     return e ? std::atoi(e) : 0;
   }();
-  if (forced == 1 || forced == 2 || forced == 4 || forced == 6 || forced == 8) return forced;
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 6 || forced == 8 || forced == 10 ||
+      forced == 16)
+    return forced;
   if (std::max(nx, ny) > 512) return 8;
   return npairs >= 148 * 16 ? 1 : 4; // enough pairs to fill the SMs with single-warp CTAs?
 }
@@ -189,6 +191,8 @@ cudaError_t launch_tile(const TileArgs &p, int64_t npairs, cudaStream_t st) {
     case 2: return launch_tile_nw<OutT, 2, 12>(p, npairs, st);
     case 4: return launch_tile_nw<OutT, 4, 8>(p, npairs, st);
     case 6: return launch_tile_nw<OutT, 6, 4>(p, npairs, st);
+    case 10: return launch_tile_nw<OutT, 10, 3>(p, npairs, st);
+    case 16: return launch_tile_nw<OutT, 16, 2>(p, npairs, st);
     default: return launch_tile_nw<OutT, 8, VHP_NW8_MINB>(p, npairs, st);
   }
 }

@@ -90,6 +90,11 @@
 #ifndef VHP_FILL_UNROLL
 #define VHP_FILL_UNROLL 4
 #endif
+// The select-free step loops only run on full 32 x 32 tiles: a literal trip count lets the
+// compiler drop the exit test (and the convergence check in front of the shuffle) per step.
+#ifndef VHP_FIXED32
+#define VHP_FIXED32 1
+#endif
 
 namespace {
 
@@ -433,8 +438,9 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
     if (ns < 32 && lane >= ns) rowE[lane] = 0.0; // columns beyond the grid
     auto steps = [&](auto masked) { // masked: the tile has occupied cells (or cells off the grid)
       double2 rn = rts[0]; // 1/i of the next step, read one step ahead
+      const int nst = (VHP_FIXED32 && !decltype(masked)::value) ? kTile : ns;
 #pragma unroll kStepUnroll
-      for (int s = 0; s < ns; ++s) {
+      for (int s = 0; s < nst; ++s) {
         const double2 rr = rn;
         rn = rts[s + 1];
         const double up = __shfl_up_sync(kAll, F, 1);
@@ -465,8 +471,9 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
       auto steps = [&](auto masked) {
         OutT *q = ptr;
         double2 rn = rts[0];
+        const int nst = (VHP_FIXED32 && !decltype(masked)::value) ? kTile : ns;
 #pragma unroll kStepUnroll
-        for (int s = 0; s < ns; ++s, q += rs) {
+        for (int s = 0; s < nst; ++s, q += rs) {
           const double2 rr = rn;
           rn = rts[s + 1];
           const double up = __shfl_up_sync(kAll, F, 1);
