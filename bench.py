@@ -432,11 +432,15 @@ def main():
     # ---- end-to-end through the host-buffer C-ABI entry point ------------------
     e2e = None
     if not args.no_e2e:
+        # host threads of the packed result transport: share the cores between the ranks of a box
+        if world > 1 and "VHP_HOST_THREADS" not in os.environ:
+            os.environ["VHP_HOST_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
         host_ctx = vhp.Context(local_rank)
         out_h = torch.empty((n, ny, nx), dtype=tdt, pin_memory=True)  # (no pageable staging copy)
         out_np = out_h.numpy()
         lib, C = host_ctx.lib, __import__("ctypes")
         dt = vhp.F32 if args.store == "f32" else vhp.F64
+        probe = sorted({0, n // 3, n // 2, n - 1})  # pairs checked against the device result
 
         def e2e_step():
             st = lib.vhp_visibility_batch(host_ctx.h, maps.ctypes.data, nmaps, nx, ny,
@@ -444,26 +448,47 @@ def main():
                                           n, dt, out_np.ctypes.data)
             assert st == 0, host_ctx.lib.vhp_last_error(host_ctx.h)
 
-        e2e_step()  # warm-up (allocations, page mapping)
-        barrier()
-        k_e2e = max(1, min(args.steps, 3))
-        t0 = time.perf_counter()
-        for _ in range(k_e2e):
-            e2e_step()
-        torch.cuda.synchronize()
-        t_e2e = (time.perf_counter() - t0) / k_e2e
-        if world > 1:
-            t = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t_e2e = float(t.item())
-        assert np.array_equal(out_np[0], out_t[0].cpu().numpy())
+        def e2e_run(mode):
+            host_ctx.set_result_transport(mode)
+            e2e_step()  # warm-up (allocations, page mapping, host threads)
+            for p in probe:
+                out_np[p].fill(np.nan)  # the timed calls must rewrite them
+            barrier()
+            k = max(1, min(args.steps, 3))
+            t0 = time.perf_counter()
+            for _ in range(k):
+                e2e_step()
+            torch.cuda.synchronize()
+            t = (time.perf_counter() - t0) / k
+            if world > 1:
+                tt = torch.tensor([t], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t = float(tt.item())
+            for p in probe:
+                assert np.array_equal(out_np[p], out_t[p].cpu().numpy()), f"e2e result differs (pair {p})"
+            d2h, res, packed = host_ctx.last_transport()
+            assert res == int(n) * nx * ny * esz
+            return t, k, d2h, packed
+
+        t_e2e, k_e2e, d2h_b, packed = e2e_run(1)   # the default (automatic) transport
+        t_plain, _, d2h_plain, _ = e2e_run(0)      # plain copies, for comparison
         e2e = {"value": cells * world / t_e2e / 1e9, "unit": "Gcells/s",
                "h2d_bytes_per_step": int(maps.nbytes + src.nbytes + (0 if smap is None else smap.nbytes)),
-               "d2h_bytes_per_step": int(n) * nx * ny * esz,
+               "d2h_bytes_per_step": int(d2h_b),
+               "result_bytes_per_step": int(n) * nx * ny * esz,
                "ms_per_step": t_e2e * 1e3, "steps": k_e2e,
-               "api": "vhp_visibility_batch (host buffers; pinned output; H2D + kernel + D2H inside the timed region)"}
-        host_ctx.close()
-        del out_h
+               "transport": ("packed%s: the device classifies 512-byte units of the results as uniform / "
+                             "literal, %s; %s host threads write the uniform units; the host buffer is "
+                             "bit-identical to the plain copy"
+                             % (" (direct)" if packed == 2 else "",
+                                "stores the literal units straight into the pinned host buffer" if packed == 2
+                                else "the literal units are copied as one stream",
+                                os.environ.get("VHP_HOST_THREADS", str(min(32, os.cpu_count() or 1)))))
+                            if packed else "plain",
+               "plain_transport": {"value": cells * world / t_plain / 1e9, "ms_per_step": t_plain * 1e3,
+                                   "d2h_bytes_per_step": int(d2h_plain)},
+               "api": "vhp_visibility_batch (host buffers; pinned output; H2D + kernel + D2H (+ host expansion) "
+                      "inside the timed region; %d result pairs compared with the device-resident run)" % len(probe)}
 
     # ---- the same grid and batch size with obstacles (kernel-only, rank-local): how the
     # headline kernel does once the sweep is more than a fill -- reported beside the headline
@@ -490,7 +515,31 @@ def main():
             penumbra[wl] = {"workload": d2, "ms_per_step": ms, "value": n2 * nx2 * ny2 / ms / 1e6,
                             "unit": "Gcells/s", "achieved_gbs": byts / ms / 1e6,
                             "frac_of_hbm_peak": byts / ms / 1e6 / measured_peak()[0], "steps": 10}
+            if wl == "c2s" and e2e is not None and o2.shape == out_t.shape:
+                # the same host-buffer call on the obstacle workload (automatic transport)
+                def c2s_step():
+                    st = lib.vhp_visibility_batch(host_ctx.h, m2.ctypes.data, m2.shape[0], nx2, ny2,
+                                                  s2.ctypes.data, None, n2, dt, out_np.ctypes.data)
+                    assert st == 0, host_ctx.lib.vhp_last_error(host_ctx.h)
+                host_ctx.set_result_transport(1)
+                c2s_step()
+                for p in probe:
+                    out_np[p].fill(np.nan)
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    c2s_step()
+                t2 = (time.perf_counter() - t0) / 2
+                for p in probe:
+                    assert np.array_equal(out_np[p], o2[p].cpu().numpy()), f"c2s e2e result differs (pair {p})"
+                d2h2, res2, packed2 = host_ctx.last_transport()
+                penumbra[wl]["e2e"] = {"value": n2 * nx2 * ny2 / t2 / 1e9, "unit": "Gcells/s",
+                                       "ms_per_step": t2 * 1e3, "d2h_bytes_per_step": int(d2h2),
+                                       "result_bytes_per_step": int(res2),
+                                       "transport": ["plain", "packed", "packed (direct)"][packed2], "steps": 2}
             del o2, occ2, src2
+    if e2e is not None:
+        host_ctx.close()
+        del out_h
 
     # ---- BASELINE configs[4] shape on ONE GPU: one planner problem on a dense 8192 x 8192 map
     # (grid route: every sweep spread over the whole GPU); rank 0 only, not part of `value`

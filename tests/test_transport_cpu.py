@@ -1,0 +1,86 @@
+"""Host half of the packed result transport (csrc/host_expand.cpp) without a GPU: a numpy
+restatement of the device-side packing (result_transport.cu) produces the chunk, the
+library's thread pool expands it, the bytes must come back exactly."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+UNIT = 512
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import visibility_heuristic_path_planner_b200 as vhp
+    return vhp.load_library()
+
+
+def pack_numpy(raw: bytes, elem: int):
+    """uniform / literal classification of 512-byte units, as pack_results_kernel does it"""
+    valid = len(raw)
+    nunits = (valid + UNIT - 1) // UNIT
+    nwords = (nunits + 31) // 32
+    buf = np.zeros(nunits * UNIT, np.uint8)
+    buf[:valid] = np.frombuffer(raw, np.uint8)
+    buf[valid:] = 0xAB  # whatever lies behind the chunk on the device
+    units = buf.reshape(nunits, UNIT)
+    mask = np.zeros(nwords, np.uint32)
+    base = np.zeros(nwords, np.uint32)
+    desc = np.zeros(nwords * 32, np.uint64)
+    lits, cursor = [], 0
+    # words in a scrambled order, like warps racing for the cursor
+    order = np.random.default_rng(7).permutation(nwords)
+    slots = {}
+    for w in order:
+        m, mine = 0, []
+        for u in range(32):
+            k = w * 32 + u
+            if k >= nunits:
+                break
+            e = units[k].view(np.uint32 if elem == 4 else np.uint64)
+            desc[k] = units[k, :8].view(np.uint64)[0]
+            if not (e == e[0]).all():
+                m |= 1 << u
+                mine.append(units[k])
+        mask[w] = m
+        base[w] = cursor
+        slots[int(w)] = (cursor, mine)
+        cursor += len(mine)
+    lit = np.zeros(max(cursor, 1) * UNIT, np.uint8)
+    for w, (b0, mine) in slots.items():
+        for i, u in enumerate(mine):
+            lit[(b0 + i) * UNIT:(b0 + i + 1) * UNIT] = u
+    return mask, base, desc, lit, nunits, cursor
+
+
+@pytest.mark.parametrize("elem,dtype", [(4, np.float32), (8, np.float64)])
+@pytest.mark.parametrize("n,offset", [(1, 0), (127, 0), (128, 0), (5000, 0), (70001, 0), (70001, 4), (33000, 8)])
+@pytest.mark.parametrize("threads", [1, 5])
+def test_expand_restores_the_bytes(lib, elem, dtype, n, offset, threads):
+    g = np.random.default_rng(n + elem)
+    a = np.ones(n, dtype)
+    # flat runs of 1 and 0 with a few ramps in between, like a visibility field
+    for _ in range(max(1, n // 700)):
+        i, l = int(g.integers(0, n)), int(g.integers(1, 900))
+        kind = int(g.integers(0, 3))
+        a[i:i + l] = 0 if kind == 0 else (1 if kind == 1 else g.random(len(a[i:i + l])))
+    raw = a.tobytes()
+    mask, base, desc, lit, nunits, nlit = pack_numpy(raw, elem)
+    # destination with a chosen misalignment (offset 0: the non-temporal path)
+    backing = np.full(len(raw) + 64 + 16, 0xEE, np.uint8)
+    start = (-backing.ctypes.data) % 16 + offset
+    dst = backing[start:start + len(raw)]
+    st = lib.vhp_expand_packed_chunk(mask.ctypes.data, base.ctypes.data, desc.ctypes.data,
+                                     lit.ctypes.data, nunits, len(raw), dst.ctypes.data, threads)
+    assert st == 0
+    assert dst.tobytes() == raw
+    assert (backing[:start] == 0xEE).all() and (backing[start + len(raw):] == 0xEE).all()
+    if n >= 5000:
+        assert nlit < nunits  # something was uniform
+
+
+def test_expand_rejects_inconsistent_sizes(lib):
+    z = np.zeros(64, np.uint64)
+    assert lib.vhp_expand_packed_chunk(z.ctypes.data, z.ctypes.data, z.ctypes.data, z.ctypes.data,
+                                       2, 400, z.ctypes.data, 1) != 0
+    assert lib.vhp_expand_packed_chunk(None, None, None, None, 0, 0, None, 1) == 0

@@ -97,6 +97,10 @@ def load_library(build_if_missing: bool = True):
     lib.vhp_strip_halo_rows.argtypes = [i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int32 * 4)]
     lib.vhp_strip_halo_rows.restype = None
     lib.vhp_context_set_grid_sweep.argtypes = [vp, i32]
+    lib.vhp_context_set_result_transport.argtypes = [vp, i32]
+    lib.vhp_expand_packed_chunk.argtypes = [vp, vp, vp, vp, i64, i64, vp, i32]
+    lib.vhp_context_last_transport.argtypes = [vp, C.POINTER(i64), C.POINTER(i64),
+                                               C.POINTER(C.c_int32)]
     lib.vhp_environment_draw.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]
     lib.vhp_environment_draw.restype = C.c_uint32
     lib.vhp_environment_generate_batch_dev.argtypes = [vp, vp, C.c_uint64, i64, i32, vp]
@@ -155,6 +159,21 @@ class Context:
         by size (default); 2: always (tests)."""
         self._check(self.lib.vhp_context_set_grid_sweep(self.h, int(mode)))
 
+    def set_result_transport(self, mode: int):
+        """Transport of host-buffer results: 0 plain copies, 1 automatic (default), 2 always
+        packed (uniform / literal 512-byte units, expanded by host threads)."""
+        self._check(self.lib.vhp_context_set_result_transport(self.h, int(mode)))
+
+    def last_transport(self):
+        """(bytes moved device-to-host, bytes of results delivered, transport) of the last
+        host-buffer sweep / ray-casting call; transport 0 = plain copies, 1 = packed with a
+        staged literal stream, 2 = packed with literal units stored straight into a pinned
+        caller buffer."""
+        d2h, res, packed = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+        self._check(self.lib.vhp_context_last_transport(self.h, C.byref(d2h), C.byref(res),
+                                                        C.byref(packed)))
+        return int(d2h.value), int(res.value), int(packed.value)
+
     def synchronize(self):
         self._check(self.lib.vhp_context_synchronize(self.h))
 
@@ -168,23 +187,28 @@ class Context:
         return bad.value
 
     # ---- host (numpy) entry points ------------------------------------------
-    def _batch_host(self, fn, occ, src_xy, src_map, dtype):
+    def _batch_host(self, fn, occ, src_xy, src_map, dtype, out=None):
         occ = _occ_u8(occ)
         nmaps, ny, nx = occ.shape
         xy = np.ascontiguousarray(src_xy, dtype=np.int32).reshape(-1, 2)
         n = xy.shape[0]
         mp = None if src_map is None else np.ascontiguousarray(src_map, dtype=np.int32)
-        out = np.empty((n, ny, nx), dtype=np.float32 if dtype == F32 else np.float64)
+        odt = np.float32 if dtype == F32 else np.float64
+        if out is None:
+            out = np.empty((n, ny, nx), dtype=odt)
+        elif out.dtype != odt or out.shape != (n, ny, nx) or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous (npairs, ny, nx) array of the result dtype")
         self._check(fn(self.h, _np_ptr(occ), nmaps, nx, ny, _np_ptr(xy), _np_ptr(mp), n,
                        dtype, _np_ptr(out)))
         return out
 
-    def visibility_batch(self, occ, src_xy, src_map=None, dtype=F64):
-        """computeVisibility for every (map, source) pair -> (npairs, ny, nx)."""
-        return self._batch_host(self.lib.vhp_visibility_batch, occ, src_xy, src_map, dtype)
+    def visibility_batch(self, occ, src_xy, src_map=None, dtype=F64, out=None):
+        """computeVisibility for every (map, source) pair -> (npairs, ny, nx).  `out`: an
+        array to fill instead of a new one (pinned host memory gets the fastest transport)."""
+        return self._batch_host(self.lib.vhp_visibility_batch, occ, src_xy, src_map, dtype, out)
 
-    def raycast_batch(self, occ, src_xy, src_map=None, dtype=F64):
-        return self._batch_host(self.lib.vhp_raycast_batch, occ, src_xy, src_map, dtype)
+    def raycast_batch(self, occ, src_xy, src_map=None, dtype=F64, out=None):
+        return self._batch_host(self.lib.vhp_raycast_batch, occ, src_xy, src_map, dtype, out)
 
     def planner_batch(self, occ, start_end, prob_map=None, threshold=0.5, max_iter=100,
                       dtype=F64, fields=True):

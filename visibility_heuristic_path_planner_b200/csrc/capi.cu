@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "vhp_internal.h"
@@ -206,8 +207,198 @@ vhp_status run_dev(vhp_context *ctx, Op op, const uint8_t *d_occ, int nmaps, int
   return VHP_OK;
 }
 
-// host buffers: upload, run in chunks, overlap the D2H of chunk c with the
-// kernel of chunk c+1 (two device buffers, copy stream)
+// Plain transport of the host-buffer entry points: run in chunks of pairs from p_begin on and
+// overlap the D2H of chunk c with the kernel of chunk c+1 (two device buffers, copy stream).
+vhp_status run_host_plain(vhp_context *ctx, Op op, int nmaps, int nx, int ny, const int32_t *d_xy,
+                          const int32_t *d_map, int64_t n, int64_t p_begin, vhp_dtype dtype,
+                          void *out) {
+  const size_t cells = (size_t)nx * ny, esz = dtype == VHP_F32 ? 4 : 8;
+  vhp_status st;
+  const size_t chunk_bytes_target = (size_t)1 << 30;
+  int64_t chunk = std::max<int64_t>(1, (int64_t)(chunk_bytes_target / (cells * esz)));
+  chunk = std::min(chunk, n - p_begin);
+  const size_t buf_bytes = (size_t)chunk * cells * esz;
+  if ((st = ensure(ctx, ctx->b_out[0], buf_bytes)) != VHP_OK) return st;
+  if (n - p_begin > chunk && (st = ensure(ctx, ctx->b_out[1], buf_bytes)) != VHP_OK) return st;
+  // pin the caller's buffer for full-rate async copies (ignore "already pinned")
+  const size_t out_bytes = (size_t)n * cells * esz;
+  const bool registered =
+      cudaHostRegister(out, out_bytes, cudaHostRegisterDefault) == cudaSuccess;
+  (void)cudaGetLastError();
+  vhp_status result = VHP_OK;
+  int it = 0;
+  for (int64_t p0 = p_begin; p0 < n && result == VHP_OK; p0 += chunk, ++it) {
+    const int b = it & 1;
+    const int64_t np = std::min(chunk, n - p0);
+    if (it >= 2) { // the copy that last read this buffer must be done
+      cudaError_t e = cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0);
+      if (e != cudaSuccess) { result = cuda_fail(ctx, e, "cudaStreamWaitEvent"); break; }
+    }
+    result = run_dev(ctx, op, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, d_xy + 2 * p0,
+                     d_map ? d_map + p0 : nullptr, np, dtype, ctx->b_out[b].p);
+    if (result != VHP_OK) break;
+    cudaEventRecord(ctx->ev_done[b], ctx->stream);
+    cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0);
+    cudaError_t e = cudaMemcpyAsync((char *)out + (size_t)p0 * cells * esz, ctx->b_out[b].p,
+                                    (size_t)np * cells * esz, cudaMemcpyDeviceToHost,
+                                    ctx->copy_stream);
+    if (e != cudaSuccess) { result = cuda_fail(ctx, e, "cudaMemcpyAsync D2H"); break; }
+    cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream);
+    ctx->last_d2h_bytes += (int64_t)((size_t)np * cells * esz);
+  }
+  cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream);
+  cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+  if (registered) cudaHostUnregister(out);
+  if (result != VHP_OK) return result;
+  if (e1 != cudaSuccess) return cuda_fail(ctx, e1, "sync copy stream");
+  if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "sync stream");
+  return VHP_OK;
+}
+
+// Packed transport (result_transport.cu, host_expand.cpp): every chunk of results is packed on
+// the device into uniform / literal 512-byte units; only the meta data and the literal units
+// cross PCIe and a pool of host threads rebuilds the exact bytes in the caller's buffer.
+// Three sets of buffers: while chunk c is computed and packed, the literals of chunk c-1 are
+// copied and chunk c-2 is expanded.  When the caller's buffer is pinned, mapped and 16-byte
+// aligned ("direct"), the pack kernel stores the literal units straight to their place in it
+// and the host threads only write the uniform units.  In automatic mode the call gives up
+// after the first chunks when they hardly compress; *resume_from is the first pair not
+// delivered.
+vhp_status run_host_packed(vhp_context *ctx, Op op, int nmaps, int nx, int ny, const int32_t *d_xy,
+                           const int32_t *d_map, int64_t n, vhp_dtype dtype, void *out,
+                           int64_t *resume_from) {
+  constexpr int NS = vhp_context::kPackSets;
+  const size_t cells = (size_t)nx * ny, esz = dtype == VHP_F32 ? 4 : 8;
+  const size_t pair_bytes = cells * esz;
+  int64_t chunk = std::max<int64_t>(1, (int64_t)(((size_t)256 << 20) / pair_bytes));
+  chunk = std::min(chunk, n);
+  const int64_t nchunks = (n + chunk - 1) / chunk;
+  const int64_t units_max = (int64_t)(((size_t)chunk * pair_bytes + kVhpPackUnit - 1) / kVhpPackUnit);
+  const size_t meta_max = vhp_pack_meta_bytes(units_max), lit_max = (size_t)units_max * kVhpPackUnit;
+  vhp_status st;
+  // direct mode: a device-accessible address of the caller's buffer, if it is pinned host memory
+  char *out_dev = nullptr;
+  {
+    cudaPointerAttributes attr;
+    void *dp = nullptr;
+    if (ctx->result_direct && (((uintptr_t)out) & 15u) == 0 && pair_bytes % 16 == 0 &&
+        cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+        cudaHostGetDevicePointer(&dp, out, 0) == cudaSuccess)
+      out_dev = (char *)dp;
+    (void)cudaGetLastError();
+  }
+  const bool direct = out_dev != nullptr;
+  ctx->last_transport_packed = direct ? 2 : 1;
+  const int nsets = (int)std::min<int64_t>(NS, nchunks);
+  for (int s = 0; s < nsets; ++s) {
+    if ((st = ensure(ctx, ctx->b_pack_out[s], lit_max)) != VHP_OK) return st;
+    if ((st = ensure(ctx, ctx->b_pack_meta[s], meta_max)) != VHP_OK) return st;
+    if (!direct && (st = ensure(ctx, ctx->b_pack_lit[s], lit_max)) != VHP_OK) return st;
+  }
+  const size_t lit_need = direct ? 0 : lit_max;
+  if (meta_max > ctx->h_pack_meta_cap || lit_need > ctx->h_pack_lit_cap) {
+    for (int s = 0; s < NS; ++s) {
+      if (ctx->h_pack_meta[s]) cudaFreeHost(ctx->h_pack_meta[s]);
+      if (ctx->h_pack_lit[s]) cudaFreeHost(ctx->h_pack_lit[s]);
+      ctx->h_pack_meta[s] = ctx->h_pack_lit[s] = nullptr;
+    }
+    ctx->h_pack_meta_cap = ctx->h_pack_lit_cap = 0;
+    for (int s = 0; s < NS; ++s) {
+      VHP_CUDA(ctx, cudaHostAlloc(&ctx->h_pack_meta[s], meta_max, cudaHostAllocDefault));
+      if (lit_need) VHP_CUDA(ctx, cudaHostAlloc(&ctx->h_pack_lit[s], lit_need, cudaHostAllocDefault));
+    }
+    ctx->h_pack_meta_cap = meta_max;
+    ctx->h_pack_lit_cap = lit_need;
+  }
+  if (!ctx->expand_pool) {
+    int t = 0;
+    if (const char *e = std::getenv("VHP_HOST_THREADS")) t = std::atoi(e);
+    if (t <= 0) t = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+    ctx->expand_pool = new VhpExpandPool(t);
+  }
+  VhpExpandPool &pool = *ctx->expand_pool;
+  int64_t tickets[NS] = {0, 0, 0}, last_ticket = 0;
+  int64_t lit_units_total = 0, units_total = 0;
+  bool bail = false;
+  vhp_status result = VHP_OK;
+
+  auto chunk_units = [&](int64_t it) {
+    const int64_t np = std::min(chunk, n - it * chunk);
+    return (int64_t)(((size_t)np * pair_bytes + kVhpPackUnit - 1) / kVhpPackUnit);
+  };
+  auto launch = [&](int64_t it) -> vhp_status {
+    const int s = (int)(it % NS);
+    const int64_t p0 = it * chunk, np = std::min(chunk, n - p0);
+    vhp_status r = run_dev(ctx, op, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, d_xy + 2 * p0,
+                           d_map ? d_map + p0 : nullptr, np, dtype, ctx->b_pack_out[s].p);
+    if (r != VHP_OK) return r;
+    const int64_t nu = chunk_units(it);
+    const int tail_partial = ((size_t)np * pair_bytes) % kVhpPackUnit != 0;
+    VHP_CUDA(ctx, vhp_launch_pack_results(ctx->b_pack_out[s].p, nu, (int)esz, ctx->b_pack_meta[s].p,
+                                          ctx->b_pack_lit[s].p,
+                                          direct ? out_dev + (size_t)p0 * pair_bytes : nullptr,
+                                          tail_partial, ctx->sm_count, ctx->stream, &ctx->launches));
+    VHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_pack_meta[s], ctx->b_pack_meta[s].p, vhp_pack_meta_bytes(nu),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    VHP_CUDA(ctx, cudaEventRecord(ctx->ev_pack_meta[s], ctx->stream));
+    return VHP_OK;
+  };
+  auto finish = [&](int64_t it) -> vhp_status {
+    const int s = (int)(it % NS);
+    const int64_t p0 = it * chunk, np = std::min(chunk, n - p0);
+    const int64_t nu = chunk_units(it), nwords = (nu + 31) / 32;
+    VHP_CUDA(ctx, cudaEventSynchronize(ctx->ev_pack_meta[s]));
+    const char *meta = (const char *)ctx->h_pack_meta[s];
+    const uint64_t nlit = *(const uint64_t *)meta;
+    if (nlit && !direct) {
+      VHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_pack_lit[s], ctx->b_pack_lit[s].p,
+                                    (size_t)nlit * kVhpPackUnit, cudaMemcpyDeviceToHost,
+                                    ctx->copy_stream));
+      VHP_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    }
+    ctx->last_d2h_bytes += (int64_t)(vhp_pack_meta_bytes(nu) + (size_t)nlit * kVhpPackUnit);
+    lit_units_total += (int64_t)nlit;
+    units_total += nu;
+    VhpPackedChunk c;
+    c.mask = (const uint32_t *)(meta + kVhpPackMetaHead);
+    c.word_base = c.mask + nwords;
+    c.desc = (const uint64_t *)(meta + kVhpPackMetaHead + (size_t)nwords * 8);
+    c.literals = direct ? nullptr : (const char *)ctx->h_pack_lit[s];
+    c.tail = meta + 16;
+    c.dst = (char *)out + (size_t)p0 * pair_bytes;
+    c.nunits = nu;
+    c.valid_bytes = (size_t)np * pair_bytes;
+    tickets[s] = last_ticket = pool.submit(c);
+    return VHP_OK;
+  };
+
+  int64_t launched = 0, finished = 0;
+  for (int64_t it = 0; it < nchunks && result == VHP_OK && !bail; ++it) {
+    const int s = (int)(it % NS);
+    if (tickets[s]) pool.wait(tickets[s]); // staging set s is free again
+    if ((result = launch(it)) != VHP_OK) break;
+    ++launched;
+    if (it >= 1) {
+      if ((result = finish(it - 1)) != VHP_OK) break;
+      ++finished;
+      // automatic mode: results that hardly compress are cheaper to copy directly
+      if (ctx->result_transport == 1 && finished == 1 && lit_units_total * 10 > units_total * 6)
+        bail = true;
+    }
+  }
+  while (result == VHP_OK && finished < launched) {
+    result = finish(finished);
+    if (result == VHP_OK) ++finished;
+  }
+  if (last_ticket) pool.wait(last_ticket);
+  cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+  if (result != VHP_OK) return result;
+  if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "sync stream");
+  *resume_from = std::min(n, launched * chunk);
+  return VHP_OK;
+}
+
+// host buffers: upload, run in chunks, deliver the results (packed or plain transport)
 vhp_status run_host(vhp_context *ctx, Op op, const uint8_t *occ, int nmaps, int nx, int ny,
                     const int32_t *xy, const int32_t *maps, int64_t n, vhp_dtype dtype,
                     void *out) {
@@ -216,6 +407,8 @@ vhp_status run_host(vhp_context *ctx, Op op, const uint8_t *occ, int nmaps, int 
   st = check_points(ctx, xy, 2, maps, n, nmaps, nx, ny,
                     op == Op::Sweep ? "vhp_visibility_batch" : "vhp_raycast_batch");
   if (st != VHP_OK) return st;
+  ctx->last_d2h_bytes = ctx->last_result_bytes = 0;
+  ctx->last_transport_packed = 0;
   if (n == 0) return VHP_OK;
   VHP_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t cells = (size_t)nx * ny, esz = dtype == VHP_F32 ? 4 : 8;
@@ -238,47 +431,21 @@ vhp_status run_host(vhp_context *ctx, Op op, const uint8_t *occ, int nmaps, int 
       return st;
     ctx->planes_sticky = true;
   }
-  const size_t chunk_bytes_target = (size_t)1 << 30;
-  int64_t chunk = std::max<int64_t>(1, (int64_t)(chunk_bytes_target / (cells * esz)));
-  chunk = std::min(chunk, n);
-  const size_t buf_bytes = (size_t)chunk * cells * esz;
-  if ((st = ensure(ctx, ctx->b_out[0], buf_bytes)) != VHP_OK) return st;
-  if (n > chunk && (st = ensure(ctx, ctx->b_out[1], buf_bytes)) != VHP_OK) return st;
-  // pin the caller's buffer for full-rate async copies (ignore "already pinned")
-  const size_t out_bytes = (size_t)n * cells * esz;
-  const bool registered =
-      cudaHostRegister(out, out_bytes, cudaHostRegisterDefault) == cudaSuccess;
-  (void)cudaGetLastError();
   const int32_t *d_xy = (const int32_t *)ctx->b_src.p;
   const int32_t *d_map = maps ? (const int32_t *)ctx->b_map.p : nullptr;
+  const size_t out_bytes = (size_t)n * cells * esz;
+  ctx->last_result_bytes = (int64_t)out_bytes;
+  int64_t p_begin = 0;
   vhp_status result = VHP_OK;
-  int it = 0;
-  for (int64_t p0 = 0; p0 < n && result == VHP_OK; p0 += chunk, ++it) {
-    const int b = it & 1;
-    const int64_t np = std::min(chunk, n - p0);
-    if (it >= 2) { // the copy that last read this buffer must be done
-      cudaError_t e = cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0);
-      if (e != cudaSuccess) { result = cuda_fail(ctx, e, "cudaStreamWaitEvent"); break; }
-    }
-    result = run_dev(ctx, op, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, d_xy + 2 * p0,
-                     d_map ? d_map + p0 : nullptr, np, dtype, ctx->b_out[b].p);
-    if (result != VHP_OK) break;
-    cudaEventRecord(ctx->ev_done[b], ctx->stream);
-    cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0);
-    cudaError_t e = cudaMemcpyAsync((char *)out + (size_t)p0 * cells * esz, ctx->b_out[b].p,
-                                    (size_t)np * cells * esz, cudaMemcpyDeviceToHost,
-                                    ctx->copy_stream);
-    if (e != cudaSuccess) { result = cuda_fail(ctx, e, "cudaMemcpyAsync D2H"); break; }
-    cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream);
+  // small results are not worth the thread pool's wake-up
+  if (ctx->result_transport == 2 || (ctx->result_transport == 1 && out_bytes >= ((size_t)64 << 20))) {
+    result = run_host_packed(ctx, op, nmaps, nx, ny, d_xy, d_map, n, dtype, out, &p_begin);
   }
-  cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream);
-  cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-  if (registered) cudaHostUnregister(out);
+  if (result == VHP_OK && p_begin < n)
+    result = run_host_plain(ctx, op, nmaps, nx, ny, d_xy, d_map, n, p_begin, dtype, out);
   ctx->planes_sticky = false;
   ctx->tile_src = nullptr;
   if (result != VHP_OK) return result;
-  if (e1 != cudaSuccess) return cuda_fail(ctx, e1, "sync copy stream");
-  if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "sync stream");
   return check_device_error(ctx);
 }
 
@@ -479,6 +646,15 @@ vhp_status vhp_context_create(int device, void *cuda_stream, vhp_context **out) 
   ctx->sweep_impl = 0;
   if (impl && std::strcmp(impl, "naive") == 0) ctx->sweep_impl = 1;
   if (const char *e = std::getenv("VHP_GRID_SWEEP")) ctx->grid_sweep = std::atoi(e);
+  for (int i = 0; i < vhp_context::kPackSets; ++i) {
+    VHP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_pack_meta[i], cudaEventDisableTiming));
+    VHP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_pack_lit[i], cudaEventDisableTiming));
+  }
+  if (const char *e = std::getenv("VHP_RESULT_TRANSPORT")) {
+    if (std::strcmp(e, "plain") == 0) ctx->result_transport = 0;
+    else if (std::strcmp(e, "packed") == 0) ctx->result_transport = 2;
+  }
+  if (const char *e = std::getenv("VHP_RESULT_DIRECT")) ctx->result_direct = std::atoi(e) != 0;
   *out = ctx;
   return VHP_OK;
 }
@@ -492,6 +668,16 @@ void vhp_context_destroy(vhp_context *ctx) {
                        &ctx->b_scratch, &ctx->b_planner, &ctx->b_misc, &ctx->b_grid};
   for (VhpDevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
+  delete ctx->expand_pool;
+  for (int i = 0; i < vhp_context::kPackSets; ++i) {
+    if (ctx->b_pack_out[i].p) cudaFree(ctx->b_pack_out[i].p);
+    if (ctx->b_pack_meta[i].p) cudaFree(ctx->b_pack_meta[i].p);
+    if (ctx->b_pack_lit[i].p) cudaFree(ctx->b_pack_lit[i].p);
+    if (ctx->h_pack_meta[i]) cudaFreeHost(ctx->h_pack_meta[i]);
+    if (ctx->h_pack_lit[i]) cudaFreeHost(ctx->h_pack_lit[i]);
+    if (ctx->ev_pack_meta[i]) cudaEventDestroy(ctx->ev_pack_meta[i]);
+    if (ctx->ev_pack_lit[i]) cudaEventDestroy(ctx->ev_pack_lit[i]);
+  }
   if (ctx->tile_buf) cudaFree(ctx->tile_buf);
   if (ctx->rcp2_table) cudaFree(ctx->rcp2_table);
   if (ctx->d_err) cudaFree(ctx->d_err);
@@ -592,6 +778,44 @@ vhp_status vhp_environment_generate_batch_dev(vhp_context *ctx, const vhp_config
     ctx->planes_sticky = false;
     ctx->tile_src = nullptr;
   }
+  return VHP_OK;
+}
+
+vhp_status vhp_context_set_result_transport(vhp_context *ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 2)
+    return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_context_set_result_transport: mode is 0, 1 or 2");
+  ctx->result_transport = mode;
+  return VHP_OK;
+}
+
+vhp_status vhp_context_last_transport(const vhp_context *ctx, int64_t *d2h_bytes,
+                                      int64_t *result_bytes, int32_t *packed) {
+  if (!ctx) return fail(nullptr, VHP_ERR_INVALID_ARG, "null context");
+  if (d2h_bytes) *d2h_bytes = ctx->last_d2h_bytes;
+  if (result_bytes) *result_bytes = ctx->last_result_bytes;
+  if (packed) *packed = ctx->last_transport_packed;
+  return VHP_OK;
+}
+
+vhp_status vhp_expand_packed_chunk(const uint32_t *mask, const uint32_t *word_base,
+                                   const uint64_t *desc, const void *literals, int64_t nunits,
+                                   int64_t valid_bytes, void *dst, int threads) {
+  if (nunits < 0 || valid_bytes < 0 || valid_bytes > nunits * (int64_t)kVhpPackUnit ||
+      valid_bytes <= (nunits - 1) * (int64_t)kVhpPackUnit)
+    return fail(nullptr, VHP_ERR_INVALID_ARG, "vhp_expand_packed_chunk: nunits does not match valid_bytes");
+  if (nunits == 0) return VHP_OK;
+  if (!mask || !word_base || !desc || !dst)
+    return fail(nullptr, VHP_ERR_INVALID_ARG, "vhp_expand_packed_chunk: null argument");
+  VhpPackedChunk c;
+  c.mask = mask;
+  c.word_base = word_base;
+  c.desc = desc;
+  c.literals = (const char *)literals;
+  c.dst = (char *)dst;
+  c.nunits = nunits;
+  c.valid_bytes = (size_t)valid_bytes;
+  VhpExpandPool pool(std::max(1, std::min(threads, 64)));
+  pool.wait(pool.submit(c));
   return VHP_OK;
 }
 

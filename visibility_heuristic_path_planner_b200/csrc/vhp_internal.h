@@ -25,6 +25,49 @@ struct VhpDevBuf {
   size_t cap = 0;
 };
 
+// ---- packed result transport (result_transport.cu, host_expand.cpp) -------------
+// A chunk of results (flat bytes) is cut into 512-byte units; 32 consecutive units make a
+// mask word.  Unit u of word w is literal iff bit u of mask[w]; the literal units of a word
+// are stored back to back from unit slot word_base[w] of the literal stream; every unit has
+// its first 8 bytes in desc[] (the fill pattern of a uniform unit).
+constexpr int kVhpPackUnit = 512;
+constexpr int kVhpPackMetaHead = 16 + kVhpPackUnit; // cursor (padded) + the tail unit
+struct VhpPackedChunk {
+  const uint32_t *mask = nullptr;
+  const uint32_t *word_base = nullptr;
+  const uint64_t *desc = nullptr;
+  const char *literals = nullptr; // null: direct mode, the device stored the literal units in dst
+  const char *tail = nullptr;     // direct mode: a partial, literal last unit
+  char *dst = nullptr;      // where the expanded chunk goes (caller's buffer)
+  int64_t nunits = 0;
+  size_t valid_bytes = 0;   // bytes of the chunk (the last unit may be partial)
+};
+// device-side meta block of one packed chunk: [cursor u64, pad to 16][tail unit][mask][word_base][desc]
+inline size_t vhp_pack_meta_bytes(int64_t nunits) {
+  const int64_t nwords = (nunits + 31) / 32;
+  return kVhpPackMetaHead + (size_t)nwords * 8 + (size_t)nwords * 32 * 8;
+}
+// in: nunits * 512 readable bytes.  Writes the meta block and either the literal stream
+// (host_dst null) or the literal units themselves to host_dst + 512 * unit (a device-accessible
+// host address, 16-byte aligned; tail_partial: the last unit is partial and goes to the meta block).
+cudaError_t vhp_launch_pack_results(const void *d_in, int64_t nunits, int elem_bytes, void *d_meta,
+                                    void *d_literals, void *host_dst, int tail_partial,
+                                    int sm_count, cudaStream_t st, int64_t *launches);
+
+// host threads that expand packed chunks into the caller's buffer (FIFO, each job is spread
+// over all threads)
+class VhpExpandPool {
+ public:
+  explicit VhpExpandPool(int nthreads);
+  ~VhpExpandPool();
+  int threads() const;
+  int64_t submit(const VhpPackedChunk &chunk); // returns a ticket
+  void wait(int64_t ticket);                   // returns when that job and all earlier ones are done
+ private:
+  struct Impl;
+  Impl *impl_;
+};
+
 struct vhp_context {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -54,6 +97,23 @@ struct vhp_context {
   int sweep_impl = 0;
   // strip sweeps over many CTAs: 0 never, 1 for windows of >= 2^20 cells, 2 always
   int grid_sweep = 1;
+  // packed result transport of the host-buffer entry points: 0 plain D2H, 1 automatic
+  // (packed when the results compress), 2 always packed (env VHP_RESULT_TRANSPORT)
+  int result_transport = 1;
+  // packed transport into a pinned, mapped caller buffer: the device stores the literal units
+  // straight into it (env VHP_RESULT_DIRECT=0 keeps the staged literal stream)
+  bool result_direct = true;
+  static constexpr int kPackSets = 3;
+  VhpDevBuf b_pack_out[kPackSets], b_pack_meta[kPackSets], b_pack_lit[kPackSets];
+  void *h_pack_meta[kPackSets] = {nullptr, nullptr, nullptr};
+  void *h_pack_lit[kPackSets] = {nullptr, nullptr, nullptr};
+  size_t h_pack_meta_cap = 0, h_pack_lit_cap = 0;
+  cudaEvent_t ev_pack_meta[kPackSets] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_pack_lit[kPackSets] = {nullptr, nullptr, nullptr};
+  VhpExpandPool *expand_pool = nullptr;
+  // statistics of the last host-buffer call (vhp_context_last_transport)
+  int64_t last_d2h_bytes = 0, last_result_bytes = 0;
+  int last_transport_packed = 0; // 0 plain, 1 packed (staged literal stream), 2 packed (direct)
 };
 
 // ---- kernel launchers (all enqueue on `st`, return cudaGetLastError()) --------
