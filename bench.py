@@ -477,7 +477,7 @@ def main():
                "d2h_bytes_per_step": int(d2h_b),
                "result_bytes_per_step": int(n) * nx * ny * esz,
                "ms_per_step": t_e2e * 1e3, "steps": k_e2e,
-               "transport": ("packed%s: the device classifies 512-byte units of the results as uniform / "
+               "transport": ("packed%s: the device classifies 128-byte units of the results as uniform / "
                              "literal, %s; %s host threads write the uniform units; the host buffer is "
                              "bit-identical to the plain copy"
                              % (" (direct)" if packed == 2 else "",

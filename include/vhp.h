@@ -121,28 +121,30 @@ vhp_status vhp_prepare_maps_dev(vhp_context *ctx, const uint8_t *d_occ, int nmap
 /* Result transport of the host-buffer calls (vhp_visibility_batch, vhp_raycast_batch).
  * Their results are far larger than what PCIe moves in the time the kernels need (16.4 GB per
  * 4096 sweeps of a 1000 x 1000 grid), and visibility fields are mostly flat (lit 1.0, shadow
- * 0.0).  In the packed transport the device classifies every 512-byte unit of a chunk of
- * results as uniform or literal; only the literal units and 8.25 bytes of meta data per unit
- * cross PCIe, and host threads (env VHP_HOST_THREADS, default: all cores, at most 32) rebuild
+ * 0.0).  In the packed transport the device classifies every 128-byte unit of a chunk of
+ * results as uniform or literal; only the literal units and one element plus one bit of meta
+ * data per unit cross PCIe (into pinned, 16-byte aligned memory the GPU stores the literal
+ * units straight to their place), and host threads (env VHP_HOST_THREADS, default: all cores, at most 32) rebuild
  * the exact bytes in `out`.  `out` is bit-identical either way.
  *   mode 0  plain: chunked device-to-host copies straight into `out`
  *   mode 1  automatic (default): packed for results of 64 MB and more, plain for the rest of
  *           a call whose first chunk is more than 60 % literal
  *   mode 2  always packed
  * env VHP_RESULT_TRANSPORT=plain|packed sets the mode at context creation.
- * vhp_context_last_transport reports the last host-buffer call: bytes copied device-to-host,
- * bytes of results delivered, whether the packed transport was used. */
+ * vhp_context_last_transport reports the last host-buffer call: bytes moved device-to-host,
+ * bytes of results delivered, transport used (0 plain, 1 packed with a staged literal stream,
+ * 2 packed with literal units stored straight into the pinned caller buffer). */
 vhp_status vhp_context_set_result_transport(vhp_context *ctx, int mode);
 vhp_status vhp_context_last_transport(const vhp_context *ctx, int64_t *d2h_bytes,
                                       int64_t *result_bytes, int32_t *packed);
 /* The host half of the packed transport on its own (no GPU needed; tests): expand one packed
- * chunk into dst[0 .. valid_bytes) with `threads` host threads.  Unit u (512 bytes; the last
+ * chunk into dst[0 .. valid_bytes) with `threads` host threads.  Unit u (128 bytes; the last
  * one may be partial) is literal iff bit u % 32 of mask[u / 32]; the literal units of mask
- * word w lie back to back from literals + 512 * word_base[w]; a uniform unit repeats the
- * 8-byte pattern desc[u]. */
+ * word w lie back to back from literals + 128 * word_base[w]; a uniform unit repeats the
+ * element desc[u] (elem_bytes = 4 or 8 bytes each). */
 vhp_status vhp_expand_packed_chunk(const uint32_t *mask, const uint32_t *word_base,
-                                   const uint64_t *desc, const void *literals, int64_t nunits,
-                                   int64_t valid_bytes, void *dst, int threads);
+                                   const void *desc, int elem_bytes, const void *literals,
+                                   int64_t nunits, int64_t valid_bytes, void *dst, int threads);
 
 /* ---- a5: batched ray casting (raycasting + the all-targets loop) -------------
  * out[p][y][x] = visibilityRayCasting_ after the loop of benchmark() :228-232 on

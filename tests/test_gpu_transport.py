@@ -1,5 +1,5 @@
 """Result transport of the host-buffer entry points (vhp_visibility_batch, vhp_raycast_batch):
-the packed transport (uniform / literal 512-byte units, expanded by host threads) must leave
+the packed transport (uniform / literal 128-byte units, expanded by host threads) must leave
 exactly the bytes of the plain device-to-host copy in the caller's buffer, and those must
 equal the oracle."""
 import numpy as np

@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-UNIT = 512
+UNIT = 128
 
 
 @pytest.fixture(scope="module")
@@ -16,7 +16,7 @@ def lib():
 
 
 def pack_numpy(raw: bytes, elem: int):
-    """uniform / literal classification of 512-byte units, as pack_results_kernel does it"""
+    """uniform / literal classification of 128-byte units, as pack_results_kernel does it"""
     valid = len(raw)
     nunits = (valid + UNIT - 1) // UNIT
     nwords = (nunits + 31) // 32
@@ -26,7 +26,7 @@ def pack_numpy(raw: bytes, elem: int):
     units = buf.reshape(nunits, UNIT)
     mask = np.zeros(nwords, np.uint32)
     base = np.zeros(nwords, np.uint32)
-    desc = np.zeros(nwords * 32, np.uint64)
+    desc = np.zeros(nwords * 32, np.uint32 if elem == 4 else np.uint64)
     lits, cursor = [], 0
     # words in a scrambled order, like warps racing for the cursor
     order = np.random.default_rng(7).permutation(nwords)
@@ -38,7 +38,7 @@ def pack_numpy(raw: bytes, elem: int):
             if k >= nunits:
                 break
             e = units[k].view(np.uint32 if elem == 4 else np.uint64)
-            desc[k] = units[k, :8].view(np.uint64)[0]
+            desc[k] = e[0]
             if not (e == e[0]).all():
                 m |= 1 << u
                 mine.append(units[k])
@@ -70,7 +70,7 @@ def test_expand_restores_the_bytes(lib, elem, dtype, n, offset, threads):
     backing = np.full(len(raw) + 64 + 16, 0xEE, np.uint8)
     start = (-backing.ctypes.data) % 16 + offset
     dst = backing[start:start + len(raw)]
-    st = lib.vhp_expand_packed_chunk(mask.ctypes.data, base.ctypes.data, desc.ctypes.data,
+    st = lib.vhp_expand_packed_chunk(mask.ctypes.data, base.ctypes.data, desc.ctypes.data, elem,
                                      lit.ctypes.data, nunits, len(raw), dst.ctypes.data, threads)
     assert st == 0
     assert dst.tobytes() == raw
@@ -81,6 +81,8 @@ def test_expand_restores_the_bytes(lib, elem, dtype, n, offset, threads):
 
 def test_expand_rejects_inconsistent_sizes(lib):
     z = np.zeros(64, np.uint64)
-    assert lib.vhp_expand_packed_chunk(z.ctypes.data, z.ctypes.data, z.ctypes.data, z.ctypes.data,
-                                       2, 400, z.ctypes.data, 1) != 0
-    assert lib.vhp_expand_packed_chunk(None, None, None, None, 0, 0, None, 1) == 0
+    assert lib.vhp_expand_packed_chunk(z.ctypes.data, z.ctypes.data, z.ctypes.data, 8, z.ctypes.data,
+                                       2, 100, z.ctypes.data, 1) != 0
+    assert lib.vhp_expand_packed_chunk(z.ctypes.data, z.ctypes.data, z.ctypes.data, 3, z.ctypes.data,
+                                       1, 100, z.ctypes.data, 1) != 0
+    assert lib.vhp_expand_packed_chunk(None, None, None, 4, None, 0, 0, None, 1) == 0

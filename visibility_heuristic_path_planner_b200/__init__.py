@@ -98,7 +98,7 @@ def load_library(build_if_missing: bool = True):
     lib.vhp_strip_halo_rows.restype = None
     lib.vhp_context_set_grid_sweep.argtypes = [vp, i32]
     lib.vhp_context_set_result_transport.argtypes = [vp, i32]
-    lib.vhp_expand_packed_chunk.argtypes = [vp, vp, vp, vp, i64, i64, vp, i32]
+    lib.vhp_expand_packed_chunk.argtypes = [vp, vp, vp, i32, vp, i64, i64, vp, i32]
     lib.vhp_context_last_transport.argtypes = [vp, C.POINTER(i64), C.POINTER(i64),
                                                C.POINTER(C.c_int32)]
     lib.vhp_environment_draw.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]
@@ -161,7 +161,7 @@ class Context:
 
     def set_result_transport(self, mode: int):
         """Transport of host-buffer results: 0 plain copies, 1 automatic (default), 2 always
-        packed (uniform / literal 512-byte units, expanded by host threads)."""
+        packed (uniform / literal 128-byte units, expanded by host threads)."""
         self._check(self.lib.vhp_context_set_result_transport(self.h, int(mode)))
 
     def last_transport(self):

@@ -256,7 +256,7 @@ vhp_status run_host_plain(vhp_context *ctx, Op op, int nmaps, int nx, int ny, co
 }
 
 // Packed transport (result_transport.cu, host_expand.cpp): every chunk of results is packed on
-// the device into uniform / literal 512-byte units; only the meta data and the literal units
+// the device into uniform / literal 128-byte units; only the meta data and the literal units
 // cross PCIe and a pool of host threads rebuilds the exact bytes in the caller's buffer.
 // Three sets of buffers: while chunk c is computed and packed, the literals of chunk c-1 are
 // copied and chunk c-2 is expanded.  When the caller's buffer is pinned, mapped and 16-byte
@@ -274,7 +274,7 @@ vhp_status run_host_packed(vhp_context *ctx, Op op, int nmaps, int nx, int ny, c
   chunk = std::min(chunk, n);
   const int64_t nchunks = (n + chunk - 1) / chunk;
   const int64_t units_max = (int64_t)(((size_t)chunk * pair_bytes + kVhpPackUnit - 1) / kVhpPackUnit);
-  const size_t meta_max = vhp_pack_meta_bytes(units_max), lit_max = (size_t)units_max * kVhpPackUnit;
+  const size_t meta_max = vhp_pack_meta_bytes(units_max, (int)esz), lit_max = (size_t)units_max * kVhpPackUnit;
   vhp_status st;
   // direct mode: a device-accessible address of the caller's buffer, if it is pinned host memory
   char *out_dev = nullptr;
@@ -332,15 +332,20 @@ vhp_status run_host_packed(vhp_context *ctx, Op op, int nmaps, int nx, int ny, c
     vhp_status r = run_dev(ctx, op, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, d_xy + 2 * p0,
                            d_map ? d_map + p0 : nullptr, np, dtype, ctx->b_pack_out[s].p);
     if (r != VHP_OK) return r;
+    // packing (PCIe-bound in direct mode) runs on the copy stream, so that the sweeps of the
+    // next chunk overlap it
+    VHP_CUDA(ctx, cudaEventRecord(ctx->ev_pack_lit[s], ctx->stream));
+    VHP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pack_lit[s], 0));
     const int64_t nu = chunk_units(it);
     const int tail_partial = ((size_t)np * pair_bytes) % kVhpPackUnit != 0;
     VHP_CUDA(ctx, vhp_launch_pack_results(ctx->b_pack_out[s].p, nu, (int)esz, ctx->b_pack_meta[s].p,
                                           ctx->b_pack_lit[s].p,
                                           direct ? out_dev + (size_t)p0 * pair_bytes : nullptr,
-                                          tail_partial, ctx->sm_count, ctx->stream, &ctx->launches));
-    VHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_pack_meta[s], ctx->b_pack_meta[s].p, vhp_pack_meta_bytes(nu),
-                                  cudaMemcpyDeviceToHost, ctx->stream));
-    VHP_CUDA(ctx, cudaEventRecord(ctx->ev_pack_meta[s], ctx->stream));
+                                          tail_partial, ctx->sm_count, ctx->copy_stream,
+                                          &ctx->launches));
+    VHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_pack_meta[s], ctx->b_pack_meta[s].p, vhp_pack_meta_bytes(nu, (int)esz),
+                                  cudaMemcpyDeviceToHost, ctx->copy_stream));
+    VHP_CUDA(ctx, cudaEventRecord(ctx->ev_pack_meta[s], ctx->copy_stream));
     return VHP_OK;
   };
   auto finish = [&](int64_t it) -> vhp_status {
@@ -356,13 +361,14 @@ vhp_status run_host_packed(vhp_context *ctx, Op op, int nmaps, int nx, int ny, c
                                     ctx->copy_stream));
       VHP_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     }
-    ctx->last_d2h_bytes += (int64_t)(vhp_pack_meta_bytes(nu) + (size_t)nlit * kVhpPackUnit);
+    ctx->last_d2h_bytes += (int64_t)(vhp_pack_meta_bytes(nu, (int)esz) + (size_t)nlit * kVhpPackUnit);
     lit_units_total += (int64_t)nlit;
     units_total += nu;
     VhpPackedChunk c;
     c.mask = (const uint32_t *)(meta + kVhpPackMetaHead);
     c.word_base = c.mask + nwords;
-    c.desc = (const uint64_t *)(meta + kVhpPackMetaHead + (size_t)nwords * 8);
+    c.desc = meta + kVhpPackMetaHead + (size_t)nwords * 8;
+    c.elem_bytes = (int)esz;
     c.literals = direct ? nullptr : (const char *)ctx->h_pack_lit[s];
     c.tail = meta + 16;
     c.dst = (char *)out + (size_t)p0 * pair_bytes;
@@ -391,7 +397,9 @@ vhp_status run_host_packed(vhp_context *ctx, Op op, int nmaps, int nx, int ny, c
     if (result == VHP_OK) ++finished;
   }
   if (last_ticket) pool.wait(last_ticket);
+  cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream);
   cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+  if (e2 == cudaSuccess) e2 = e1;
   if (result != VHP_OK) return result;
   if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "sync stream");
   *resume_from = std::min(n, launched * chunk);
@@ -798,8 +806,10 @@ vhp_status vhp_context_last_transport(const vhp_context *ctx, int64_t *d2h_bytes
 }
 
 vhp_status vhp_expand_packed_chunk(const uint32_t *mask, const uint32_t *word_base,
-                                   const uint64_t *desc, const void *literals, int64_t nunits,
-                                   int64_t valid_bytes, void *dst, int threads) {
+                                   const void *desc, int elem_bytes, const void *literals,
+                                   int64_t nunits, int64_t valid_bytes, void *dst, int threads) {
+  if (elem_bytes != 4 && elem_bytes != 8)
+    return fail(nullptr, VHP_ERR_INVALID_ARG, "vhp_expand_packed_chunk: elem_bytes is 4 or 8");
   if (nunits < 0 || valid_bytes < 0 || valid_bytes > nunits * (int64_t)kVhpPackUnit ||
       valid_bytes <= (nunits - 1) * (int64_t)kVhpPackUnit)
     return fail(nullptr, VHP_ERR_INVALID_ARG, "vhp_expand_packed_chunk: nunits does not match valid_bytes");
@@ -810,6 +820,7 @@ vhp_status vhp_expand_packed_chunk(const uint32_t *mask, const uint32_t *word_ba
   c.mask = mask;
   c.word_base = word_base;
   c.desc = desc;
+  c.elem_bytes = elem_bytes;
   c.literals = (const char *)literals;
   c.dst = (char *)dst;
   c.nunits = nunits;

@@ -2,8 +2,8 @@
 //
 // The host-buffer entry points (vhp_visibility_batch, vhp_raycast_batch) return fields in
 // which long runs of cells carry one value (lit: 1.0, shadow: 0.0).  Instead of moving
-// every byte over PCIe, the device packs each chunk of results into 512-byte units that
-// are either "uniform" (one 8-byte pattern) or "literal" (copied verbatim); this file
+// every byte over PCIe, the device packs each chunk of results into 128-byte units that
+// are either "uniform" (one element value) or "literal" (copied verbatim); this file
 // expands a packed chunk into the caller's buffer with a small pool of host threads using
 // non-temporal stores.  The expansion is lossless: the caller's buffer ends up bit-identical
 // to the device buffer.
@@ -22,7 +22,7 @@
 
 namespace {
 
-constexpr int kSliceWords = 16; // 16 mask words = 512 units = 256 KB of output per grab
+constexpr int kSliceWords = 64; // 64 mask words = 2048 units = 256 KB of output per grab
 
 inline void fill_unit(char *dst, uint64_t pat, size_t bytes) {
   if ((((uintptr_t)dst) & 15u) == 0 && bytes == kVhpPackUnit) {
@@ -30,7 +30,7 @@ inline void fill_unit(char *dst, uint64_t pat, size_t bytes) {
     __m128i *d = reinterpret_cast<__m128i *>(dst);
     for (int i = 0; i < kVhpPackUnit / 16; ++i) _mm_stream_si128(d + i, v);
   } else {
-    // pattern period is 8 bytes and units start on multiples of 512 of the chunk
+    // pattern period is 8 bytes and units start on multiples of 128 of the chunk
     uint64_t blk[kVhpPackUnit / 8];
     for (uint64_t &b : blk) b = pat;
     std::memcpy(dst, blk, bytes);
@@ -64,7 +64,14 @@ void expand_words(const VhpPackedChunk &c, int64_t w0, int64_t w1) {
           std::memcpy(c.dst + off, c.tail, bytes);
         }
       } else {
-        fill_unit(c.dst + off, c.desc[u0 + u], bytes);
+        uint64_t pat;
+        if (c.elem_bytes == 4) {
+          const uint32_t e = static_cast<const uint32_t *>(c.desc)[u0 + u];
+          pat = ((uint64_t)e << 32) | e;
+        } else {
+          pat = static_cast<const uint64_t *>(c.desc)[u0 + u];
+        }
+        fill_unit(c.dst + off, pat, bytes);
       }
     }
   }

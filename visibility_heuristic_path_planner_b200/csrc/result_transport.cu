@@ -3,19 +3,21 @@
 // The host-buffer entry points are PCIe-bound: 4096 sweeps of a 1000 x 1000 grid are 16.4 GB
 // of fp32 results per call against a kernel that produces them in 2.5 ms.  Visibility fields
 // are mostly flat (lit 1.0, shadow 0.0), so before a chunk of results leaves the device this
-// kernel classifies every 512-byte unit of it as uniform (all elements equal, bit for bit) or
-// literal, and compacts the literal units into one stream.  Only the stream and 8.25 bytes of
-// meta data per unit cross PCIe; host threads rebuild the exact bytes (host_expand.cpp).
+// kernel classifies every 128-byte unit of it as uniform (all elements equal, bit for bit) or
+// literal, and compacts the literal units into one stream.  Only the stream and one element
+// plus a bit of meta data per unit cross PCIe; host threads rebuild the exact bytes
+// (host_expand.cpp).
 //
-// One warp packs one mask word (32 consecutive units = 16 KB): a unit is one 16-byte load per
-// lane; the literal units of the word get consecutive slots of the stream from one atomicAdd
-// on the chunk's cursor and are copied in a second pass (an L1/L2 hit).
+// Units are 128 bytes (32 fp32 / 16 fp64 cells): one warp-wide 16-byte load covers four units,
+// eight loads make a mask word (32 units = 4 KB), kept in registers.  A unit is uniform when
+// the eight lanes that hold it see one element value, bit for bit.  The literal units of a word
+// get consecutive slots of the stream from one atomicAdd on the chunk's cursor.
 //
 // Direct mode (the caller's buffer is pinned, mapped and 16-byte aligned): the literal units
-// are not compacted but stored by this kernel straight to their final place in host memory
-// (512 contiguous bytes per warp store over PCIe), so the host threads only write the uniform
-// units and no byte of the result is written to host memory twice.  A partial last unit of the
-// chunk cannot be stored whole: it goes to the meta block and the host copies its valid bytes.
+// are not compacted but stored by this kernel straight to their final place in host memory, so
+// the host threads only write the uniform units and no byte of the result is written to host
+// memory twice.  A partial last unit of the chunk cannot be stored whole: it goes to the meta
+// block and the host copies its valid bytes.
 #include <cstdint>
 
 #include "vhp_internal.h"
@@ -23,9 +25,12 @@
 namespace {
 
 constexpr unsigned kAllLanes = 0xffffffffu;
+constexpr int kLanesPerUnit = kVhpPackUnit / 16; // 8
+constexpr int kUnitsPerLoad = 32 / kLanesPerUnit; // 4
+constexpr int kLoadsPerWord = 32 / kUnitsPerLoad; // 8
 
-// meta block: [cursor u64, pad to 16][tail unit 512 B][mask u32 x nwords][word_base u32 x nwords]
-//             [desc u64 x 32*nwords]
+// meta block: [cursor u64, pad to 16][tail unit][mask u32 x nwords][word_base u32 x nwords]
+//             [desc ELEM bytes x 32*nwords]
 template <int ELEM> // element size in bytes: 4 or 8
 __global__ void __launch_bounds__(256)
 pack_results_kernel(const uint4 *__restrict__ in, const int64_t nunits, unsigned char *__restrict__ meta,
@@ -35,31 +40,47 @@ pack_results_kernel(const uint4 *__restrict__ in, const int64_t nunits, unsigned
   uint4 *tail = reinterpret_cast<uint4 *>(meta + 16);
   uint32_t *mask = reinterpret_cast<uint32_t *>(meta + kVhpPackMetaHead);
   uint32_t *word_base = mask + nwords;
-  uint2 *desc = reinterpret_cast<uint2 *>(meta + kVhpPackMetaHead + (size_t)nwords * 8);
+  unsigned char *desc = meta + kVhpPackMetaHead + (size_t)nwords * 8;
   const int lane = threadIdx.x & 31;
+  const int grp = lane / kLanesPerUnit;        // which of the four units of a load this lane holds
+  const int lead = grp * kLanesPerUnit;        // first lane of that unit
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n16 = nunits * kLanesPerUnit;  // readable 16-byte pieces
   for (int64_t w = warp0; w < nwords; w += nwarps) {
     const int64_t u0 = w * 32;
-    const int nu = (int)min((int64_t)32, nunits - u0);
-    const uint4 *src = in + u0 * 32 + lane;
-    bool my_lit = false;
-    uint2 my_desc = make_uint2(0u, 0u);
-#pragma unroll 8
-    for (int u = 0; u < 32; ++u) {
-      if (u < nu) { // warp-uniform
-        const uint4 v = __ldg(src + (size_t)u * 32);
-        const uint32_t f0 = __shfl_sync(kAllLanes, v.x, 0), f1 = __shfl_sync(kAllLanes, v.y, 0);
-        const bool same = ELEM == 4 ? (v.x == f0 && v.y == f0 && v.z == f0 && v.w == f0)
-                                    : (v.x == f0 && v.y == f1 && v.z == f0 && v.w == f1);
-        const bool uni = __all_sync(kAllLanes, same);
-        if (lane == u) {
-          my_lit = !uni;
-          my_desc = make_uint2(f0, f1);
-        }
+    const int64_t q0 = u0 * kLanesPerUnit + lane; // this lane's 16-byte piece of load 0
+    uint4 v[kLoadsPerWord];
+    uint32_t lit_bits = 0;                       // bit k: this lane's unit of load k is literal
+    uint32_t d0 = 0, d1 = 0;                     // first element of unit u0 + lane
+#pragma unroll
+    for (int k = 0; k < kLoadsPerWord; ++k) {
+      const int64_t q = q0 + 32 * k;
+      v[k] = q < n16 ? __ldg(in + q) : make_uint4(0u, 0u, 0u, 0u);
+      const uint32_t f0 = __shfl_sync(kAllLanes, v[k].x, lead), f1 = __shfl_sync(kAllLanes, v[k].y, lead);
+      const bool same = ELEM == 4 ? (v[k].x == f0 && v[k].y == f0 && v[k].z == f0 && v[k].w == f0)
+                                  : (v[k].x == f0 && v[k].y == f1 && v[k].z == f0 && v[k].w == f1);
+      const uint32_t b = __ballot_sync(kAllLanes, same);
+      const bool uni = ((b >> lead) & 0xffu) == 0xffu;
+      lit_bits |= (uni ? 0u : 1u) << k;
+      // lane j describes unit u0 + j = unit (j % 4) of load j / 4
+      const uint32_t e0 = __shfl_sync(kAllLanes, v[k].x, (lane % kUnitsPerLoad) * kLanesPerUnit);
+      const uint32_t e1 = __shfl_sync(kAllLanes, v[k].y, (lane % kUnitsPerLoad) * kLanesPerUnit);
+      if (lane / kUnitsPerLoad == k) {
+        d0 = e0;
+        d1 = e1;
       }
     }
-    const uint32_t m = __ballot_sync(kAllLanes, my_lit);
+    // mask bit of unit u0 + 4k + g  <-  lit_bits bit k of any lane of group g
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < kLoadsPerWord; ++k) {
+      const uint32_t b = __ballot_sync(kAllLanes, (lit_bits >> k) & 1u);
+#pragma unroll
+      for (int g = 0; g < kUnitsPerLoad; ++g)
+        m |= ((b >> (g * kLanesPerUnit)) & 1u) << (k * kUnitsPerLoad + g);
+    }
+    if (u0 + 32 > nunits) m &= (1u << (int)(nunits - u0)) - 1u; // units past the end of the chunk
     uint32_t base = 0;
     if (lane == 0 && m) base = (uint32_t)atomicAdd(cursor, (unsigned long long)__popc(m));
     base = __shfl_sync(kAllLanes, base, 0);
@@ -67,20 +88,19 @@ pack_results_kernel(const uint4 *__restrict__ in, const int64_t nunits, unsigned
       mask[w] = m;
       word_base[w] = base;
     }
-    desc[u0 + lane] = my_desc; // the desc array is padded to whole words
-    if (host_dst) {
-      for (uint32_t rest = m; rest; rest &= rest - 1) {
-        const int u = __ffs(rest) - 1;
-        const uint4 v = __ldg(src + (size_t)u * 32);
-        if (tail_partial && u0 + u == nunits - 1) tail[lane] = v;
-        else host_dst[(u0 + u) * 32 + lane] = v;
-      }
-    } else {
-      uint4 *dst = lit + (size_t)base * 32 + lane;
-      for (uint32_t rest = m; rest; rest &= rest - 1) {
-        const int u = __ffs(rest) - 1;
-        *dst = __ldg(src + (size_t)u * 32);
-        dst += 32;
+    if (ELEM == 4) reinterpret_cast<uint32_t *>(desc)[u0 + lane] = d0; // padded to whole words
+    else reinterpret_cast<uint2 *>(desc)[u0 + lane] = make_uint2(d0, d1);
+#pragma unroll
+    for (int k = 0; k < kLoadsPerWord; ++k) {
+      const int u = k * kUnitsPerLoad + grp; // this lane's unit of load k
+      if ((m >> u) & 1u) {
+        if (host_dst) {
+          if (tail_partial && u0 + u == nunits - 1) tail[lane - lead] = v[k];
+          else host_dst[q0 + 32 * k] = v[k];
+        } else {
+          const uint32_t rank = __popc(m & ((1u << u) - 1u));
+          lit[(size_t)(base + rank) * kLanesPerUnit + (lane - lead)] = v[k];
+        }
       }
     }
   }
@@ -96,7 +116,7 @@ cudaError_t vhp_launch_pack_results(const void *d_in, int64_t nunits, int elem_b
   if (e != cudaSuccess) return e;
   const int64_t nwords = (nunits + 31) / 32;
   const int64_t want = (nwords + 7) / 8; // 8 warps per CTA
-  const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sm_count * 8);
+  const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sm_count * 16);
   if (elem_bytes == 4)
     pack_results_kernel<4><<<grid, 256, 0, st>>>(reinterpret_cast<const uint4 *>(d_in), nunits,
                                                  reinterpret_cast<unsigned char *>(d_meta),

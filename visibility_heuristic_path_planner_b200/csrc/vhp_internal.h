@@ -26,29 +26,30 @@ struct VhpDevBuf {
 };
 
 // ---- packed result transport (result_transport.cu, host_expand.cpp) -------------
-// A chunk of results (flat bytes) is cut into 512-byte units; 32 consecutive units make a
+// A chunk of results (flat bytes) is cut into 128-byte units; 32 consecutive units make a
 // mask word.  Unit u of word w is literal iff bit u of mask[w]; the literal units of a word
 // are stored back to back from unit slot word_base[w] of the literal stream; every unit has
-// its first 8 bytes in desc[] (the fill pattern of a uniform unit).
-constexpr int kVhpPackUnit = 512;
+// its first element in desc[] (the fill value of a uniform unit).
+constexpr int kVhpPackUnit = 128;
 constexpr int kVhpPackMetaHead = 16 + kVhpPackUnit; // cursor (padded) + the tail unit
 struct VhpPackedChunk {
   const uint32_t *mask = nullptr;
   const uint32_t *word_base = nullptr;
-  const uint64_t *desc = nullptr;
+  const void *desc = nullptr;     // elem_bytes per unit
+  int elem_bytes = 4;             // 4 or 8
   const char *literals = nullptr; // null: direct mode, the device stored the literal units in dst
   const char *tail = nullptr;     // direct mode: a partial, literal last unit
-  char *dst = nullptr;      // where the expanded chunk goes (caller's buffer)
+  char *dst = nullptr;            // where the expanded chunk goes (caller's buffer)
   int64_t nunits = 0;
-  size_t valid_bytes = 0;   // bytes of the chunk (the last unit may be partial)
+  size_t valid_bytes = 0;         // bytes of the chunk (the last unit may be partial)
 };
 // device-side meta block of one packed chunk: [cursor u64, pad to 16][tail unit][mask][word_base][desc]
-inline size_t vhp_pack_meta_bytes(int64_t nunits) {
+inline size_t vhp_pack_meta_bytes(int64_t nunits, int elem_bytes) {
   const int64_t nwords = (nunits + 31) / 32;
-  return kVhpPackMetaHead + (size_t)nwords * 8 + (size_t)nwords * 32 * 8;
+  return kVhpPackMetaHead + (size_t)nwords * 8 + (size_t)nwords * 32 * elem_bytes;
 }
-// in: nunits * 512 readable bytes.  Writes the meta block and either the literal stream
-// (host_dst null) or the literal units themselves to host_dst + 512 * unit (a device-accessible
+// in: nunits * 128 readable bytes.  Writes the meta block and either the literal stream
+// (host_dst null) or the literal units themselves to host_dst + 128 * unit (a device-accessible
 // host address, 16-byte aligned; tail_partial: the last unit is partial and goes to the meta block).
 cudaError_t vhp_launch_pack_results(const void *d_in, int64_t nunits, int elem_bytes, void *d_meta,
                                     void *d_literals, void *host_dst, int tail_partial,
@@ -108,8 +109,8 @@ struct vhp_context {
   void *h_pack_meta[kPackSets] = {nullptr, nullptr, nullptr};
   void *h_pack_lit[kPackSets] = {nullptr, nullptr, nullptr};
   size_t h_pack_meta_cap = 0, h_pack_lit_cap = 0;
-  cudaEvent_t ev_pack_meta[kPackSets] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev_pack_lit[kPackSets] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_pack_meta[kPackSets] = {nullptr, nullptr, nullptr}; // packed + meta copied
+  cudaEvent_t ev_pack_lit[kPackSets] = {nullptr, nullptr, nullptr};  // results of the set computed
   VhpExpandPool *expand_pool = nullptr;
   // statistics of the last host-buffer call (vhp_context_last_transport)
   int64_t last_d2h_bytes = 0, last_result_bytes = 0;
