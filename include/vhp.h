@@ -135,6 +135,12 @@ vhp_status vhp_prepare_maps_dev(vhp_context *ctx, const uint8_t *d_occ, int nmap
  * bytes of results delivered, transport used (0 plain, 1 packed with a staged literal stream,
  * 2 packed with literal units stored straight into the pinned caller buffer). */
 vhp_status vhp_context_set_result_transport(vhp_context *ctx, int mode);
+/* Packed transport into pinned memory: besides the literal units the GPU can deliver
+ * `sixteenths`/16 of the result completely (uniform units included) while the host threads
+ * write the rest.  Default 0 (measured fastest where the host has 16 threads: bytes arriving
+ * over PCIe compete with the host threads for the same memory system); a host with few
+ * threads per GPU may prefer a larger share.  env VHP_RESULT_GPU_SHARE. */
+vhp_status vhp_context_set_result_gpu_share(vhp_context *ctx, int sixteenths);
 vhp_status vhp_context_last_transport(const vhp_context *ctx, int64_t *d2h_bytes,
                                       int64_t *result_bytes, int32_t *packed);
 /* The host half of the packed transport on its own (no GPU needed; tests): expand one packed

@@ -105,9 +105,10 @@ def test_automatic_mode_falls_back_when_results_do_not_compress(ctx, vhp):
     ctx.set_result_transport(1)
 
 
+@pytest.mark.parametrize("gpu_share", [0, 5, 16])
 @pytest.mark.parametrize("dtype_name", ["F32", "F64"])
 @pytest.mark.parametrize("shape,npairs", [((100, 101), 3), ((300, 217), 9), ((1000, 1000), 150)])
-def test_direct_mode_into_pinned_memory(ctx, vhp, shape, npairs, dtype_name):
+def test_direct_mode_into_pinned_memory(ctx, vhp, shape, npairs, dtype_name, gpu_share):
     """a pinned caller buffer: the device stores the literal units straight into it, the host
     threads write the uniform ones (a partial last unit comes through the meta block)"""
     import torch
@@ -122,12 +123,16 @@ def test_direct_mode_into_pinned_memory(ctx, vhp, shape, npairs, dtype_name):
     tdt = torch.float32 if dtype == vhp.F32 else torch.float64
     pinned = torch.full((npairs, ny, nx), float("nan"), dtype=tdt).pin_memory()
     ctx.set_result_transport(2)
+    ctx.set_result_gpu_share(gpu_share)
     got = ctx.visibility_batch(occ, srcs, dtype=dtype, out=pinned.numpy())
     d2h, res, mode = ctx.last_transport()
     assert mode == 2 and res == plain.nbytes
+    if gpu_share == 16:
+        assert d2h >= 0.9 * res  # (nearly) everything came from the device
     assert got.tobytes() == plain.tobytes()
     # a second call must rewrite every byte as well
     pinned.fill_(float("nan"))
     ctx.visibility_batch(occ, srcs, dtype=dtype, out=pinned.numpy())
     assert pinned.numpy().tobytes() == plain.tobytes()
     ctx.set_result_transport(1)
+    ctx.set_result_gpu_share(0)

@@ -98,6 +98,7 @@ def load_library(build_if_missing: bool = True):
     lib.vhp_strip_halo_rows.restype = None
     lib.vhp_context_set_grid_sweep.argtypes = [vp, i32]
     lib.vhp_context_set_result_transport.argtypes = [vp, i32]
+    lib.vhp_context_set_result_gpu_share.argtypes = [vp, i32]
     lib.vhp_expand_packed_chunk.argtypes = [vp, vp, vp, i32, vp, i64, i64, vp, i32]
     lib.vhp_context_last_transport.argtypes = [vp, C.POINTER(i64), C.POINTER(i64),
                                                C.POINTER(C.c_int32)]
@@ -163,6 +164,11 @@ class Context:
         """Transport of host-buffer results: 0 plain copies, 1 automatic (default), 2 always
         packed (uniform / literal 128-byte units, expanded by host threads)."""
         self._check(self.lib.vhp_context_set_result_transport(self.h, int(mode)))
+
+    def set_result_gpu_share(self, sixteenths: int):
+        """Packed transport into pinned memory: share of the result (in sixteenths) the GPU
+        delivers completely (uniform units included); default 0."""
+        self._check(self.lib.vhp_context_set_result_gpu_share(self.h, int(sixteenths)))
 
     def last_transport(self):
         """(bytes moved device-to-host, bytes of results delivered, transport) of the last

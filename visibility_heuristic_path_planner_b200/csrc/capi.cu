@@ -322,6 +322,13 @@ vhp_status run_host_packed(vhp_context *ctx, Op op, int nmaps, int nx, int ny, c
   bool bail = false;
   vhp_status result = VHP_OK;
 
+  // Direct mode: the device can also deliver a share of the mask words completely (uniform
+  // units included).  Off by default: on the B200 boxes every byte that arrives over PCIe
+  // while 16 host threads stream into the same memory costs about as much time as 3.5 bytes
+  // written by the host threads (share 0 / 2 / 4 / 6 sixteenths: 96 / 125 / 155 / 184 ms for
+  // 16.4 GB), so the fastest split moves as few bytes over PCIe as possible.
+  int share_of[NS] = {0, 0, 0};
+  auto gpu_share_now = [&]() -> int { return std::max(0, std::min(ctx->result_gpu_share, 16)); };
   auto chunk_units = [&](int64_t it) {
     const int64_t np = std::min(chunk, n - it * chunk);
     return (int64_t)(((size_t)np * pair_bytes + kVhpPackUnit - 1) / kVhpPackUnit);
@@ -338,11 +345,12 @@ vhp_status run_host_packed(vhp_context *ctx, Op op, int nmaps, int nx, int ny, c
     VHP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pack_lit[s], 0));
     const int64_t nu = chunk_units(it);
     const int tail_partial = ((size_t)np * pair_bytes) % kVhpPackUnit != 0;
+    share_of[s] = direct ? gpu_share_now() : 0;
     VHP_CUDA(ctx, vhp_launch_pack_results(ctx->b_pack_out[s].p, nu, (int)esz, ctx->b_pack_meta[s].p,
                                           ctx->b_pack_lit[s].p,
                                           direct ? out_dev + (size_t)p0 * pair_bytes : nullptr,
-                                          tail_partial, ctx->sm_count, ctx->copy_stream,
-                                          &ctx->launches));
+                                          tail_partial, share_of[s], ctx->sm_count,
+                                          ctx->copy_stream, &ctx->launches));
     VHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_pack_meta[s], ctx->b_pack_meta[s].p, vhp_pack_meta_bytes(nu, (int)esz),
                                   cudaMemcpyDeviceToHost, ctx->copy_stream));
     VHP_CUDA(ctx, cudaEventRecord(ctx->ev_pack_meta[s], ctx->copy_stream));
@@ -361,9 +369,14 @@ vhp_status run_host_packed(vhp_context *ctx, Op op, int nmaps, int nx, int ny, c
                                     ctx->copy_stream));
       VHP_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     }
-    ctx->last_d2h_bytes += (int64_t)(vhp_pack_meta_bytes(nu, (int)esz) + (size_t)nlit * kVhpPackUnit);
+    // words the device delivered completely (their literal units are not in the cursor)
+    const int64_t gpu_words = share_of[s] ? ((nwords - 1) / 16) * share_of[s] +
+                                                std::min<int64_t>((nwords - 1) % 16, share_of[s])
+                                          : 0;
+    ctx->last_d2h_bytes += (int64_t)(vhp_pack_meta_bytes(nu, (int)esz) + (size_t)nlit * kVhpPackUnit +
+                                     (size_t)gpu_words * 32 * kVhpPackUnit);
     lit_units_total += (int64_t)nlit;
-    units_total += nu;
+    units_total += nu - gpu_words * 32; // the literal fraction is measured on the host's words
     VhpPackedChunk c;
     c.mask = (const uint32_t *)(meta + kVhpPackMetaHead);
     c.word_base = c.mask + nwords;
@@ -371,6 +384,7 @@ vhp_status run_host_packed(vhp_context *ctx, Op op, int nmaps, int nx, int ny, c
     c.elem_bytes = (int)esz;
     c.literals = direct ? nullptr : (const char *)ctx->h_pack_lit[s];
     c.tail = meta + 16;
+    c.gpu_share = share_of[s];
     c.dst = (char *)out + (size_t)p0 * pair_bytes;
     c.nunits = nu;
     c.valid_bytes = (size_t)np * pair_bytes;
@@ -663,6 +677,7 @@ vhp_status vhp_context_create(int device, void *cuda_stream, vhp_context **out) 
     else if (std::strcmp(e, "packed") == 0) ctx->result_transport = 2;
   }
   if (const char *e = std::getenv("VHP_RESULT_DIRECT")) ctx->result_direct = std::atoi(e) != 0;
+  if (const char *e = std::getenv("VHP_RESULT_GPU_SHARE")) ctx->result_gpu_share = std::atoi(e);
   *out = ctx;
   return VHP_OK;
 }
@@ -793,6 +808,13 @@ vhp_status vhp_context_set_result_transport(vhp_context *ctx, int mode) {
   if (!ctx || mode < 0 || mode > 2)
     return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_context_set_result_transport: mode is 0, 1 or 2");
   ctx->result_transport = mode;
+  return VHP_OK;
+}
+
+vhp_status vhp_context_set_result_gpu_share(vhp_context *ctx, int sixteenths) {
+  if (!ctx || sixteenths < 0 || sixteenths > 16)
+    return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_context_set_result_gpu_share: 0..16");
+  ctx->result_gpu_share = sixteenths;
   return VHP_OK;
 }
 

@@ -48,7 +48,9 @@ inline void copy_unit(char *dst, const char *src, size_t bytes) {
 }
 
 void expand_words(const VhpPackedChunk &c, int64_t w0, int64_t w1) {
+  const int64_t last_word = (c.nunits + 31) / 32 - 1;
   for (int64_t w = w0; w < w1; ++w) {
+    if (!c.literals && (int)(w & 15) < c.gpu_share && w != last_word) continue; // the device's word
     const uint32_t m = c.mask[w];
     const char *lit = c.literals ? c.literals + (size_t)c.word_base[w] * kVhpPackUnit : nullptr;
     const int64_t u0 = w * 32;

@@ -17,7 +17,10 @@
 // are not compacted but stored by this kernel straight to their final place in host memory, so
 // the host threads only write the uniform units and no byte of the result is written to host
 // memory twice.  A partial last unit of the chunk cannot be stored whole: it goes to the meta
-// block and the host copies its valid bytes.
+// block and the host copies its valid bytes.  To balance PCIe against the host threads the
+// device can also take whole mask words: in direct mode the words w with w % 16 < gpu_share
+// (except the last word of the chunk) are stored completely by this kernel, uniform units
+// included, and skipped by the host.
 #include <cstdint>
 
 #include "vhp_internal.h"
@@ -34,7 +37,8 @@ constexpr int kLoadsPerWord = 32 / kUnitsPerLoad; // 8
 template <int ELEM> // element size in bytes: 4 or 8
 __global__ void __launch_bounds__(256)
 pack_results_kernel(const uint4 *__restrict__ in, const int64_t nunits, unsigned char *__restrict__ meta,
-                    uint4 *__restrict__ lit, uint4 *__restrict__ host_dst, const int tail_partial) {
+                    uint4 *__restrict__ lit, uint4 *__restrict__ host_dst, const int tail_partial,
+                    const int gpu_share) {
   const int64_t nwords = (nunits + 31) / 32;
   unsigned long long *cursor = reinterpret_cast<unsigned long long *>(meta);
   uint4 *tail = reinterpret_cast<uint4 *>(meta + 16);
@@ -81,6 +85,16 @@ pack_results_kernel(const uint4 *__restrict__ in, const int64_t nunits, unsigned
         m |= ((b >> (g * kLanesPerUnit)) & 1u) << (k * kUnitsPerLoad + g);
     }
     if (u0 + 32 > nunits) m &= (1u << (int)(nunits - u0)) - 1u; // units past the end of the chunk
+    if (host_dst && (int)(w & 15) < gpu_share && w != nwords - 1) {
+      // a word the device delivers completely (mask 0: nothing left for the host to copy)
+#pragma unroll
+      for (int k = 0; k < kLoadsPerWord; ++k) host_dst[q0 + 32 * k] = v[k];
+      if (lane == 0) {
+        mask[w] = 0u;
+        word_base[w] = 0u;
+      }
+      continue;
+    }
     uint32_t base = 0;
     if (lane == 0 && m) base = (uint32_t)atomicAdd(cursor, (unsigned long long)__popc(m));
     base = __shfl_sync(kAllLanes, base, 0);
@@ -110,7 +124,8 @@ pack_results_kernel(const uint4 *__restrict__ in, const int64_t nunits, unsigned
 
 cudaError_t vhp_launch_pack_results(const void *d_in, int64_t nunits, int elem_bytes, void *d_meta,
                                     void *d_literals, void *host_dst, int tail_partial,
-                                    int sm_count, cudaStream_t st, int64_t *launches) {
+                                    int gpu_share, int sm_count, cudaStream_t st,
+                                    int64_t *launches) {
   if (nunits <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(d_meta, 0, 16, st);
   if (e != cudaSuccess) return e;
@@ -121,12 +136,14 @@ cudaError_t vhp_launch_pack_results(const void *d_in, int64_t nunits, int elem_b
     pack_results_kernel<4><<<grid, 256, 0, st>>>(reinterpret_cast<const uint4 *>(d_in), nunits,
                                                  reinterpret_cast<unsigned char *>(d_meta),
                                                  reinterpret_cast<uint4 *>(d_literals),
-                                                 reinterpret_cast<uint4 *>(host_dst), tail_partial);
+                                                 reinterpret_cast<uint4 *>(host_dst), tail_partial,
+                                                 gpu_share);
   else
     pack_results_kernel<8><<<grid, 256, 0, st>>>(reinterpret_cast<const uint4 *>(d_in), nunits,
                                                  reinterpret_cast<unsigned char *>(d_meta),
                                                  reinterpret_cast<uint4 *>(d_literals),
-                                                 reinterpret_cast<uint4 *>(host_dst), tail_partial);
+                                                 reinterpret_cast<uint4 *>(host_dst), tail_partial,
+                                                 gpu_share);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }

@@ -39,6 +39,8 @@ struct VhpPackedChunk {
   int elem_bytes = 4;             // 4 or 8
   const char *literals = nullptr; // null: direct mode, the device stored the literal units in dst
   const char *tail = nullptr;     // direct mode: a partial, literal last unit
+  int gpu_share = 0;              // direct mode: words w with w % 16 < gpu_share (not the last
+                                  // one) were delivered completely by the device
   char *dst = nullptr;            // where the expanded chunk goes (caller's buffer)
   int64_t nunits = 0;
   size_t valid_bytes = 0;         // bytes of the chunk (the last unit may be partial)
@@ -53,7 +55,8 @@ inline size_t vhp_pack_meta_bytes(int64_t nunits, int elem_bytes) {
 // host address, 16-byte aligned; tail_partial: the last unit is partial and goes to the meta block).
 cudaError_t vhp_launch_pack_results(const void *d_in, int64_t nunits, int elem_bytes, void *d_meta,
                                     void *d_literals, void *host_dst, int tail_partial,
-                                    int sm_count, cudaStream_t st, int64_t *launches);
+                                    int gpu_share, int sm_count, cudaStream_t st,
+                                    int64_t *launches);
 
 // host threads that expand packed chunks into the caller's buffer (FIFO, each job is spread
 // over all threads)
@@ -104,6 +107,9 @@ struct vhp_context {
   // packed transport into a pinned, mapped caller buffer: the device stores the literal units
   // straight into it (env VHP_RESULT_DIRECT=0 keeps the staged literal stream)
   bool result_direct = true;
+  // direct mode: sixteenths of the mask words the device delivers completely (default 0: only
+  // the literal units come over PCIe; env VHP_RESULT_GPU_SHARE)
+  int result_gpu_share = 0;
   static constexpr int kPackSets = 3;
   VhpDevBuf b_pack_out[kPackSets], b_pack_meta[kPackSets], b_pack_lit[kPackSets];
   void *h_pack_meta[kPackSets] = {nullptr, nullptr, nullptr};
