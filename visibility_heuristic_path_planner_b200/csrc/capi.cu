@@ -1,6 +1,7 @@
 // capi.cu -- extern "C" entry points of include/vhp.h: context management and the
 // batched sweep / ray-casting / planner calls.  Plain pointers in, status out.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -327,6 +328,9 @@ vhp_status run_host_packed(vhp_context *ctx, Op op, int nmaps, int nx, int ny, c
   // while 16 host threads stream into the same memory costs about as much time as 3.5 bytes
   // written by the host threads (share 0 / 2 / 4 / 6 sixteenths: 96 / 125 / 155 / 184 ms for
   // 16.4 GB), so the fastest split moves as few bytes over PCIe as possible.
+  double trace_pack_ms = 0.0, trace_wait_s = 0.0, trace_ticket_s = 0.0;
+  const double trace_busy0 = pool.busy_seconds();
+  const auto trace_t0 = std::chrono::steady_clock::now();
   int share_of[NS] = {0, 0, 0};
   auto gpu_share_now = [&]() -> int { return std::max(0, std::min(ctx->result_gpu_share, 16)); };
   auto chunk_units = [&](int64_t it) {
@@ -343,6 +347,7 @@ vhp_status run_host_packed(vhp_context *ctx, Op op, int nmaps, int nx, int ny, c
     // next chunk overlap it
     VHP_CUDA(ctx, cudaEventRecord(ctx->ev_pack_lit[s], ctx->stream));
     VHP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pack_lit[s], 0));
+    VHP_CUDA(ctx, cudaEventRecord(ctx->ev_pack_t0[s], ctx->copy_stream));
     const int64_t nu = chunk_units(it);
     const int tail_partial = ((size_t)np * pair_bytes) % kVhpPackUnit != 0;
     share_of[s] = direct ? gpu_share_now() : 0;
@@ -360,7 +365,14 @@ vhp_status run_host_packed(vhp_context *ctx, Op op, int nmaps, int nx, int ny, c
     const int s = (int)(it % NS);
     const int64_t p0 = it * chunk, np = std::min(chunk, n - p0);
     const int64_t nu = chunk_units(it), nwords = (nu + 31) / 32;
+    const auto tw0 = std::chrono::steady_clock::now();
     VHP_CUDA(ctx, cudaEventSynchronize(ctx->ev_pack_meta[s]));
+    trace_wait_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - tw0).count();
+    if (ctx->transport_trace) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ctx->ev_pack_t0[s], ctx->ev_pack_meta[s]) == cudaSuccess)
+        trace_pack_ms += ms;
+    }
     const char *meta = (const char *)ctx->h_pack_meta[s];
     const uint64_t nlit = *(const uint64_t *)meta;
     if (nlit && !direct) {
@@ -395,7 +407,11 @@ vhp_status run_host_packed(vhp_context *ctx, Op op, int nmaps, int nx, int ny, c
   int64_t launched = 0, finished = 0;
   for (int64_t it = 0; it < nchunks && result == VHP_OK && !bail; ++it) {
     const int s = (int)(it % NS);
-    if (tickets[s]) pool.wait(tickets[s]); // staging set s is free again
+    if (tickets[s]) { // staging set s is free again
+      const auto tt0 = std::chrono::steady_clock::now();
+      pool.wait(tickets[s]);
+      trace_ticket_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - tt0).count();
+    }
     if ((result = launch(it)) != VHP_OK) break;
     ++launched;
     if (it >= 1) {
@@ -417,6 +433,16 @@ vhp_status run_host_packed(vhp_context *ctx, Op op, int nmaps, int nx, int ny, c
   if (result != VHP_OK) return result;
   if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "sync stream");
   *resume_from = std::min(n, launched * chunk);
+  if (ctx->transport_trace)
+    std::fprintf(stderr,
+                 "[vhp transport] %s, %lld chunks: wall %.1f ms | packing on the GPU %.1f ms | host "
+                 "expansion %.1f ms (%d threads) | main thread waited %.1f ms for the GPU, %.1f ms "
+                 "for the host threads | %.2f of %.2f GB over PCIe\n",
+                 direct ? "direct" : "staged", (long long)launched,
+                 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - trace_t0).count(),
+                 trace_pack_ms, 1e3 * (pool.busy_seconds() - trace_busy0), pool.threads(),
+                 1e3 * trace_wait_s, 1e3 * trace_ticket_s, ctx->last_d2h_bytes / 1e9,
+                 (double)(launched * chunk * pair_bytes) / 1e9);
   return VHP_OK;
 }
 
@@ -669,7 +695,8 @@ vhp_status vhp_context_create(int device, void *cuda_stream, vhp_context **out) 
   if (impl && std::strcmp(impl, "naive") == 0) ctx->sweep_impl = 1;
   if (const char *e = std::getenv("VHP_GRID_SWEEP")) ctx->grid_sweep = std::atoi(e);
   for (int i = 0; i < vhp_context::kPackSets; ++i) {
-    VHP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_pack_meta[i], cudaEventDisableTiming));
+    VHP_CUDA(nullptr, cudaEventCreate(&ctx->ev_pack_meta[i]));
+    VHP_CUDA(nullptr, cudaEventCreate(&ctx->ev_pack_t0[i]));
     VHP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_pack_lit[i], cudaEventDisableTiming));
   }
   if (const char *e = std::getenv("VHP_RESULT_TRANSPORT")) {
@@ -678,6 +705,7 @@ vhp_status vhp_context_create(int device, void *cuda_stream, vhp_context **out) 
   }
   if (const char *e = std::getenv("VHP_RESULT_DIRECT")) ctx->result_direct = std::atoi(e) != 0;
   if (const char *e = std::getenv("VHP_RESULT_GPU_SHARE")) ctx->result_gpu_share = std::atoi(e);
+  ctx->transport_trace = std::getenv("VHP_TRANSPORT_TRACE") != nullptr;
   *out = ctx;
   return VHP_OK;
 }
@@ -699,6 +727,7 @@ void vhp_context_destroy(vhp_context *ctx) {
     if (ctx->h_pack_meta[i]) cudaFreeHost(ctx->h_pack_meta[i]);
     if (ctx->h_pack_lit[i]) cudaFreeHost(ctx->h_pack_lit[i]);
     if (ctx->ev_pack_meta[i]) cudaEventDestroy(ctx->ev_pack_meta[i]);
+    if (ctx->ev_pack_t0[i]) cudaEventDestroy(ctx->ev_pack_t0[i]);
     if (ctx->ev_pack_lit[i]) cudaEventDestroy(ctx->ev_pack_lit[i]);
   }
   if (ctx->tile_buf) cudaFree(ctx->tile_buf);

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -90,7 +91,10 @@ struct VhpExpandPool::Impl {
     std::atomic<int> active{0}; // threads inside this job
     bool done = false;
     int64_t id = 0;
+    std::chrono::steady_clock::time_point t_start;
+    bool started = false;
   };
+  double busy_seconds = 0.0; // sum over jobs of (last thread out - first thread in)
   std::vector<std::thread> threads;
   std::mutex mu;
   std::condition_variable cv_work, cv_done;
@@ -108,6 +112,10 @@ struct VhpExpandPool::Impl {
         if (stop && queue.empty()) return;
         job = queue.front();
         job->active.fetch_add(1);
+        if (!job->started) {
+          job->started = true;
+          job->t_start = std::chrono::steady_clock::now();
+        }
       }
       for (;;) {
         const int64_t w0 = job->next.fetch_add(kSliceWords);
@@ -119,6 +127,7 @@ struct VhpExpandPool::Impl {
         if (!queue.empty() && queue.front() == job) queue.pop_front(); // no slices left
         if (job->active.fetch_sub(1) == 1 && job->next.load() >= job->nwords && !job->done) {
           job->done = true;
+          busy_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - job->t_start).count();
           // retire finished jobs in order
           while (!in_flight.empty() && in_flight.front()->done) {
             delete in_flight.front();
@@ -149,6 +158,11 @@ VhpExpandPool::~VhpExpandPool() {
 }
 
 int VhpExpandPool::threads() const { return (int)impl_->threads.size(); }
+
+double VhpExpandPool::busy_seconds() const {
+  std::unique_lock<std::mutex> lk(impl_->mu);
+  return impl_->busy_seconds;
+}
 
 int64_t VhpExpandPool::submit(const VhpPackedChunk &chunk) {
   Impl::Job *job = new Impl::Job();

@@ -65,6 +65,7 @@ class VhpExpandPool {
   explicit VhpExpandPool(int nthreads);
   ~VhpExpandPool();
   int threads() const;
+  double busy_seconds() const;                 // time spent expanding so far (jobs are serial)
   int64_t submit(const VhpPackedChunk &chunk); // returns a ticket
   void wait(int64_t ticket);                   // returns when that job and all earlier ones are done
  private:
@@ -117,6 +118,8 @@ struct vhp_context {
   size_t h_pack_meta_cap = 0, h_pack_lit_cap = 0;
   cudaEvent_t ev_pack_meta[kPackSets] = {nullptr, nullptr, nullptr}; // packed + meta copied
   cudaEvent_t ev_pack_lit[kPackSets] = {nullptr, nullptr, nullptr};  // results of the set computed
+  cudaEvent_t ev_pack_t0[kPackSets] = {nullptr, nullptr, nullptr};   // timing: packing starts
+  bool transport_trace = false; // env VHP_TRANSPORT_TRACE: per-call timing summary on stderr
   VhpExpandPool *expand_pool = nullptr;
   // statistics of the last host-buffer call (vhp_context_last_transport)
   int64_t last_d2h_bytes = 0, last_result_bytes = 0;
