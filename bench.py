@@ -363,6 +363,7 @@ def main():
     numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     maps, src, smap, desc = workload(args.workload, rank, world)
