@@ -95,6 +95,10 @@
 #ifndef VHP_FIXED32
 #define VHP_FIXED32 1
 #endif
+// Runs of dark tiles of a tile row written in one go (see run_row).
+#ifndef VHP_DARK_TAIL
+#define VHP_DARK_TAIL 1
+#endif
 
 namespace {
 
@@ -711,8 +715,56 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
     const uint32_t *colpl = (g.diry > 0 ? p.pl.colF : p.pl.colR) + (size_t)map * p.pl.col_plane;
     double Lv = 1.0, cor = 1.0; // left of the first tile: lit tiles or the virtual boundary
     TilePre pre = tile_prefetch(p, g, rowpl, colpl, bsum, sx, sy, I0, J, lane);
+#if VHP_DARK_TAIL
+    // rows of this tile row that hold cells to compute (lane <-> row j0 + lane), as in process_tile
+    const int j0row = tile_start(g.a, J);
+    const int nvyrow = min(J ? kTile : g.a, g.Ey - (g.diry < 0) - j0row + 1);
+    const bool rowc_row = lane < nvyrow;
+    int dark_seen = -1; // a boundary column >= the tile start known to be non-zero (finished row below)
+#endif
 #pragma unroll 1
     for (int I = I0; I < g.TX; ++I) {
+#if VHP_DARK_TAIL
+      // Dark run: the left inputs are zero and the top row of the row below is zero over the
+      // next n finished tiles -> every cell of those n tiles is 0 (zero inputs give zero whatever
+      // the occupancy; the boundary row stays zero and is not rewritten).  Hand them to the row
+      // above at once and write the zeros as row spans, without per-tile set-up.  (Multi-warp
+      // CTAs only: the single-warp kernels are bound by their code size.)
+      if (NW > 1 && !GE && J > 0 && I > I0 && cor == 0.0 && tile_start(g.a, I) > dark_seen &&
+          __all_sync(kAll, !rowc_row || Lv == 0.0)) {
+        const int Iend = min(ld_acquire_shared(prog + q * lmcap + J - 1), g.TX); // finished below
+        if (Iend > I) {
+          const int i0 = tile_start(g.a, I);
+          const int ilim = min(g.Ex - (g.dirx < 0), tile_start(g.a, Iend) - 1);
+          const double *rowB = edges + g.rowOff;
+          int bad = -1;
+          for (int ib = i0; ib <= ilim && bad < 0; ib += 32) {
+            const unsigned nz = __ballot_sync(kAll, ib + lane <= ilim && rowB[ib + lane] != 0.0);
+            if (nz) bad = ib + __ffs(nz) - 1;
+          }
+          int Istop = Iend; // first tile not known to be dark
+          if (bad >= 0) {
+            Istop = tile_row_of(g.a, bad);
+            dark_seen = bad;
+          }
+          if (Istop > I) {
+            __syncwarp();
+            if (lane == 0) st_release_shared(prog + q * lmcap + J, Istop);
+            const int r0 = max(0, g.jw0 - j0row);
+            const int rlast = min(min((J ? kTile : g.a) - 1, g.Ey - j0row), g.jw1 - j0row);
+            const int ie = min(g.Ex, tile_start(g.a, Istop) - 1); // last local column of the run
+            const int xa = g.dirx > 0 ? sx + i0 : sx - ie, xb = g.dirx > 0 ? sx + ie : sx - i0;
+            for (int r = r0; r <= rlast; ++r)
+              fill_span<OutT>(out + (size_t)(sy + g.diry * (j0row + r)) * nx, xa, xb, (OutT)0, lane,
+                              p.vec != 0);
+            if (Istop >= g.TX) return;
+            pre = tile_prefetch(p, g, rowpl, colpl, bsum, sx, sy, Istop, J, lane);
+            I = Istop - 1;
+            continue;
+          }
+        }
+      }
+#endif
       const TilePre cur = pre;
       if (I + 1 < g.TX) pre = tile_prefetch(p, g, rowpl, colpl, bsum, sx, sy, I + 1, J, lane);
       if (NW > 1 && J > 0) { // tile (I, J-1) must be finished
