@@ -359,11 +359,14 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    # stdout carries the JSON line only: whatever libraries print (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     maps, src, smap, desc = workload(args.workload, rank, world)
@@ -437,6 +440,24 @@ def main():
         if world > 1 and "VHP_HOST_THREADS" not in os.environ:
             os.environ["VHP_HOST_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
         host_ctx = vhp.Context(local_rank)
+        # every rank pins a host buffer for its whole result (16.4 GB): with many ranks on one box
+        # keep the sum within the host's free memory (all ranks then use the same, smaller, number
+        # of pairs for this leg; stated in the JSON line)
+        n_e2e = n
+        try:
+            avail = next(int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable"))
+            n_e2e = max(64, min(n, int(0.55 * avail / world) // (nx * ny * esz)))
+        except Exception:
+            pass
+        if world > 1:
+            tn = torch.tensor([n_e2e], device=dev, dtype=torch.int64)
+            dist.all_reduce(tn, op=dist.ReduceOp.MIN)
+            n_e2e = int(tn.item())
+        n_full, n = n, n_e2e  # the e2e leg's batch
+        src_full, smap_full = src, smap
+        src = np.ascontiguousarray(src[:n])
+        smap = None if smap is None else np.ascontiguousarray(smap[:n])
+        cells_e2e = n * nx * ny
         out_h = torch.empty((n, ny, nx), dtype=tdt, pin_memory=True)  # (no pageable staging copy)
         out_np = out_h.numpy()
         lib, C = host_ctx.lib, __import__("ctypes")
@@ -473,7 +494,8 @@ def main():
 
         t_e2e, k_e2e, d2h_b, packed = e2e_run(1)   # the default (automatic) transport
         t_plain, _, d2h_plain, _ = e2e_run(0)      # plain copies, for comparison
-        e2e = {"value": cells * world / t_e2e / 1e9, "unit": "Gcells/s",
+        e2e = {"value": cells_e2e * world / t_e2e / 1e9, "unit": "Gcells/s",
+               "pairs_per_gpu": int(n),
                "h2d_bytes_per_step": int(maps.nbytes + src.nbytes + (0 if smap is None else smap.nbytes)),
                "d2h_bytes_per_step": int(d2h_b),
                "result_bytes_per_step": int(n) * nx * ny * esz,
@@ -486,10 +508,11 @@ def main():
                                 else "the literal units are copied as one stream",
                                 os.environ.get("VHP_HOST_THREADS", str(min(32, os.cpu_count() or 1)))))
                             if packed else "plain",
-               "plain_transport": {"value": cells * world / t_plain / 1e9, "ms_per_step": t_plain * 1e3,
+               "plain_transport": {"value": cells_e2e * world / t_plain / 1e9, "ms_per_step": t_plain * 1e3,
                                    "d2h_bytes_per_step": int(d2h_plain)},
                "api": "vhp_visibility_batch (host buffers; pinned output; H2D + kernel + D2H (+ host expansion) "
                       "inside the timed region; %d result pairs compared with the device-resident run)" % len(probe)}
+        n, src, smap = n_full, src_full, smap_full
 
     # ---- the same grid and batch size with obstacles (kernel-only, rank-local): how the
     # headline kernel does once the sweep is more than a fill -- reported beside the headline
@@ -516,7 +539,7 @@ def main():
             penumbra[wl] = {"workload": d2, "ms_per_step": ms, "value": n2 * nx2 * ny2 / ms / 1e6,
                             "unit": "Gcells/s", "achieved_gbs": byts / ms / 1e6,
                             "frac_of_hbm_peak": byts / ms / 1e6 / measured_peak()[0], "steps": 10}
-            if wl == "c2s" and e2e is not None and o2.shape == out_t.shape:
+            if wl == "c2s" and e2e is not None and tuple(o2.shape) == tuple(out_np.shape):
                 # the same host-buffer call on the obstacle workload (automatic transport)
                 def c2s_step():
                     st = lib.vhp_visibility_batch(host_ctx.h, m2.ctypes.data, m2.shape[0], nx2, ny2,
@@ -607,7 +630,8 @@ def main():
                        "l2": "outputs (%.1f GB per step) exceed the 126 MB L2; the shared map is L2-resident by design" % (n * nx * ny * esz / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches), "planner": planner, "penumbra": penumbra, "giant": giant}
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
