@@ -65,8 +65,9 @@ struct PlannerParams {
 // NWK warps per CTA: 8 by default, capped at 128 registers so that two CTAs share an SM (the
 // uncapped build takes 147 registers, one CTA per SM: 192k vs 239k solves/s on the 1024 x 256^2
 // batch).  4- and 2-warp CTAs (more problems resident per SM) were measured slower even on
-// batches of 256 x 256 maps -- the epilogue pass wants the threads -- as were 6 warps at three
-// CTAs per SM (182k); they stay selectable with VHP_PLANNER_WARPS for experiments.
+// batches of 256 x 256 maps -- the epilogue pass wants the threads -- and stay selectable with
+// VHP_PLANNER_WARPS for experiments.  Also measured and dropped: 6 warps x 3 CTAs per SM and 10
+// warps x 2 (both 96 registers: 182k / 180k), 12 warps x 1 (140 registers: 244k, no better).
 template <int NWK, int MINB = 1>
 __global__ void __launch_bounds__(NWK * 32, MINB) planner_kernel(const PlannerParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -405,7 +406,7 @@ cudaError_t vhp_launch_planner(const VhpTilePlanes &pl, int nx, int ny, const in
     return e ? std::atoi(e) : 0;
   }();
   int nw = 8; // measured on the 1024 x 256^2 batch: 8 warps 240k solves/s, 4 warps 206k, 2 warps slower still
-  if (forced == 2 || forced == 4 || forced == 6 || forced == 8 || forced == 81) nw = forced;
+  if (forced == 2 || forced == 4 || forced == 8) nw = forced;
   auto go = [&](auto kern, int nwarps) -> cudaError_t {
     const size_t smem = tile_smem_bytes<double>(nx, ny, nwarps);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -416,7 +417,5 @@ cudaError_t vhp_launch_planner(const VhpTilePlanes &pl, int nx, int ny, const in
   };
   if (nw == 2) return go(planner_kernel<2>, 2);
   if (nw == 4) return go(planner_kernel<4>, 4);
-  if (nw == 6) return go(planner_kernel<6, 3>, 6); // 3 CTAs per SM (113 registers, 63 KB at 256 x 256)
-  if (nw == 81) return go(planner_kernel<8, 1>, 8); // no register cap (A/B)
   return go(planner_kernel<8, 2>, 8);               // 2 CTAs per SM (<= 128 registers)
 }
