@@ -147,7 +147,9 @@ vhp_status vhp_context_last_transport(const vhp_context *ctx, int64_t *d2h_bytes
  * chunk into dst[0 .. valid_bytes) with `threads` host threads.  Unit u (128 bytes; the last
  * one may be partial) is literal iff bit u % 32 of mask[u / 32]; the literal units of mask
  * word w lie back to back from literals + 128 * word_base[w]; a uniform unit repeats the
- * element desc[u] (elem_bytes = 4 or 8 bytes each). */
+ * element desc[u] (elem_bytes = 4 or 8 bytes each).  literals == NULL is the direct mode: the
+ * literal units are taken to be in dst already (the device stored them there) and are left
+ * untouched; only the uniform units are written. */
 vhp_status vhp_expand_packed_chunk(const uint32_t *mask, const uint32_t *word_base,
                                    const void *desc, int elem_bytes, const void *literals,
                                    int64_t nunits, int64_t valid_bytes, void *dst, int threads);

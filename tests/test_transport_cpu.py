@@ -86,3 +86,32 @@ def test_expand_rejects_inconsistent_sizes(lib):
     assert lib.vhp_expand_packed_chunk(z.ctypes.data, z.ctypes.data, z.ctypes.data, 3, z.ctypes.data,
                                        1, 100, z.ctypes.data, 1) != 0
     assert lib.vhp_expand_packed_chunk(None, None, None, 4, None, 0, 0, None, 1) == 0
+
+
+@pytest.mark.parametrize("elem,dtype", [(4, np.float32), (8, np.float64)])
+def test_direct_mode_leaves_literal_units_alone(lib, elem, dtype):
+    """literals == NULL: the device has stored the literal units in dst; the host threads write
+    the uniform units only"""
+    g = np.random.default_rng(5)
+    n = 40000
+    a = np.ones(n, dtype)
+    for _ in range(60):
+        i, l = int(g.integers(0, n)), int(g.integers(1, 700))
+        a[i:i + l] = g.random(len(a[i:i + l])) if g.random() < 0.5 else 0
+    raw = a.tobytes()
+    assert len(raw) % UNIT == 0
+    mask, base, desc, lit, nunits, nlit = pack_numpy(raw, elem)
+    dst = np.full(len(raw), 0xEE, np.uint8)
+    litmask = np.zeros(nunits, bool)
+    for w in range(len(mask)):
+        for u in range(32):
+            if (int(mask[w]) >> u) & 1:
+                litmask[w * 32 + u] = True
+    src = np.frombuffer(raw, np.uint8).reshape(nunits, UNIT)
+    view = dst.reshape(nunits, UNIT)
+    view[litmask] = src[litmask]          # what the device's stores leave behind
+    st = lib.vhp_expand_packed_chunk(mask.ctypes.data, base.ctypes.data, desc.ctypes.data, elem,
+                                     None, nunits, len(raw), dst.ctypes.data, 3)
+    assert st == 0
+    assert dst.tobytes() == raw
+    assert 0 < nlit < nunits

@@ -63,8 +63,8 @@ void expand_words(const VhpPackedChunk &c, int64_t w0, int64_t w1) {
         if (lit) {
           copy_unit(c.dst + off, lit, bytes);
           lit += kVhpPackUnit;
-        } else if (bytes < (size_t)kVhpPackUnit) { // direct mode: only a partial last unit is ours
-          std::memcpy(c.dst + off, c.tail, bytes);
+        } else if (bytes < (size_t)kVhpPackUnit && c.tail) { // direct mode: only a partial last
+          std::memcpy(c.dst + off, c.tail, bytes);            // unit is ours (from the meta block)
         }
       } else {
         uint64_t pat;
