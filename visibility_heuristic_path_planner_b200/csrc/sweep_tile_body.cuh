@@ -84,6 +84,12 @@
 #ifndef VHP_POLL_BACKOFF
 #define VHP_POLL_BACKOFF 1
 #endif
+#ifndef VHP_POLL_NS0 // first and longest sleep of a warp that waits for the row below (ns)
+#define VHP_POLL_NS0 32
+#endif
+#ifndef VHP_POLL_NSMAX
+#define VHP_POLL_NSMAX 256
+#endif
 #ifndef VHP_DIAG_UNROLL
 #define VHP_DIAG_UNROLL 1
 #endif
@@ -770,8 +776,8 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
       if (NW > 1 && J > 0) { // tile (I, J-1) must be finished
         const int *flag = prog + q * lmcap + J - 1;
 #if VHP_POLL_BACKOFF
-        for (unsigned ns = 32; (GE ? ld_acquire_gpu(flag) : ld_acquire_shared(flag)) <= I;
-             ns = min(2 * ns, 256u))
+        for (unsigned ns = VHP_POLL_NS0; (GE ? ld_acquire_gpu(flag) : ld_acquire_shared(flag)) <= I;
+             ns = min(2 * ns, (unsigned)VHP_POLL_NSMAX))
           __nanosleep(ns);
 #else
         while ((GE ? ld_acquire_gpu(flag) : ld_acquire_shared(flag)) <= I) __nanosleep(40);
