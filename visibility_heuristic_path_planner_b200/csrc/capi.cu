@@ -289,6 +289,18 @@ vhp_status run_host_packed(vhp_context *ctx, Op op, int nmaps, int nx, int ny, c
     (void)cudaGetLastError();
   }
   const bool direct = out_dev != nullptr;
+  if (!ctx->expand_pool) {
+    int t = 0;
+    if (const char *e = std::getenv("VHP_HOST_THREADS")) t = std::atoi(e);
+    if (t <= 0) t = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+    try {
+      ctx->expand_pool = new VhpExpandPool(t);
+    } catch (...) { // no host threads to be had: deliver everything by plain copies
+      ctx->expand_pool = nullptr;
+      *resume_from = 0;
+      return VHP_OK;
+    }
+  }
   ctx->last_transport_packed = direct ? 2 : 1;
   const int nsets = (int)std::min<int64_t>(NS, nchunks);
   for (int s = 0; s < nsets; ++s) {
@@ -310,12 +322,6 @@ vhp_status run_host_packed(vhp_context *ctx, Op op, int nmaps, int nx, int ny, c
     }
     ctx->h_pack_meta_cap = meta_max;
     ctx->h_pack_lit_cap = lit_need;
-  }
-  if (!ctx->expand_pool) {
-    int t = 0;
-    if (const char *e = std::getenv("VHP_HOST_THREADS")) t = std::atoi(e);
-    if (t <= 0) t = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
-    ctx->expand_pool = new VhpExpandPool(t);
   }
   VhpExpandPool &pool = *ctx->expand_pool;
   int64_t tickets[NS] = {0, 0, 0}, last_ticket = 0;
