@@ -115,3 +115,31 @@ def test_direct_mode_leaves_literal_units_alone(lib, elem, dtype):
     assert st == 0
     assert dst.tobytes() == raw
     assert 0 < nlit < nunits
+
+
+def test_expand_fuzz(lib):
+    """random byte strings of every length class: all-literal, all-uniform, partial last units"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 9000), st.sampled_from([4, 8]), st.integers(0, 3), st.integers(0, 2 ** 31))
+    def run(nelem, elem, kind, seed):
+        g = np.random.default_rng(seed)
+        dt = np.uint32 if elem == 4 else np.uint64
+        if kind == 0:
+            a = g.integers(0, 2 ** 31, nelem).astype(dt)                       # nothing compresses
+        elif kind == 1:
+            a = np.full(nelem, 0x3F800000 if elem == 4 else 0x3FF0000000000000, dt)  # all lit
+        else:
+            a = np.repeat(g.integers(0, 3, nelem // 40 + 1), 40)[:nelem].astype(dt)  # flat runs
+        raw = a.tobytes()
+        mask, base, desc, lit, nunits, _ = pack_numpy(raw, elem)
+        dst = np.full(len(raw) + 32, 0xEE, np.uint8)
+        off = (-dst.ctypes.data) % 16
+        d = dst[off:off + len(raw)]
+        assert lib.vhp_expand_packed_chunk(mask.ctypes.data, base.ctypes.data, desc.ctypes.data, elem,
+                                           lit.ctypes.data, nunits, len(raw), d.ctypes.data, 2) == 0
+        assert d.tobytes() == raw
+        assert (dst[off + len(raw):] == 0xEE).all()
+
+    run()
