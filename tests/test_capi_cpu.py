@@ -52,3 +52,20 @@ def test_product_does_not_touch_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle_py" not in src and "vhp_oracle" not in src, f
                 assert "libvhp_ref" not in src and "/root/reference" not in src, f
+
+
+def test_headers_compile_standalone(tmp_path):
+    """include/vhp.h is plain C99 (MATLAB loadlibrary, cgo, ctypes generators read it);
+    include/vhp_solver.hpp is the C++20 drop-in for the reference's classes."""
+    import shutil
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    c = tmp_path / "t.c"
+    c.write_text('#include "vhp.h"\nint main(void) { return vhp_abi_version() > 0 ? 0 : 1; }\n')
+    cpp = tmp_path / "t.cpp"
+    cpp.write_text('#include "vhp_solver.hpp"\nint main() { return 0; }\n')
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                    "-I", inc, str(c)], check=True)
+    subprocess.run(["g++", "-std=c++20", "-Wall", "-fsyntax-only", "-I", inc, str(cpp)], check=True)
