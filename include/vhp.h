@@ -246,6 +246,60 @@ vhp_status vhp_strip_epilogue_dev(vhp_context *ctx, int nx, int ny, int y0, int 
                                   double *d_h_strip, int32_t *d_came_strip,
                                   uint64_t *d_best);
 
+/* ---- e: the planner on ONE giant map over several GPUs, as one call (BASELINE
+ * configs[4]).  One process per GPU; every rank creates a handle for the same map and calls
+ * vhp_giant_solve with the same arguments (collective, like an MPI call).  The map's rows are cut
+ * into world * strips_per_rank contiguous strips, rank r owns strips [r * spr, (r + 1) * spr).
+ * Per planner iteration (updateVisibility :379-565 + the loop of solve() :127-140):
+ *   - two chains of strip sweeps, the +y quadrants upwards and the -y quadrants downwards, on two
+ *     streams; neighbours exchange 2 x nx doubles per chain with ncclSend / ncclRecv over NVLink;
+ *   - epilogue + arg-min per strip, ncclAllGather of 32 bytes per rank {h bits, push-order key,
+ *     vg(end) bits}; every rank takes the lexicographic minimum = priority_queue::top()'s
+ *     first-pushed tie-break and runs the loop control on the device.
+ * The loop state lives in device memory and no launch argument depends on it: one process
+ * captures the iteration as the body of a CUDA-graph WHILE node; several ranks enqueue
+ * iterations in batches, reading a snapshot of the loop state one batch behind.  Either way the
+ * GPU never waits for the host between the first sweep and reconstructPath.
+ * Results are bit-identical to vhp_planner_batch on one GPU (tests/test_gpu_giant.py,
+ * tests/test_gpu_giant_multirank.py).  NCCL is bound at run time (dlopen of libnccl.so.2, env
+ * VHP_NCCL_LIB overrides); world == 1 needs none.
+ *   vhp_giant_unique_id   rank 0: 128 bytes (an ncclUniqueId) to hand to every rank by any side
+ *                         channel (a file, MPI, torch.distributed broadcast ...)
+ *   vhp_giant_create      occ: host uint8 [ny][nx], the whole map on every rank; id: NULL if world == 1
+ *   vhp_giant_solve       se_xy = {start x, start y, end x, end y}; `out` as in vhp_planner_batch
+ *                         for ONE problem, host pointers, any may be NULL; the fields vg / came /
+ *                         vis receive THIS rank's rows (vhp_giant_local_rows) as fp64 / int32
+ *                         [rows][nx]; dtype must be VHP_F64 when vg or vis is requested
+ *   vhp_giant_set_loop_mode  0 automatic (default), 1 CUDA-graph WHILE node (one process only),
+ *                         2 batches of `batch` iterations (0: keep; default 4), 3 one read-back per
+ *                         iteration (for comparisons).  env VHP_GIANT_LOOP / VHP_GIANT_BATCH. */
+#define VHP_GIANT_ID_BYTES 128
+typedef struct vhp_giant vhp_giant;
+typedef struct vhp_giant_stats {
+  int32_t iterations;       /* sweeps run (= nb_of_sources unless the fixed point was fast-forwarded) */
+  int32_t loop_mode;        /* 1 graph, 2 batches, 3 read-back per iteration */
+  double solve_ms;          /* host wall time of the call */
+  double loop_ms;           /* device time of the loop (CUDA events on the main stream) */
+  double nccl_ms;           /* device time between the events around this rank's NCCL calls of the
+                             * loop, waiting for the neighbour included (batches mode) */
+  int64_t nccl_ops, nccl_ops_timed;
+  int64_t halo_bytes_sent;  /* bytes this rank sent to its neighbours in the iterations that ran */
+  int64_t launches;         /* kernels launched by the call */
+} vhp_giant_stats;
+vhp_status vhp_giant_unique_id(void *id);
+vhp_status vhp_giant_create(vhp_context *ctx, const uint8_t *occ, int nx, int ny, int rank,
+                            int world, const void *id, int strips_per_rank, vhp_giant **out);
+void vhp_giant_destroy(vhp_giant *g);
+vhp_status vhp_giant_strip_bounds(const vhp_giant *g, int strip, int *y0, int *y1);
+vhp_status vhp_giant_local_rows(const vhp_giant *g, int *y0, int *y1);
+vhp_status vhp_giant_set_loop_mode(vhp_giant *g, int mode, int batch);
+vhp_status vhp_giant_solve(vhp_giant *g, const int32_t *se_xy, double threshold,
+                           int32_t max_iter, int32_t ls_cap, vhp_dtype dtype,
+                           const vhp_planner_out *out, vhp_giant_stats *stats);
+/* How vhp_planner_batch drives a single large problem (the "grid route"): 0 automatic = CUDA-graph
+ * WHILE node, 2 batches, 3 one read-back per iteration (round-1 behaviour).  env VHP_GIANT_LOOP. */
+vhp_status vhp_context_set_planner_loop(vhp_context *ctx, int mode);
+
 /* widen int32 parents to the reference's Field<size_t> content (host arrays) */
 void vhp_export_came_from_u64(const int32_t *came, int64_t n, uint64_t *out);
 

@@ -108,6 +108,15 @@ def load_library(build_if_missing: bool = True):
     lib.vhp_strip_sweep_dev.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, C.POINTER(vp * 4), i32, vp]
     lib.vhp_strip_epilogue_dev.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, C.c_double,
                                            C.c_int32, vp, vp, vp, vp, vp, vp]
+    lib.vhp_giant_unique_id.argtypes = [vp]
+    lib.vhp_giant_create.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, C.POINTER(vp)]
+    lib.vhp_giant_destroy.argtypes = [vp]
+    lib.vhp_giant_destroy.restype = None
+    lib.vhp_giant_strip_bounds.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
+    lib.vhp_giant_local_rows.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+    lib.vhp_giant_set_loop_mode.argtypes = [vp, i32, i32]
+    lib.vhp_giant_solve.argtypes = [vp, vp, C.c_double, C.c_int32, C.c_int32, i32, C.POINTER(PlannerOut), vp]
+    lib.vhp_context_set_planner_loop.argtypes = [vp, i32]
     lib.vhp_selftest_ratio.argtypes = [vp, i32, C.POINTER(i64)]
     lib.vhp_export_came_from_u64.argtypes = [vp, i64, vp]
     lib.vhp_export_came_from_u64.restype = None
@@ -159,6 +168,11 @@ class Context:
         """0: strip sweeps / large planner problems always on one CTA; 1: spread over many CTAs
         by size (default); 2: always (tests)."""
         self._check(self.lib.vhp_context_set_grid_sweep(self.h, int(mode)))
+
+    def set_planner_loop(self, mode: int):
+        """How vhp_planner_batch drives a single large problem: 0 automatic (CUDA-graph WHILE
+        node), 2 batches of iterations, 3 one host read-back per iteration."""
+        self._check(self.lib.vhp_context_set_planner_loop(self.h, int(mode)))
 
     def set_result_transport(self, mode: int):
         """Transport of host-buffer results: 0 plain copies, 1 automatic (default), 2 always

@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             subprocess.run(cmd, check=True)
     if force or _newer(LIB, objs):
         subprocess.run([NVCC, *ARCH, "-shared", "-ccbin", HOST_CXX, "-o", LIB, *objs,
-                        "-lz", "-cudart", "static"], check=True)
+                        "-lz", "-ldl", "-cudart", "static"], check=True)
     cli_src = os.path.join(CSRC, "cli_main.cpp")
     if os.path.exists(cli_src) and (force or _newer(CLI, [cli_src, LIB] + hdrs)):
         subprocess.run([HOST_CXX, "-std=c++20", "-O2", "-I", os.path.join(ROOT, "include"),

@@ -504,47 +504,23 @@ vhp_status run_host(vhp_context *ctx, Op op, const uint8_t *occ, int nmaps, int 
 }
 
 // ---- planner ------------------------------------------------------------------
-// One LARGE problem on the whole GPU: solve() (src/visibilityBasedSolver.cpp:76-160) driven from
-// the host.  Per iteration: grid-mode sweep of the whole map (many CTAs), per-cell epilogue +
-// arg-min over the whole map (strip epilogue kernels with the strip = the map), next-source
-// selection on the device, 20 bytes of loop state back to the host.  Same results as the
-// persistent single-CTA planner kernel, which would leave all but one SM idle.
+// One LARGE problem on the whole GPU: solve() (src/visibilityBasedSolver.cpp:76-160) as the
+// one-strip case of the strip engine (giant.cu).  Per iteration: grid-mode sweep of the whole
+// map (many CTAs, the +y and -y quadrants as two concurrent launches), per-cell epilogue +
+// arg-min, next-source selection -- all with the loop state on the device, captured as the
+// body of a CUDA-graph WHILE node: no host round trip between the first sweep and the path.
+// Same results as the persistent single-CTA planner kernel, which would leave all but one SM
+// idle.
 vhp_status planner_grid_one(vhp_context *ctx, const VhpTilePlanes &pl, int nx, int ny,
                             const int32_t se[4], double thr, int32_t max_iter, int32_t ls_cap,
                             double *vis, double *vg, double *hc, int32_t *came, int32_t *status,
                             int32_t *nb, int32_t *ls, double *plen, int32_t *pn, int32_t *path,
                             float *vg32, float *vis32) {
-  const int nblocks = vhp_strip_epilogue_blocks(ctx->sm_count);
-  vhp_status st = ensure(ctx, ctx->b_misc, (size_t)nblocks * 16 + 128);
+  vhp_status st = vhp_i_grid_planner_run(ctx, pl, nx, ny, se, thr, max_iter, ls_cap, vis, vg, hc, came, ls);
   if (st != VHP_OK) return st;
-  if ((st = ensure(ctx, ctx->b_grid, vhp_sweep_grid_ws_bytes(nx, ny))) != VHP_OK) return st;
-  unsigned long long *d_partial = (unsigned long long *)ctx->b_misc.p;
-  unsigned long long *d_best = d_partial + 2 * (size_t)nblocks;
-  int *d_ctl = (int *)(d_best + 2);
-  const int stx = se[0], sty = se[1], ex = se[2], ey = se[3];
-  VHP_CUDA(ctx, vhp_launch_grid_planner_begin(pl, nx, ny, stx, sty, ex, ey, thr, vg, hc, came, ls,
-                                              d_ctl, ctx->stream, &ctx->launches));
-  int ctl[5];
-  auto read_ctl = [&]() -> cudaError_t {
-    cudaError_t e = cudaMemcpyAsync(ctl, d_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, ctx->stream);
-    return e != cudaSuccess ? e : cudaStreamSynchronize(ctx->stream);
-  };
-  VHP_CUDA(ctx, read_ctl());
-  const int ctas = grid_sweep_ctas(ctx, ny);
-  while (!ctl[0]) {
-    VHP_CUDA(ctx, vhp_launch_sweep_window(pl, nx, ny, ctl[1], ctl[2], 0, ny, nullptr, VHP_F64, vis,
-                                          ctx->rcp2_table, ctx->d_err, ctx->b_grid.p, ctas,
-                                          ctx->stream, &ctx->launches));
-    VHP_CUDA(ctx, vhp_launch_strip_epilogue(nx, ny, 0, ny, ctl[1], ctl[2], ex, ey, thr, ctl[4], ls,
-                                            vis, vg, hc, came, d_partial, nblocks, d_best,
-                                            ctx->stream, &ctx->launches));
-    VHP_CUDA(ctx, vhp_launch_grid_planner_step(d_best, nx, ex, ey, thr, max_iter, vg, ls, d_ctl,
-                                               ctx->stream, &ctx->launches));
-    VHP_CUDA(ctx, read_ctl());
-  }
-  VHP_CUDA(ctx, vhp_launch_grid_planner_finish(d_ctl, nx, ny, ex, ey, ls_cap, ls, came, vis, vg,
-                                               status, nb, plen, pn, path, vg32, vis32,
-                                               ctx->stream, &ctx->launches));
+  VHP_CUDA(ctx, vhp_launch_grid_planner_finish(vhp_i_grid_planner_ctl(ctx), nx, ny, se[2], se[3], ls_cap,
+                                               ls, came, vis, vg, status, nb, plen, pn, path, vg32,
+                                               vis32, ctx->stream, &ctx->launches));
   return VHP_OK;
 }
 
@@ -644,6 +620,17 @@ vhp_status planner_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx
 
 } // namespace
 
+vhp_status vhp_i_fail(vhp_context *ctx, vhp_status st, const std::string &msg) { return fail(ctx, st, msg); }
+vhp_status vhp_i_ensure_rcp2(vhp_context *ctx, int len) { return ensure_rcp2(ctx, len); }
+int vhp_i_grid_ctas(const vhp_context *ctx, int nx, int ny, int rows) {
+  const bool cta_ok = vhp_sweep_tile_supported(nx, ny);
+  const int mode = ctx->grid_sweep;
+  if (!cta_ok || (mode && vhp_sweep_grid_supported(nx, ny) &&
+                  (int64_t)nx * rows >= (mode > 1 ? 0 : (1 << 20))))
+    return grid_sweep_ctas(ctx, rows);
+  return 1;
+}
+
 extern "C" {
 
 int vhp_abi_version(void) { return VHP_ABI_VERSION; }
@@ -719,6 +706,7 @@ vhp_status vhp_context_create(int device, void *cuda_stream, vhp_context **out) 
 void vhp_context_destroy(vhp_context *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  vhp_i_grid_planner_release(ctx);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
   VhpDevBuf *bufs[] = {&ctx->b_occ, &ctx->b_src, &ctx->b_map, &ctx->b_out[0], &ctx->b_out[1],
@@ -884,6 +872,12 @@ vhp_status vhp_expand_packed_chunk(const uint32_t *mask, const uint32_t *word_ba
   c.valid_bytes = (size_t)valid_bytes;
   VhpExpandPool pool(std::max(1, std::min(threads, 64)));
   pool.wait(pool.submit(c));
+  return VHP_OK;
+}
+
+vhp_status vhp_context_set_planner_loop(vhp_context *ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 3) return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_context_set_planner_loop: bad argument");
+  ctx->grid_loop_mode = mode;
   return VHP_OK;
 }
 

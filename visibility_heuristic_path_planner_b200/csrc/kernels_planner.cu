@@ -220,16 +220,25 @@ struct StripEpilogueParams {
   double *vg, *hc;
   int32_t *came;
   Best *partial; // [gridDim.x]
+  const int *ctl; // non-null: {done, sx, sy, status, nb} on the device replace sx, sy, nb
 };
 
 __global__ void __launch_bounds__(256) strip_epilogue_kernel(const StripEpilogueParams p) {
   __shared__ Best s_best[8];
   const size_t cells = (size_t)(p.y1 - p.y0) * p.nx;
+  int sx = p.sx, sy = p.sy, nb = p.nb, ex = p.ex, ey = p.ey;
+  double thr = p.thr;
+  if (p.ctl) { // loop state and query on the device (kernels_giant.cu)
+    if (p.ctl[0]) return;
+    sx = p.ctl[1]; sy = p.ctl[2]; nb = p.ctl[4];
+    ex = p.ctl[6]; ey = p.ctl[7];
+    thr = *reinterpret_cast<const double *>(p.ctl + 8);
+  }
   Best best{~0ull, ~0ull};
   for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < cells;
        c += (size_t)gridDim.x * blockDim.x) {
     const int Yl = (int)(c / p.nx), X = (int)(c - (size_t)Yl * p.nx);
-    epilogue_cell(X, p.y0 + Yl, c, p.sx, p.sy, p.ex, p.ey, p.thr, p.scale, p.nb, p.ls, p.vis, p.vg,
+    epilogue_cell(X, p.y0 + Yl, c, sx, sy, ex, ey, thr, p.scale, nb, p.ls, p.vis, p.vg,
                   p.hc, p.came, best);
   }
   best = warp_best(best);
@@ -242,8 +251,10 @@ __global__ void __launch_bounds__(256) strip_epilogue_kernel(const StripEpilogue
   }
 }
 
-__global__ void __launch_bounds__(256) strip_best_kernel(const Best *partial, int n, Best *out) {
+__global__ void __launch_bounds__(256) strip_best_kernel(const Best *partial, int n, Best *out,
+                                                         const int *ctl) {
   __shared__ Best s_best[8];
+  if (ctl && ctl[0]) return;
   Best best{~0ull, ~0ull};
   for (int i = threadIdx.x; i < n; i += blockDim.x)
     if (better(partial[i], best)) best = partial[i];
@@ -359,15 +370,16 @@ cudaError_t vhp_launch_strip_epilogue(int nx, int ny, int y0, int y1, int sx, in
                                       double *d_vg, double *d_hc, int32_t *d_came,
                                       unsigned long long *d_partial, int nblocks,
                                       unsigned long long *d_best, cudaStream_t st,
-                                      int64_t *launches) {
+                                      int64_t *launches, const int *d_ctl) {
   StripEpilogueParams p;
   p.nx = nx; p.y0 = y0; p.y1 = y1; p.sx = sx; p.sy = sy; p.ex = ex; p.ey = ey; p.nb = nb;
   p.thr = thr;
   p.scale = std::sqrt((double)((unsigned long long)ny * ny + (unsigned long long)nx * nx)); // :49
   p.ls = d_ls; p.vis = d_vis; p.vg = d_vg; p.hc = d_hc; p.came = d_came;
   p.partial = reinterpret_cast<Best *>(d_partial);
+  p.ctl = d_ctl;
   strip_epilogue_kernel<<<nblocks, 256, 0, st>>>(p);
-  strip_best_kernel<<<1, 256, 0, st>>>(p.partial, nblocks, reinterpret_cast<Best *>(d_best));
+  strip_best_kernel<<<1, 256, 0, st>>>(p.partial, nblocks, reinterpret_cast<Best *>(d_best), d_ctl);
   if (launches) *launches += 2;
   return cudaGetLastError();
 }
@@ -395,6 +407,8 @@ cudaError_t vhp_launch_planner(const VhpTilePlanes &pl, int nx, int ny, const in
   for (int q = 0; q < 4; ++q) p.fp.halo[q] = nullptr;
   p.fp.g_edges = nullptr;
   p.fp.g_lm = p.fp.g_prog = p.fp.g_next_row = nullptr;
+  p.fp.qmask = 0xF;
+  p.fp.src_ctl = nullptr;
   p.se_xy = d_se_xy; p.prob_map = d_prob_map;
   p.thr = threshold; p.max_iter = max_iter; p.ls_cap = ls_cap;
   p.vis = d_vis; p.vg = d_vg; p.hc = d_hc; p.came = d_came;

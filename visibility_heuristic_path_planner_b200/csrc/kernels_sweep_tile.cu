@@ -39,8 +39,13 @@ sweep_tile_kernel(const TileArgs p) {
 // p.out is the strip buffer, row win_y0 first.
 template <typename OutT>
 __global__ void __launch_bounds__(kTileWarps * 32, 1)
-sweep_window_kernel(const TileArgs p, const int sx, const int sy) {
+sweep_window_kernel(const TileArgs p, int sx, int sy) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (p.src_ctl) { // device-side loop control (see TileArgs::src_ctl)
+    if (p.src_ctl[0]) return;
+    sx = p.src_ctl[1];
+    sy = p.src_ctl[2];
+  }
   OutT *out = reinterpret_cast<OutT *>(p.out) - (ptrdiff_t)p.win_y0 * p.nx;
   tile_sweep_cta<OutT, kTileWarps>(p, 0, sx, sy, out, smem_raw);
 }
@@ -51,8 +56,13 @@ sweep_window_kernel(const TileArgs p, const int sx, const int sy) {
 // writes the lit region and runs the tile rows (see tile_sweep_cta).
 template <typename OutT, int MODE>
 __global__ void __launch_bounds__(kTileWarps * 32, MODE == kSweepGridWork ? 2 : 1)
-sweep_grid_kernel(const TileArgs p, const int sx, const int sy) {
+sweep_grid_kernel(const TileArgs p, int sx, int sy) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (p.src_ctl) {
+    if (p.src_ctl[0]) return;
+    sx = p.src_ctl[1];
+    sy = p.src_ctl[2];
+  }
   OutT *out = reinterpret_cast<OutT *>(p.out) - (ptrdiff_t)p.win_y0 * p.nx;
   tile_sweep_cta<OutT, kTileWarps, MODE>(p, 0, sx, sy, out, smem_raw);
 }
@@ -271,6 +281,8 @@ cudaError_t vhp_launch_sweep_tile(const VhpTilePlanes &pl, int nx, int ny, const
   for (int q = 0; q < 4; ++q) p.halo[q] = nullptr;
   p.g_edges = nullptr;
   p.g_lm = p.g_prog = p.g_next_row = nullptr;
+  p.qmask = 0xF;
+  p.src_ctl = nullptr;
   const cudaError_t e = dtype == VHP_F32 ? launch_tile<float>(p, npairs, st)
                                          : launch_tile<double>(p, npairs, st);
   if (launches) *launches += 1;
@@ -332,7 +344,7 @@ cudaError_t vhp_launch_sweep_window(const VhpTilePlanes &pl, int nx, int ny, int
                                     int y1, const double *const d_halo[4], vhp_dtype dtype,
                                     void *d_out_strip, const double *d_rcp2, int *d_err,
                                     void *d_grid_ws, int grid_ctas, cudaStream_t st,
-                                    int64_t *launches) {
+                                    int64_t *launches, int qmask, const int *d_src_ctl) {
   TileArgs p;
   p.pl = pl;
   p.nx = nx;
@@ -347,6 +359,8 @@ cudaError_t vhp_launch_sweep_window(const VhpTilePlanes &pl, int nx, int ny, int
   p.win_y0 = y0;
   p.win_y1 = y1;
   for (int q = 0; q < 4; ++q) p.halo[q] = d_halo ? d_halo[q] : nullptr;
+  p.qmask = qmask;
+  p.src_ctl = d_src_ctl;
   return dtype == VHP_F32 ? launch_window<float>(p, sx, sy, d_grid_ws, grid_ctas, st, launches)
                           : launch_window<double>(p, sx, sy, d_grid_ws, grid_ctas, st, launches);
 }

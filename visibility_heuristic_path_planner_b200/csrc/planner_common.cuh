@@ -157,21 +157,25 @@ __device__ __forceinline__ int planner_next_source(const Best b, const int sx, c
 
 // lightSources_[nb] = end (:141) and reconstructPath (:1183-1213): walk end -> start through
 // cameFrom_ / lightSources_, reverse, sum the segment lengths.  Returns the number of points.
-__device__ __forceinline__ long planner_reconstruct(const int status, const int nb, const int ex,
-                                                    const int ey, const int nx, const int ls_cap,
-                                                    int32_t *ls, const int32_t *came, int32_t *path,
-                                                    double &total) {
+// came_of(t, x, y) = cameFrom_(x, y), where (x, y) is lightSources_[t] (t == nb: the end point);
+// the single-GPU kernels read the field, the strip-partitioned planner a table gathered from
+// the ranks that own the rows.
+template <typename CameOf>
+__device__ __forceinline__ long planner_reconstruct_with(const int status, const int nb, const int ex,
+                                                         const int ey, const int ls_cap, int32_t *ls,
+                                                         int32_t *path, double &total,
+                                                         CameOf came_of) {
   long n = 0;
   total = 0.0;
   if (status != VHP_OK) return 0;
   ls[2 * nb] = ex; ls[2 * nb + 1] = ey;
   int x = ex, y = ey;
-  int t = __ldcg(came + (size_t)y * nx + x), t_old = -2;
+  int t = came_of(nb, x, y), t_old = -2;
   while (t != t_old && t >= 0 && n < ls_cap - 1) {
     path[2 * n] = x; path[2 * n + 1] = y; ++n;
     t_old = t;
     x = ls[2 * t]; y = ls[2 * t + 1];
-    t = __ldcg(came + (size_t)y * nx + x);
+    t = came_of(t, x, y);
   }
   path[2 * n] = x; path[2 * n + 1] = y; ++n;
   for (long a = 0, b = n - 1; a < b; ++a, --b) {
@@ -182,6 +186,14 @@ __device__ __forceinline__ long planner_reconstruct(const int status, const int 
   for (long k = 0; k + 1 < n; ++k)
     total = __dadd_rn(total, eval_d(path[2 * k], path[2 * k + 1], path[2 * k + 2], path[2 * k + 3]));
   return n;
+}
+
+__device__ __forceinline__ long planner_reconstruct(const int status, const int nb, const int ex,
+                                                    const int ey, const int nx, const int ls_cap,
+                                                    int32_t *ls, const int32_t *came, int32_t *path,
+                                                    double &total) {
+  return planner_reconstruct_with(status, nb, ex, ey, ls_cap, ls, path, total,
+                                  [&](int, int x, int y) { return __ldcg(came + (size_t)y * nx + x); });
 }
 
 // lane 0 of the warp ends up with the warp's best

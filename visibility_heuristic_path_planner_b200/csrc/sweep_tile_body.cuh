@@ -132,6 +132,14 @@ struct TileArgs {
   // the row counter live in global memory (null otherwise)
   double *g_edges;
   int *g_lm, *g_prog, *g_next_row;
+  // quadrants to run, bit q = Q(q+1) (0xF: all).  The strip-partitioned planner sweeps the +y
+  // quadrants (Q1, Q2) and the -y quadrants (Q3, Q4) of a strip as two launches: the two
+  // directions travel along the strips independently of each other.
+  int qmask;
+  // window / grid kernels only: {done, sx, sy, ...} in device memory.  Non-null: the source comes
+  // from there and the launch is a no-op once `done` is set, so a planner iteration can be
+  // enqueued (or captured in a CUDA graph) before the host knows the next source.
+  const int *src_ctl;
 };
 
 // how tile_sweep_cta is used
@@ -607,7 +615,7 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
       g.psy = g.diry > 0 ? sy : WYb - 1 - sy;
       int halo_y;
       tile_window_of(q, nx, ny, sx, sy, p.win_y0, p.win_y1, &g.jw0, &g.jw1, &g.Jlo, &g.Jhi, &halo_y);
-      if (g.Jhi < g.Jlo) g.TX = g.TY = 0; // nothing of this quadrant inside the window
+      if (g.Jhi < g.Jlo || !((p.qmask >> q) & 1)) g.TX = g.TY = 0; // nothing of this quadrant to do
       quads[q] = g;
     }
   }

@@ -73,6 +73,8 @@ class VhpExpandPool {
   Impl *impl_;
 };
 
+struct vhp_giant;
+
 struct vhp_context {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -124,7 +126,23 @@ struct vhp_context {
   // statistics of the last host-buffer call (vhp_context_last_transport)
   int64_t last_d2h_bytes = 0, last_result_bytes = 0;
   int last_transport_packed = 0; // 0 plain, 1 packed (staged literal stream), 2 packed (direct)
+  // vhp_planner_batch, one large problem on the whole GPU: the strip engine of giant.cu with one
+  // strip (cached with its captured graph); loop mode as vhp_giant_set_loop_mode
+  vhp_giant *grid_engine = nullptr;
+  int grid_loop_mode = 0;
 };
+
+// helpers of capi.cu used by giant.cu
+vhp_status vhp_i_fail(vhp_context *ctx, vhp_status st, const std::string &msg);
+vhp_status vhp_i_ensure_rcp2(vhp_context *ctx, int len);
+// CTAs one strip sweep of `rows` rows is spread over (1: the single-CTA window kernel)
+int vhp_i_grid_ctas(const vhp_context *ctx, int nx, int ny, int rows);
+// giant.cu: solve() of one problem on buffers the caller owns (planner_dev's grid route)
+vhp_status vhp_i_grid_planner_run(vhp_context *ctx, const VhpTilePlanes &pl, int nx, int ny,
+                                  const int32_t se[4], double thr, int32_t max_iter, int32_t ls_cap,
+                                  double *vis, double *vg, double *hc, int32_t *came, int32_t *ls);
+const int *vhp_i_grid_planner_ctl(const vhp_context *ctx);
+void vhp_i_grid_planner_release(vhp_context *ctx);
 
 // ---- kernel launchers (all enqueue on `st`, return cudaGetLastError()) --------
 // Each launcher returns the number of kernel launches it made through *launches.
@@ -160,7 +178,8 @@ cudaError_t vhp_launch_sweep_window(const VhpTilePlanes &pl, int nx, int ny, int
                                     int y1, const double *const d_halo[4], vhp_dtype dtype,
                                     void *d_out_strip, const double *d_rcp2, int *d_err,
                                     void *d_grid_ws, int grid_ctas, cudaStream_t st,
-                                    int64_t *launches);
+                                    int64_t *launches, int qmask = 0xF,
+                                    const int *d_src_ctl = nullptr);
 // one LARGE planner problem on the whole GPU, host-driven loop (capi.cu: planner_grid_one):
 // reset + validity checks; next-source selection after each sweep + epilogue; outputs.
 // d_ctl = int[5] {done, next x, next y, status, nb_of_sources}
@@ -184,7 +203,7 @@ cudaError_t vhp_launch_strip_epilogue(int nx, int ny, int y0, int y1, int sx, in
                                       double *d_vg, double *d_hc, int32_t *d_came,
                                       unsigned long long *d_partial, int nblocks,
                                       unsigned long long *d_best, cudaStream_t st,
-                                      int64_t *launches);
+                                      int64_t *launches, const int *d_ctl = nullptr);
 
 cudaError_t vhp_launch_rcp2_table(double *d_table, int len, cudaStream_t st, int64_t *launches);
 cudaError_t vhp_launch_ratio2_selftest(const double *d_rcp2, int kmax,
