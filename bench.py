@@ -67,6 +67,22 @@ def workload(name, rank, world=1):
         return maps, src, None, ("1000x1000 grid with the shipped settings.config environment (15 rectangles "
                                  "100-200 cells, %.1f%% occupied), 4096 free-cell light sources per GPU"
                                  % (100.0 * (1.0 - maps.mean())))
+    if name == "c2d":
+        # the headline grid crowded with small obstacles (400 rectangles of 8-40 cells, the
+        # C4 / C5 obstacle sizes): penumbra nearly everywhere, few lit or dark tiles
+        nx = ny = 1000
+        n = 4096
+        g = np.random.default_rng(2600 + rank)
+        maps = np.ones((1, ny, nx), dtype=np.uint8)
+        for _ in range(400):
+            x, y = int(g.integers(1, nx)), int(g.integers(1, ny))
+            w, h = int(g.integers(8, 41)), int(g.integers(8, 41))
+            maps[0, y:y + h, x:x + w] = 0
+        free = np.argwhere(maps[0] != 0)
+        pick = free[g.integers(0, len(free), n)]
+        src = np.ascontiguousarray(pick[:, ::-1]).astype(np.int32)
+        return maps, src, None, ("1000x1000 grid with 400 random rectangles of 8-40 cells (%.1f%% occupied), "
+                                 "4096 free-cell light sources per GPU" % (100.0 * (1.0 - maps.mean())))
     if name == "c4":
         nx = ny = 256
         nmaps, per = 1024, 16
@@ -177,15 +193,37 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def kernel_source_hash():
+    """SHA-256 (first 16 hex digits) of the sources of the dominant kernel: ties an ncu capture to
+    the code it was taken from."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("sweep_tile_body.cuh", "kernels_sweep_tile.cu", "sweep_common.cuh"):
+        h.update(open(os.path.join(ROOT, "visibility_heuristic_path_planner_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic(workload_name, pairs):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture
-    (captured per pair on a subset of the batch, scaled to this launch's pairs)."""
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (per pair on a
+    subset of the batch, scaled to this launch's pairs) -- only while the capture was taken from
+    the kernel sources that are being benchmarked (tools/capture_traffic.py stamps their hash);
+    otherwise null."""
     p = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(p):
-        d = json.load(open(p)).get(workload_name)
-        if d:
+        j = json.load(open(p))
+        d = j.get(workload_name)
+        if d and j.get("kernel_source_hash") == kernel_source_hash():
             return d["dram_bytes_per_pair"] * pairs
     return None
+
+
+def bench_config(workload_name, desc, nx, ny, n, store, world):
+    """The `config` object of the JSON line -- the same for both arms (--impl ours / reference)."""
+    esz = 4 if store == "f32" else 8
+    return {"workload": f"{workload_name}: {desc}", "grid": [nx, ny], "pairs_per_gpu": n, "store": store,
+            "parallelism": f"batch-shard x{world}, no collective",
+            "l2": "outputs (%.1f GB per step) exceed the 126 MB L2; the shared map is L2-resident by design"
+                  % (n * nx * ny * esz / 1e9)}
 
 
 # ----------------------------------------------------------------------------
@@ -195,7 +233,7 @@ def run_reference(args, rank, world):
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     from oracle_py import Oracle, Ref
-    maps, src, smap, desc = workload(args.workload, 0)
+    maps, src, smap, desc = workload(args.workload, 0, max(1, args.gpus))
     ny, nx = maps.shape[1:]
     cores = os.cpu_count() or 1
     per_step = min(len(src), 16 * cores)
@@ -224,10 +262,11 @@ def run_reference(args, rank, world):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "sources_per_step": per_step,
-                       "note": "reference computeVisibility() on host cores; maps with one map only use map 0"},
+            "config": bench_config(args.workload, desc, nx, ny, len(src), args.store, max(1, args.gpus)),
             "cpu_baseline": {"value": val, "unit": "Gcells/s", "cores": cores, "kind": kind,
-                             "sample": f"{per_step} sources per step, one solver instance per thread, flags {flags}"},
+                             "sample": f"each step = {per_step} sources of the workload's batch (a bounded sample, the rate "
+                                       f"is per cell), one solver instance per thread on {cores} threads, fp64 "
+                                       f"Field<double> output, flags {flags}"},
             "e2e": {"value": val, "unit": "Gcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -261,10 +300,170 @@ def cpu_baseline(maps, src, nx, ny):
             "sample": f"oracle/vhp_oracle.c (-O2 -ffp-contract=off), {n1} sources, 1 thread"}
 
 
+
+def _timed_dev(stream, fn, reps, warm=3):
+    """Average milliseconds of fn() enqueued on `stream` (CUDA events on that stream)."""
+    import torch
+    with torch.cuda.stream(stream):
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+    stream.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def _ref_fast():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from oracle_py import Ref
+    return Ref("fast") if Ref.available("fast") else None
+
+
+def c1_leg(vhp, ctx, stream, dev, local_rank, with_cpu):
+    """BASELINE configs[0]: 101 x 101 random environment (parser.h defaults, seed 2), ONE light
+    source, stand-alone visibility -- the reference's only published figure (README.md:9,
+    "~55 kHz").  Latency of one sweep, not throughput."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from oracle_py import Oracle
+    occ = (Oracle().generate_environment(101, 101, 10, 10, 20, 10, 20, 2) != 0).astype(np.uint8)[None]
+    src = np.array([[5, 5]], np.int32)
+    occ_t, src_t = torch.from_numpy(occ).to(dev), torch.from_numpy(src).to(dev)
+    out_t = torch.empty((1, 101, 101), dtype=torch.float64, device=dev)
+    ctx.prepare_maps_dev(occ_t)
+    ms = _timed_dev(stream, lambda: ctx.visibility_batch_dev(occ_t, src_t, out_t), 2000, 20)
+    # the same sweep 4096 times in one launch: what the kernel does when it is not a single CTA
+    nb = 4096
+    srcb = torch.from_numpy(np.repeat(src, nb, 0)).to(dev)
+    outb = torch.empty((nb, 101, 101), dtype=torch.float64, device=dev)
+    msb = _timed_dev(stream, lambda: ctx.visibility_batch_dev(occ_t, srcb, outb), 20)
+    hctx = vhp.Context(local_rank)
+    hctx.visibility_batch(occ, src, dtype=vhp.F64)
+    t0 = time.perf_counter()
+    for _ in range(200):
+        hctx.visibility_batch(occ, src, dtype=vhp.F64)
+    host_us = (time.perf_counter() - t0) / 200 * 1e6
+    hctx.close()
+    out = {"workload": "101x101 random environment (10 rectangles 10-20, glibc rand seed 2), one light source (5,5), fp64",
+           "device_us_per_sweep": ms * 1e3, "device_khz": 1.0 / ms,
+           "host_call_us_per_sweep": host_us, "host_call_khz": 1e3 / host_us,
+           "batched_us_per_sweep": msb * 1e3 / nb, "batched_khz": nb / msb,
+           "note": "device = vhp_visibility_batch_dev with one pair, maps prepared, back-to-back launches timed with "
+                   "CUDA events; host_call = vhp_visibility_batch (upload, pack, sweep, 82 KB back, synchronous); "
+                   "batched = 4096 pairs per launch / time",
+           "published": {"value_khz": 55.0, "hardware": "i9-13980HX, one core", "source": "README.md:9"}}
+    ref = _ref_fast() if with_cpu else None
+    if ref is not None:
+        t = ref.time_compute_visibility(occ[0].astype(np.float64), np.repeat(src, 2000, 0), nthreads=1)
+        out["cpu_reference"] = {"us_per_sweep": t / 2000 * 1e6, "khz": 2000 / t / 1e3, "cores": 1, "kind": "reference",
+                                "sample": f"reference computeVisibility() ({ref.flags()}), 2000 repetitions, one thread"}
+    return out
+
+
+def c3_leg(vhp, local_rank, with_cpu):
+    """BASELINE configs[2]: images/maze_5.png (242 x 322), start {118,317}, end {123,10} (bottom-left
+    origin), threshold 0.2: 112 light sources, path length 1341.7118586874171.  The map
+    comes from the committed golden fixture (the PNG is not on the GPU box)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "maze5.npz"))
+    ny, nx = (int(v) for v in g["shape"])
+    occ = np.unpackbits(g["occ_bits"])[: ny * nx].reshape(ny, nx).astype(np.uint8)
+    start, end = tuple(int(v) for v in g["start"]), tuple(int(v) for v in g["end"])
+    se1 = np.array([start + end], np.int32)
+    ctx = vhp.Context(local_rank)
+    out = {"workload": f"maze_5 ({nx}x{ny}), start {start} end {end} (internal frame), threshold 0.2, max_iter 250"}
+
+    def timed(se, reps, **kw):
+        r = ctx.planner_batch(occ, se, threshold=0.2, max_iter=250, fields=False, **kw)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = ctx.planner_batch(occ, se, threshold=0.2, max_iter=250, fields=False, **kw)
+        return (time.perf_counter() - t0) / reps, r
+
+    t1, r = timed(se1, 5)
+    assert int(r["status"][0]) == 0 and int(r["nb_sources"][0]) == 112, (r["status"], r["nb_sources"])
+    assert float(r["path_len"][0]) == float(g["thr020_len"][0])
+    out["single"] = {"ms_per_solve": t1 * 1e3, "solves_per_s": 1.0 / t1, "sources": 112,
+                     "path_length": float(r["path_len"][0]),
+                     "route": "one problem on the whole GPU: sweeps over many CTAs, loop as a CUDA-graph WHILE node"}
+    for mode, name in ((3, "single_readback_per_iteration"),):
+        ctx.set_planner_loop(mode)
+        t, r2 = timed(se1, 5)
+        assert float(r2["path_len"][0]) == float(r["path_len"][0])
+        out[name] = {"ms_per_solve": t * 1e3}
+    ctx.set_planner_loop(0)
+    ctx.set_grid_sweep(0)  # the persistent one-CTA-per-problem kernel
+    t, r2 = timed(se1, 3)
+    assert float(r2["path_len"][0]) == float(r["path_len"][0])
+    out["single_one_cta"] = {"ms_per_solve": t * 1e3}
+    ctx.set_grid_sweep(1)
+    nb = 1024
+    tb, rb = timed(np.repeat(se1, nb, 0), 2)
+    assert (rb["nb_sources"] == 112).all() and (rb["path_len"] == r["path_len"][0]).all()
+    out["batch_identical"] = {"problems": nb, "ms_per_batch": tb * 1e3, "solves_per_s": nb / tb}
+    rng = np.random.default_rng(5)
+    free = np.argwhere(occ != 0)
+    a, b = free[rng.integers(0, len(free), nb)], free[rng.integers(0, len(free), nb)]
+    sed = np.stack([a[:, 1], a[:, 0], b[:, 1], b[:, 0]], 1).astype(np.int32)
+    td, rd = timed(sed, 2)
+    out["batch_distinct"] = {"problems": nb, "ms_per_batch": td * 1e3, "solves_per_s": nb / td,
+                             "solved": int((rd["status"] == 0).sum()), "max_iter_hit": int((rd["status"] == 5).sum()),
+                             "mean_sources": float(rd["nb_sources"].mean())}
+    ctx.close()
+    ref = _ref_fast() if with_cpu else None
+    if ref is not None:
+        cores = os.cpu_count() or 1
+        s1, _ = ref.time_solve(occ.astype(np.float64), se1, 0.2, 250, nthreads=1)
+        sn, _ = ref.time_solve(occ.astype(np.float64), np.repeat(se1, cores, 0), 0.2, 250, nthreads=cores)
+        out["cpu_reference"] = {"ms_per_solve_1core": s1 * 1e3, "solves_per_s_1core": 1.0 / s1,
+                                "solves_per_s_all_cores": cores / sn, "cores": cores, "kind": "reference",
+                                "sample": f"reference solve() ({ref.flags()}): one solve on one thread; {cores} copies "
+                                          f"of it on {cores} threads"}
+    return out
+
+
+def raycast_leg(vhp, ctx, stream, dev, with_cpu):
+    """BASELINE configs[1] second half, "sweep vs raycasting" (README.md:13, benchmark() :226-235):
+    the all-targets ray casting loop on the empty 1000 x 1000 grid for a 64-source subset of the
+    batch, beside the sweep of the same 64 sources."""
+    import torch
+    maps, src, _, _ = workload("c2", 0, 1)
+    src = np.ascontiguousarray(src[:64])
+    ny, nx = maps.shape[1:]
+    occ_t, src_t = torch.from_numpy(maps).to(dev), torch.from_numpy(src).to(dev)
+    out_t = torch.empty((64, ny, nx), dtype=torch.float32, device=dev)
+    ctx.prepare_maps_dev(occ_t)
+    ms_ray = _timed_dev(stream, lambda: ctx.raycast_batch_dev(occ_t, src_t, out_t), 3, 1)
+    ms_swp = _timed_dev(stream, lambda: ctx.visibility_batch_dev(occ_t, src_t, out_t), 20, 3)
+    rays = 64 * nx * ny
+    # cell visits of the Bresenham walks: max(|dx|, |dy|) per ray
+    xs, ys = np.arange(nx), np.arange(ny)
+    visits = sum(int(np.maximum(np.abs(xs[None, :] - sx), np.abs(ys[:, None] - sy)).sum()) for sx, sy in src)
+    out = {"workload": "empty 1000x1000 grid, 64 light sources (the first 64 of the c2 batch), every cell a target",
+           "raycast_ms": ms_ray, "rays_per_s": rays / ms_ray * 1e3, "cell_visits_per_s": visits / ms_ray * 1e3,
+           "sweep_ms_same_sources": ms_swp, "sweep_vs_raycast": ms_ray / ms_swp,
+           "note": "sweep_vs_raycast = ray-casting time / sweep time for the same 64 sources on the GPU (64 pairs "
+                   "do not fill the machine for either kernel); the reference reports this ratio for one source on "
+                   "one core (README.md:13: ~80x; Samples/benchmark_results.txt N=971: 135x)"}
+    ref = _ref_fast() if with_cpu else None
+    if ref is not None:
+        occ = maps[0].astype(np.float64)
+        t0 = time.perf_counter()
+        ref.raycast_all(occ, int(src[0][0]), int(src[0][1]))
+        t_ray = time.perf_counter() - t0
+        t_swp = ref.time_compute_visibility(occ, src[:8], nthreads=1) / 8
+        out["cpu_reference"] = {"raycast_ms_per_source": t_ray * 1e3, "sweep_ms_per_source": t_swp * 1e3,
+                                "ratio": t_ray / t_swp, "cores": 1, "kind": "reference",
+                                "sample": f"reference raycasting loop for one source and computeVisibility() for 8 "
+                                          f"({ref.flags()}), one thread"}
+    return out
+
 def planner_workload(rank):
-    """Batched planner problems: 16 random 256x256 obstacle maps x 64 (start, end) pairs."""
+    """Batched planner problems: 64 random 256x256 obstacle maps x 128 (start, end) pairs."""
     nx = ny = 256
-    nmaps, per = 16, 64
+    nmaps, per = 64, 128
     g = np.random.default_rng(777 + rank)
     maps = np.ones((nmaps, ny, nx), dtype=np.uint8)
     for m in range(nmaps):
@@ -282,12 +481,26 @@ def planner_workload(rank):
     return maps, se, pmap
 
 
+def executed_sweeps(r):
+    """Sweeps the planner really ran per problem: nb_of_sources, except that a problem stuck on a
+    fixed point (the same source selected again) stops sweeping there while the
+    reference's list is filled up to max_iter."""
+    ls, nb = r["light_sources"], r["nb_sources"]
+    same = (ls[:, 1:] == ls[:, :-1]).all(axis=2)          # ls[i] == ls[i-1], i = 1..
+    idx = np.arange(1, ls.shape[1])[None, :]
+    same &= (idx <= nb[:, None]) & (r["status"][:, None] == 5)
+    first = np.where(same.any(axis=1), same.argmax(axis=1) + 1, nb)
+    return np.minimum(first, nb)
+
+
 def planner_leg(vhp, local_rank, rank, world, dist, dev, with_cpu):
     """Secondary metric of BASELINE.json: planner solves/s (solve() + reconstructPath() per
-    problem, whole loop on the device), through the host-buffer C-ABI call."""
+    problem, whole loop on the device), through the host-buffer C-ABI call, plus the device-
+    resident rate of the same batch and its roofline (29 B per cell and iteration)."""
     import torch
     maps, se, pmap = planner_workload(rank)
     thr, max_iter = 0.5, 100
+    nmaps, ny, nx = maps.shape
     ctx = vhp.Context(local_rank)
     ctx.planner_batch(maps, se, prob_map=pmap, threshold=thr, max_iter=max_iter, fields=False)  # warm-up
     torch.cuda.synchronize()
@@ -298,23 +511,53 @@ def planner_leg(vhp, local_rank, rank, world, dist, dev, with_cpu):
     torch.cuda.synchronize()
     t = (time.perf_counter() - t0) / reps
     ctx.close()
+    # device-resident: inputs and small outputs stay on the GPU, CUDA events on the launch stream
+    stream = torch.cuda.Stream(dev)
+    dctx = vhp.torch_context(local_rank, stream)
+    cap = max_iter + 2
+    n = len(se)
+    occ_t, se_t, pm_t = (torch.from_numpy(a).to(dev) for a in (maps, se, pmap))
+    o = dict(status=torch.zeros(n, dtype=torch.int32, device=dev), nb=torch.zeros(n, dtype=torch.int32, device=dev),
+             ls=torch.zeros((n, cap, 2), dtype=torch.int32, device=dev), plen=torch.zeros(n, dtype=torch.float64, device=dev),
+             pn=torch.zeros(n, dtype=torch.int32, device=dev), path=torch.zeros((n, cap, 2), dtype=torch.int32, device=dev))
+    po = vhp.PlannerOut(o["status"].data_ptr(), o["nb"].data_ptr(), o["ls"].data_ptr(), o["plen"].data_ptr(),
+                        o["pn"].data_ptr(), o["path"].data_ptr(), None, None, None)
+    import ctypes as C
+    dctx.prepare_maps_dev(occ_t)
+
+    def dev_step():
+        st = dctx.lib.vhp_planner_batch_dev(dctx.h, occ_t.data_ptr(), nmaps, nx, ny, se_t.data_ptr(), pm_t.data_ptr(),
+                                            n, thr, max_iter, cap, vhp.F64, C.byref(po))
+        assert st == 0, dctx.lib.vhp_last_error(dctx.h)
+    ms_dev = _timed_dev(stream, dev_step, 3, 1)
+    assert np.array_equal(o["nb"].cpu().numpy(), r["nb_sources"]) and np.array_equal(o["plen"].cpu().numpy(), r["path_len"])
+    dctx.close()
     if world > 1:
-        tt = torch.tensor([t], device=dev, dtype=torch.float64)
+        tt = torch.tensor([t, ms_dev], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t = float(tt.item())
-    out = {"metric": "planner solves/s", "value": world * len(se) / t, "unit": "solves/s",
-           "problems_per_gpu": len(se), "ms_per_batch": t * 1e3,
-           "workload": "16 random 256x256 maps (12 rectangles 8-40) x 64 (start,end) pairs per GPU, "
+        t, ms_dev = float(tt[0].item()), float(tt[1].item())
+    sweeps = int(executed_sweeps(r).sum())
+    peak, _ = measured_peak()
+    alg = 29.0 * nx * ny * sweeps  # occ 1 + vis 8 W + vg 8 R + 8 W + parent 4 R (fp64 working set), SURVEY 8d
+    out = {"metric": "planner solves/s", "value": world * n / t, "unit": "solves/s",
+           "problems_per_gpu": n, "ms_per_batch": t * 1e3,
+           "workload": "64 random 256x256 maps (12 rectangles 8-40) x 128 (start,end) pairs per GPU, "
                        "threshold 0.5, max_iter 100; host-buffer vhp_planner_batch, small outputs only",
            "solved": int((r["status"] == 0).sum()), "max_iter_hit": int((r["status"] == 5).sum()),
-           "mean_sources": float(r["nb_sources"].mean()), "sweeps": int(r["nb_sources"].sum())}
+           "mean_sources": float(r["nb_sources"].mean()), "light_sources": int(r["nb_sources"].sum()),
+           "sweeps": sweeps,
+           "device": {"ms_per_batch": ms_dev, "solves_per_s": world * n / ms_dev * 1e3,
+                      "api": "vhp_planner_batch_dev, maps prepared, inputs and outputs resident, CUDA events"},
+           "roofline": {"bound": "hbm", "achieved": alg / ms_dev / 1e6, "peak": peak, "unit": "GB/s",
+                        "frac": alg / ms_dev / 1e6 / peak, "traffic": None, "kernel": "planner_kernel",
+                        "algorithmic_bytes_per_launch": alg,
+                        "note": "29 B per cell and executed sweep (SURVEY 8d) x %d sweeps of 256x256 cells; "
+                                "device-resident batch time" % sweeps}}
     if with_cpu and rank == 0:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        from oracle_py import Ref
-        if Ref.available("fast"):
-            ref = Ref("fast")
+        ref = _ref_fast()
+        if ref is not None:
             cores = os.cpu_count() or 1
-            nm = 4  # bounded sample: 4 of the 16 maps
+            nm = 2  # bounded sample: 2 of the 64 maps
             secs = 0.0
             for m in range(nm):
                 sel = se[pmap == m]
@@ -327,6 +570,87 @@ def planner_leg(vhp, local_rank, rank, world, dist, dev, with_cpu):
     return out
 
 
+def giant_map(n=8192, seed=8192):
+    g = np.random.default_rng(seed)
+    occ = np.ones((n, n), dtype=np.uint8)
+    for _ in range(int(6000 * (n / 8192) ** 2)):
+        x, y = int(g.integers(1, n)), int(g.integers(1, n))
+        w, h = int(g.integers(8, 65)), int(g.integers(8, 65))
+        occ[y:y + h, x:x + w] = 0
+    return occ, g
+
+
+def giant_leg(vhp, local_rank, rank, world, dist, check=True, size=8192, queries=4):
+    """BASELINE configs[4]: ONE dense random-obstacle 8192 x 8192 map, multi-source planner, the
+    rows partitioned into one strip per GPU (NCCL halo rows + arg-min key exchange inside the
+    library, vhp_giant_*).  On one GPU the same engine runs with a single strip.  With several
+    ranks every rank compares its rows of the first query's fields, and every query's light
+    sources and path, with the single-GPU planner it runs itself."""
+    from visibility_heuristic_path_planner_b200.giant import GiantPlanner
+    occ, g = giant_map(size)
+    free = np.argwhere(occ != 0)
+    picks = free[g.integers(0, len(free), 2 * queries)]
+    qs = [((int(a[1]), int(a[0])), (int(b[1]), int(b[0]))) for a, b in zip(picks[::2], picks[1::2])]
+    thr, max_iter = 0.3, 60
+    if world > 1:
+        gp = GiantPlanner.from_torch_dist(occ, local_rank, dist)
+    else:
+        gp = GiantPlanner(occ, device=local_rank)
+    gp.solve(qs[0][0], qs[0][1], thr, max_iter, fields=False)  # warm-up: graph / communicators
+    recs, firsts = [], None
+    for qi, (a, b) in enumerate(qs):
+        if world > 1:
+            dist.barrier()
+        r = gp.solve(a, b, thr, max_iter, fields=(check and qi == 0 and world > 1))
+        if qi == 0:
+            firsts = r
+        st = r["stats"]
+        recs.append(dict(status=r["status"], sources=r["nb_of_sources"], iterations=st["iterations"],
+                         path_length=r["path_length"], loop_ms=st["loop_ms"], solve_ms=st["solve_ms"],
+                         nccl_ms=st["nccl_ms"], halo_bytes_sent=st["halo_bytes_sent"], ls=r["light_sources"],
+                         path=r["path"]))
+    equal = None
+    if check and world > 1:
+        ctx = vhp.Context(local_rank)
+        same = True
+        for qi, ((a, b), rec) in enumerate(zip(qs, recs)):
+            ref = ctx.planner_batch(occ, [a + b], threshold=thr, max_iter=max_iter, fields=(qi == 0))
+            nb = int(ref["nb_sources"][0])
+            same &= (int(ref["status"][0]) == rec["status"] and nb == rec["sources"]
+                     and np.array_equal(ref["light_sources"][0][: nb + 1], rec["ls"])
+                     and float(ref["path_len"][0]) == rec["path_length"]
+                     and np.array_equal(ref["path"][0][: int(ref["path_n"][0])], rec["path"]))
+            if qi == 0:
+                y0, y1 = firsts["rows"]
+                same &= (np.array_equal(ref["vg"][0][y0:y1], firsts["vg"])
+                         and np.array_equal(ref["vis"][0][y0:y1], firsts["vis"])
+                         and np.array_equal(ref["came"][0][y0:y1], firsts["came"]))
+        ctx.close()
+        verdicts = [None] * world
+        dist.all_gather_object(verdicts, bool(same))
+        equal = all(verdicts)
+    loop_mode = gp.solve(qs[0][0], qs[0][1], thr, 1, fields=False)["stats"]["loop_mode"]
+    gp.close()
+    its = sum(q["iterations"] for q in recs)
+    loop = sum(q["loop_ms"] for q in recs)
+    nccl = sum(q["nccl_ms"] for q in recs)
+    return {"workload": f"one dense random-obstacle {size}x{size} map ({int(6000 * (size / 8192) ** 2)} rectangles 8-64, "
+                        f"{100.0 * (1.0 - occ.mean()):.1f}% occupied), {queries} (start, end) queries, threshold {thr}, "
+                        f"max_iter {max_iter}; fp64 working fields; {world} strip(s), one per GPU",
+            "ranks": world, "queries": queries, "iterations": its, "ms_per_iteration": loop / max(1, its),
+            "ms_per_query": loop / queries,
+            "solve_ms_per_query_host_wall": sum(q["solve_ms"] for q in recs) / queries,
+            "halo_bytes_sent_per_iteration_rank0": (sum(q["halo_bytes_sent"] for q in recs) / max(1, its)),
+            "nccl_time_share_rank0": (nccl / loop) if loop > 0 and world > 1 else 0.0,
+            "nccl_note": "device time between events around rank 0's NCCL calls (ncclSend / ncclRecv of the halo rows, "
+                         "ncclAllGather of the 32-byte key) / loop time; it includes waiting for the neighbour's strip",
+            "loop": {1: "CUDA-graph WHILE node", 2: "batches of 4 iterations, snapshot one batch behind",
+                     3: "read-back per iteration"}.get(loop_mode, loop_mode),
+            "equal_single_gpu": equal,
+            "per_query": [dict(sources=q["sources"], iterations=q["iterations"], status=q["status"],
+                               path_length=q["path_length"], loop_ms=q["loop_ms"]) for q in recs]}
+
+
 # ----------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -334,7 +658,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c2s", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c2s", "c2d", "c4"])
     ap.add_argument("--store", default="f32", choices=["f32", "f64"])
     ap.add_argument("--pairs", type=int, default=0, help="override pairs per GPU (profiling only)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -342,6 +666,7 @@ def main():
     ap.add_argument("--no-planner", action="store_true")
     ap.add_argument("--no-penumbra", action="store_true")
     ap.add_argument("--no-giant", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the C1 / C3 / ray-casting legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -386,6 +711,10 @@ def main():
     src_t = torch.from_numpy(src).to(dev)
     smap_t = None if smap is None else torch.from_numpy(smap).to(dev)
     out_t = torch.empty((n, ny, nx), dtype=tdt, device=dev)
+    # inputs resident in HBM when the timed region starts: the maps and their bit planes (the
+    # kernel's input layout, packed once per batch of maps)
+    with torch.cuda.stream(stream):
+        ctx.prepare_maps_dev(occ_t)
     torch.cuda.synchronize()
 
     def step():
@@ -519,22 +848,15 @@ def main():
     penumbra = None
     if args.workload == "c2" and not args.no_penumbra and not args.pairs:
         penumbra = {}
-        for wl in ("c2s", "c4"):
+        for wl in ("c2s", "c2d", "c4"):
             m2, s2, sm2, d2 = workload(wl, rank, world)
             n2, (ny2, nx2) = len(s2), m2.shape[1:]
             o2 = torch.empty((n2, ny2, nx2), dtype=tdt, device=dev)
             occ2, src2 = torch.from_numpy(m2).to(dev), torch.from_numpy(s2).to(dev)
             smap2 = None if sm2 is None else torch.from_numpy(sm2).to(dev)
             with torch.cuda.stream(stream):
-                for _ in range(3):
-                    ctx.visibility_batch_dev(occ2, src2, o2, smap2)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                for _ in range(10):
-                    ctx.visibility_batch_dev(occ2, src2, o2, smap2)
-                e1.record(stream)
-            stream.synchronize()
-            ms = e0.elapsed_time(e1) / 10
+                ctx.prepare_maps_dev(occ2)
+            ms = _timed_dev(stream, lambda: ctx.visibility_batch_dev(occ2, src2, o2, smap2), 10)
             byts = n2 * nx2 * ny2 * esz + m2.shape[0] * nx2 * ny2
             penumbra[wl] = {"workload": d2, "ms_per_step": ms, "value": n2 * nx2 * ny2 / ms / 1e6,
                             "unit": "Gcells/s", "achieved_gbs": byts / ms / 1e6,
@@ -560,41 +882,44 @@ def main():
                                        "ms_per_step": t2 * 1e3, "d2h_bytes_per_step": int(d2h2),
                                        "result_bytes_per_step": int(res2),
                                        "transport": ["plain", "packed", "packed (direct)"][packed2], "steps": 2}
-            del o2, occ2, src2
+            del o2
+            if wl in ("c2s", "c2d") and args.store == "f32":  # the same batch stored as fp64 (north_star's fp64 mode)
+                o3 = torch.empty((n2, ny2, nx2), dtype=torch.float64, device=dev)
+                ms3 = _timed_dev(stream, lambda: ctx.visibility_batch_dev(occ2, src2, o3, smap2), 5)
+                b3 = n2 * nx2 * ny2 * 8 + m2.shape[0] * nx2 * ny2
+                penumbra[wl]["f64_store"] = {"ms_per_step": ms3, "value": n2 * nx2 * ny2 / ms3 / 1e6, "unit": "Gcells/s",
+                                             "achieved_gbs": b3 / ms3 / 1e6,
+                                             "frac_of_hbm_peak": b3 / ms3 / 1e6 / measured_peak()[0]}
+                del o3
+            del occ2, src2
+    f64_store = None
+    if args.workload == "c2" and args.store == "f32" and not args.no_penumbra and not args.pairs:
+        with torch.cuda.stream(stream):
+            ctx.prepare_maps_dev(occ_t)
+        o3 = torch.empty((n, ny, nx), dtype=torch.float64, device=dev)
+        ms3 = _timed_dev(stream, lambda: ctx.visibility_batch_dev(occ_t, src_t, o3, smap_t), 10)
+        b3 = n * nx * ny * 8 + nmaps * nx * ny
+        f64_store = {"workload": "the headline batch stored as fp64 (bit-identical to the reference's Field<double>)",
+                     "ms_per_step": ms3, "value": cells / ms3 / 1e6, "unit": "Gcells/s",
+                     "roofline": {"bound": "hbm", "achieved": b3 / ms3 / 1e6, "peak": measured_peak()[0], "unit": "GB/s",
+                                  "frac": b3 / ms3 / 1e6 / measured_peak()[0], "algorithmic_bytes_per_launch": b3}}
+        del o3
     if e2e is not None:
         host_ctx.close()
         del out_h
 
-    # ---- BASELINE configs[4] shape on ONE GPU: one planner problem on a dense 8192 x 8192 map
-    # (grid route: every sweep spread over the whole GPU); rank 0 only, not part of `value`
+    # ---- BASELINE configs[4]: one dense 8192 x 8192 map, the planner over all ranks (strip
+    # partition, NCCL inside the library); not part of `value`
     giant = None
-    if args.workload == "c2" and not args.no_giant and not args.pairs and rank == 0:
-        ng = 8192
-        g = np.random.default_rng(8192)
-        occ_g = np.ones((ng, ng), dtype=np.uint8)
-        for _ in range(6000):
-            x, y = int(g.integers(1, ng)), int(g.integers(1, ng))
-            w, h = int(g.integers(8, 65)), int(g.integers(8, 65))
-            occ_g[y:y + h, x:x + w] = 0
-        def free_cell(x0, y0):  # first free cell at or after (x0, y0) in its row
-            x = x0 + int(np.flatnonzero(occ_g[y0, x0:])[0])
-            return x, y0
-        (ax, ay), (bx, by) = free_cell(1200, 1100), free_cell(6800, 7300)
-        se_g = np.array([[ax, ay, bx, by]], np.int32)
-        gctx = vhp.Context(local_rank)
-        gctx.planner_batch(occ_g, se_g, threshold=0.3, max_iter=60, fields=False)  # warm-up
-        gctx.synchronize()
-        t0 = time.perf_counter()
-        rg = gctx.planner_batch(occ_g, se_g, threshold=0.3, max_iter=60, fields=False)
-        gctx.synchronize()
-        tg = time.perf_counter() - t0
-        gctx.close()
-        nbg = int(rg["nb_sources"][0])
-        giant = {"workload": "one planner problem on a dense random-obstacle 8192x8192 map (6000 rectangles 8-64), "
-                             "threshold 0.3, host-buffer vhp_planner_batch incl. the 67 MB map upload",
-                 "ms_per_solve": tg * 1e3, "sources": nbg, "status": int(rg["status"][0]),
-                 "ms_per_iteration": tg * 1e3 / max(nbg, 1), "path_length": float(rg["path_len"][0])}
-        del occ_g
+    if args.workload == "c2" and not args.no_giant and not args.pairs:
+        giant = giant_leg(vhp, local_rank, rank, world, dist if world > 1 else None)
+
+    # ---- single-GPU latency / comparison legs of the other BASELINE configs (rank 0, N = 1)
+    c1 = c3 = raycast = None
+    if args.workload == "c2" and world == 1 and not args.pairs and not args.no_legs:
+        c1 = c1_leg(vhp, ctx, stream, dev, local_rank, not args.no_cpu)
+        c3 = c3_leg(vhp, local_rank, not args.no_cpu)
+        raycast = raycast_leg(vhp, ctx, stream, dev, not args.no_cpu)
 
     planner = None
     if not args.no_planner:
@@ -614,8 +939,11 @@ def main():
                 "frac": achieved / peak, "traffic": ncu_traffic(args.workload, n),
                 "kernel": "sweep_tile_kernel", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
+                "traffic_source": "profiles/k1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per pair; "
+                                  "null unless that capture was taken from the kernel sources benchmarked here, hash %s)"
+                                  % kernel_source_hash(),
                 "note": "per-launch time = CUDA events around one step on the launch stream "
-                        "(sweep kernel + the map-packing launches of a few microseconds); the peak is the "
+                        "(one sweep kernel per step; the maps' bit planes are packed before the timed region); the peak is the "
                         "driver's STREAM-copy figure, a write-only stream can exceed it (torch fill_ of the "
                         "same buffer: 7.5 TB/s on this pool)"}
     cpu = None
@@ -625,11 +953,10 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "grid": [nx, ny],
-                       "pairs_per_gpu": n, "store": args.store, "parallelism": f"batch-shard x{world}, no collective", "rank0_numa_node": numa_node,
-                       "l2": "outputs (%.1f GB per step) exceed the 126 MB L2; the shared map is L2-resident by design" % (n * nx * ny * esz / 1e9)},
+            "config": bench_config(args.workload, desc, nx, ny, n, args.store, world), "rank0_numa_node": numa_node,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": int(launches), "planner": planner, "penumbra": penumbra, "giant": giant}
+            "gpu_launches": int(launches), "planner": planner, "penumbra": penumbra, "f64_store": f64_store,
+            "giant": giant, "c1": c1, "c3": c3, "raycast": raycast}
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:

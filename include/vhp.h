@@ -84,6 +84,7 @@ int vhp_device_count(void);                  /* 0 when there is no usable GPU */
 vhp_status vhp_context_create(int device, void *cuda_stream, vhp_context **out);
 void vhp_context_destroy(vhp_context *ctx);
 vhp_status vhp_context_synchronize(vhp_context *ctx);
+int vhp_context_device(const vhp_context *ctx); /* CUDA device index of the context (-1: NULL) */
 const char *vhp_last_error(const vhp_context *ctx); /* ctx may be NULL: global */
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t vhp_launch_count(const vhp_context *ctx);
@@ -117,6 +118,9 @@ vhp_status vhp_visibility_batch_dev(vhp_context *ctx, const uint8_t *d_occ,
  * nmaps, nx, ny skip the packing pass.  Invalidate by calling it again. */
 vhp_status vhp_prepare_maps_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps,
                                 int nx, int ny);
+/* Forget the prepared maps: call it before the buffer behind d_occ is freed or rewritten (a later
+ * allocation may get the same address). */
+vhp_status vhp_release_maps_dev(vhp_context *ctx);
 
 /* Result transport of the host-buffer calls (vhp_visibility_batch, vhp_raycast_batch).
  * Their results are far larger than what PCIe moves in the time the kernels need (16.4 GB per

@@ -176,9 +176,23 @@ public:
     for (int64_t k = 0; k < n; ++k) out.emplace_back(xy[2 * k], xy[2 * k + 1]);
     return out;
   }
+  // every field as doubles, like the reference's members: cameFrom_ holds the parent index or
+  // 1e15 (Field<size_t> filled with 1e15, :46), occupancyComplement_ 1.0 / 0.0
   Field<double> field(vhp_field which) const {
-    Field<double> f(occupancyComplement_->nx(), occupancyComplement_->ny(), 0.0);
-    vhp_solver_get_field(solver_, which, f.data());
+    const size_t nx = occupancyComplement_->nx(), ny = occupancyComplement_->ny();
+    Field<double> f(nx, ny, 0.0);
+    if (which == VHP_FIELD_CAME_FROM) {
+      std::vector<int32_t> tmp(nx * ny);
+      vhp_solver_get_field(solver_, which, tmp.data());
+      for (size_t k = 0; k < tmp.size(); ++k)
+        f.data()[k] = tmp[k] < 0 ? (double)VHP_NO_PARENT_U64 : (double)tmp[k];
+    } else if (which == VHP_FIELD_OCCUPANCY) {
+      std::vector<uint8_t> tmp(nx * ny);
+      vhp_solver_get_field(solver_, which, tmp.data());
+      for (size_t k = 0; k < tmp.size(); ++k) f.data()[k] = tmp[k] ? 1.0 : 0.0;
+    } else {
+      vhp_solver_get_field(solver_, which, f.data());
+    }
     return f;
   }
 

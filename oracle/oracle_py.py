@@ -177,7 +177,20 @@ class Ref(_Base):
     def available(kind="strict"):
         return os.path.exists(Ref.path(kind))
 
+    @staticmethod
+    def host_has_avx512():
+        try:
+            flags = next(l for l in open("/proc/cpuinfo") if l.startswith("flags")).split()
+        except Exception:
+            return False
+        return all(f in flags for f in ("avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"))
+
     def __init__(self, kind="strict"):
+        # "fast" = the reference's own CMake flags (-O3 -Ofast -march=native -flto); built off the
+        # box, so "native" is the best prebuilt variant this host's CPU can run
+        if kind == "fast" and os.environ.get("VHP_REF_FAST", "") != "v3" and Ref.available("fast_v4") \
+                and Ref.host_has_avx512():
+            kind = "fast_v4"
         self.kind = kind
         self.lib = C.CDLL(Ref.path(kind))
         self._bind_common()

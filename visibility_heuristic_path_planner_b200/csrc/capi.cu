@@ -31,6 +31,24 @@ vhp_status cuda_fail(vhp_context *ctx, cudaError_t e, const char *what) {
     if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);  \
   } while (0)
 
+// Entry points run on the context's device and leave the caller's current device as they found it
+// (a torch process with several GPUs keeps its own notion of the current device).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) err = cudaSetDevice(device);
+    else prev = -1; // nothing to restore
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define VHP_ON_DEVICE(ctx)                 \
+  DeviceGuard device_guard_((ctx)->device); \
+  if (device_guard_.err != cudaSuccess) return cuda_fail(ctx, device_guard_.err, "cudaSetDevice")
+
 vhp_status ensure(vhp_context *ctx, VhpDevBuf &b, size_t bytes) {
   if (bytes <= b.cap) return VHP_OK;
   if (b.p) {
@@ -52,6 +70,7 @@ vhp_status ensure_rcp2(vhp_context *ctx, int len) {
     VHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     VHP_CUDA(ctx, cudaFree(ctx->rcp2_table));
     ctx->rcp2_table = nullptr;
+    ctx->rcp2_len = 0;
   }
   VHP_CUDA(ctx, cudaMalloc(&ctx->rcp2_table, (size_t)len * 2 * sizeof(double)));
   VHP_CUDA(ctx, vhp_launch_rcp2_table(ctx->rcp2_table, len, ctx->stream, &ctx->launches));
@@ -74,6 +93,9 @@ vhp_status pack_tile(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx, 
       VHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       VHP_CUDA(ctx, cudaFree(ctx->tile_buf));
       ctx->tile_buf = nullptr;
+      ctx->tile_bytes = 0;
+      ctx->tile_src = nullptr;
+      ctx->planes_sticky = false;
     }
     VHP_CUDA(ctx, cudaMalloc(&ctx->tile_buf, bytes));
     ctx->tile_bytes = bytes;
@@ -238,13 +260,15 @@ vhp_status run_host_plain(vhp_context *ctx, Op op, int nmaps, int nx, int ny, co
     result = run_dev(ctx, op, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, d_xy + 2 * p0,
                      d_map ? d_map + p0 : nullptr, np, dtype, ctx->b_out[b].p);
     if (result != VHP_OK) break;
-    cudaEventRecord(ctx->ev_done[b], ctx->stream);
-    cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0);
-    cudaError_t e = cudaMemcpyAsync((char *)out + (size_t)p0 * cells * esz, ctx->b_out[b].p,
+    cudaError_t e = cudaEventRecord(ctx->ev_done[b], ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0);
+    if (e != cudaSuccess) { result = cuda_fail(ctx, e, "event hand-over to the copy stream"); break; }
+    e = cudaMemcpyAsync((char *)out + (size_t)p0 * cells * esz, ctx->b_out[b].p,
                                     (size_t)np * cells * esz, cudaMemcpyDeviceToHost,
                                     ctx->copy_stream);
     if (e != cudaSuccess) { result = cuda_fail(ctx, e, "cudaMemcpyAsync D2H"); break; }
-    cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream);
+    e = cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream);
+    if (e != cudaSuccess) { result = cuda_fail(ctx, e, "cudaEventRecord"); break; }
     ctx->last_d2h_bytes += (int64_t)((size_t)np * cells * esz);
   }
   cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream);
@@ -464,7 +488,7 @@ vhp_status run_host(vhp_context *ctx, Op op, const uint8_t *occ, int nmaps, int 
   ctx->last_d2h_bytes = ctx->last_result_bytes = 0;
   ctx->last_transport_packed = 0;
   if (n == 0) return VHP_OK;
-  VHP_CUDA(ctx, cudaSetDevice(ctx->device));
+  VHP_ON_DEVICE(ctx);
   const size_t cells = (size_t)nx * ny, esz = dtype == VHP_F32 ? 4 : 8;
   const size_t occ_bytes = (size_t)nmaps * cells;
   if ((st = ensure(ctx, ctx->b_occ, occ_bytes)) != VHP_OK) return st;
@@ -666,31 +690,40 @@ vhp_status vhp_context_create(int device, void *cuda_stream, vhp_context **out) 
   if (prop.major != 10)
     return fail(nullptr, VHP_ERR_NO_DEVICE,
                 "device is not sm_100 (this library ships sm_100a code only)");
+#define CTX_TRY(call)                                      \
+  do {                                                     \
+    cudaError_t e_ = (call);                               \
+    if (e_ != cudaSuccess) {                               \
+      vhp_context_destroy(ctx);                            \
+      return cuda_fail(nullptr, e_, #call);                \
+    }                                                      \
+  } while (0)
   vhp_context *ctx = new vhp_context();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  VHP_CUDA(nullptr, cudaSetDevice(device));
+  DeviceGuard device_guard_(device);
+  CTX_TRY(device_guard_.err);
   if (cuda_stream) {
     ctx->stream = (cudaStream_t)cuda_stream;
   } else {
-    VHP_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CTX_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->owns_stream = true;
   }
-  VHP_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  CTX_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
-    VHP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
-    VHP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+    CTX_TRY(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+    CTX_TRY(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
   }
-  VHP_CUDA(nullptr, cudaMalloc(&ctx->d_err, sizeof(int)));
-  VHP_CUDA(nullptr, cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+  CTX_TRY(cudaMalloc(&ctx->d_err, sizeof(int)));
+  CTX_TRY(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
   const char *impl = std::getenv("VHP_SWEEP_IMPL");
   ctx->sweep_impl = 0;
   if (impl && std::strcmp(impl, "naive") == 0) ctx->sweep_impl = 1;
   if (const char *e = std::getenv("VHP_GRID_SWEEP")) ctx->grid_sweep = std::atoi(e);
   for (int i = 0; i < vhp_context::kPackSets; ++i) {
-    VHP_CUDA(nullptr, cudaEventCreate(&ctx->ev_pack_meta[i]));
-    VHP_CUDA(nullptr, cudaEventCreate(&ctx->ev_pack_t0[i]));
-    VHP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_pack_lit[i], cudaEventDisableTiming));
+    CTX_TRY(cudaEventCreate(&ctx->ev_pack_meta[i]));
+    CTX_TRY(cudaEventCreate(&ctx->ev_pack_t0[i]));
+    CTX_TRY(cudaEventCreateWithFlags(&ctx->ev_pack_lit[i], cudaEventDisableTiming));
   }
   if (const char *e = std::getenv("VHP_RESULT_TRANSPORT")) {
     if (std::strcmp(e, "plain") == 0) ctx->result_transport = 0;
@@ -699,16 +732,17 @@ vhp_status vhp_context_create(int device, void *cuda_stream, vhp_context **out) 
   if (const char *e = std::getenv("VHP_RESULT_DIRECT")) ctx->result_direct = std::atoi(e) != 0;
   if (const char *e = std::getenv("VHP_RESULT_GPU_SHARE")) ctx->result_gpu_share = std::atoi(e);
   ctx->transport_trace = std::getenv("VHP_TRANSPORT_TRACE") != nullptr;
+#undef CTX_TRY
   *out = ctx;
   return VHP_OK;
 }
 
 void vhp_context_destroy(vhp_context *ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
+  DeviceGuard device_guard_(ctx->device);
   vhp_i_grid_planner_release(ctx);
-  cudaStreamSynchronize(ctx->stream);
-  cudaStreamSynchronize(ctx->copy_stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   VhpDevBuf *bufs[] = {&ctx->b_occ, &ctx->b_src, &ctx->b_map, &ctx->b_out[0], &ctx->b_out[1],
                        &ctx->b_scratch, &ctx->b_planner, &ctx->b_misc, &ctx->b_grid};
   for (VhpDevBuf *b : bufs)
@@ -731,21 +765,25 @@ void vhp_context_destroy(vhp_context *ctx) {
     if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
     if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
   }
-  cudaStreamDestroy(ctx->copy_stream);
-  if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  (void)cudaGetLastError();
   delete ctx;
 }
 
 vhp_status vhp_context_synchronize(vhp_context *ctx) {
   if (!ctx) return fail(nullptr, VHP_ERR_INVALID_ARG, "null context");
+  VHP_ON_DEVICE(ctx);
   return check_device_error(ctx);
 }
+
+int vhp_context_device(const vhp_context *ctx) { return ctx ? ctx->device : -1; }
 
 vhp_status vhp_prepare_maps_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx,
                                 int ny) {
   if (!ctx || !d_occ || nmaps < 1 || nx < 1 || ny < 1)
     return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_prepare_maps_dev: bad argument");
-  VHP_CUDA(ctx, cudaSetDevice(ctx->device));
+  VHP_ON_DEVICE(ctx);
   if (!vhp_sweep_tile_supported(nx, ny) && !vhp_sweep_grid_supported(nx, ny))
     return VHP_OK; // the naive kernel reads the byte maps
   const vhp_status st = pack_tile(ctx, d_occ, nmaps, nx, ny, true);
@@ -753,12 +791,19 @@ vhp_status vhp_prepare_maps_dev(vhp_context *ctx, const uint8_t *d_occ, int nmap
   return st;
 }
 
+vhp_status vhp_release_maps_dev(vhp_context *ctx) {
+  if (!ctx) return fail(nullptr, VHP_ERR_INVALID_ARG, "null context");
+  ctx->planes_sticky = false;
+  ctx->tile_src = nullptr;
+  return VHP_OK;
+}
+
 vhp_status vhp_visibility_batch_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx,
                                     int ny, const int32_t *d_src_xy, const int32_t *d_src_map,
                                     int64_t npairs, vhp_dtype dtype, void *d_out) {
   vhp_status st = check_common(ctx, d_occ, nmaps, nx, ny, d_src_xy, npairs, dtype, d_out);
   if (st != VHP_OK) return st;
-  VHP_CUDA(ctx, cudaSetDevice(ctx->device));
+  VHP_ON_DEVICE(ctx);
   return run_dev(ctx, Op::Sweep, d_occ, nmaps, nx, ny, d_src_xy, d_src_map, npairs, dtype, d_out);
 }
 
@@ -773,7 +818,7 @@ vhp_status vhp_raycast_batch_dev(vhp_context *ctx, const uint8_t *d_occ, int nma
                                  int64_t npairs, vhp_dtype dtype, void *d_out) {
   vhp_status st = check_common(ctx, d_occ, nmaps, nx, ny, d_src_xy, npairs, dtype, d_out);
   if (st != VHP_OK) return st;
-  VHP_CUDA(ctx, cudaSetDevice(ctx->device));
+  VHP_ON_DEVICE(ctx);
   return run_dev(ctx, Op::Raycast, d_occ, nmaps, nx, ny, d_src_xy, d_src_map, npairs, dtype,
                  d_out);
 }
@@ -787,7 +832,7 @@ vhp_status vhp_raycast_batch(vhp_context *ctx, const uint8_t *occ, int nmaps, in
 vhp_status vhp_selftest_ratio(vhp_context *ctx, int kmax, int64_t *mismatches) {
   if (!ctx || !mismatches || kmax < 1 || kmax > 16384)
     return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_selftest_ratio: bad argument");
-  VHP_CUDA(ctx, cudaSetDevice(ctx->device));
+  VHP_ON_DEVICE(ctx);
   vhp_status st = ensure_rcp2(ctx, kmax + 8);
   if (st != VHP_OK) return st;
   if ((st = ensure(ctx, ctx->b_misc, 64)) != VHP_OK) return st;
@@ -815,7 +860,7 @@ vhp_status vhp_environment_generate_batch_dev(vhp_context *ctx, const vhp_config
       cfg->nb_of_obstacles < 0 || cfg->nb_of_obstacles > 0x7fffffff || cfg->min_width < 0 ||
       cfg->min_height < 0 || cfg->max_width < cfg->min_width || cfg->max_height < cfg->min_height)
     return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_environment_generate_batch_dev: bad environment settings");
-  VHP_CUDA(ctx, cudaSetDevice(ctx->device));
+  VHP_ON_DEVICE(ctx);
   VHP_CUDA(ctx, vhp_launch_env_generate(d_occ, nmaps, (int)cfg->ncols, (int)cfg->nrows, first_map,
                                         seed, cfg->nb_of_obstacles, cfg->min_width, cfg->max_width,
                                         cfg->min_height, cfg->max_height, ctx->stream,
@@ -907,7 +952,7 @@ vhp_status vhp_strip_sweep_dev(vhp_context *ctx, const uint8_t *d_occ, int nx, i
   for (int q = 0; q < 4; ++q)
     if (rows[q] >= 0 && (!d_halo || !d_halo[q]))
       return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_strip_sweep_dev: missing halo row");
-  VHP_CUDA(ctx, cudaSetDevice(ctx->device));
+  VHP_ON_DEVICE(ctx);
   vhp_status st = ensure_rcp2(ctx, std::max(nx, ny) + 64);
   if (st != VHP_OK) return st;
   if ((st = pack_tile(ctx, d_occ, 1, nx, ny, false)) != VHP_OK) return st;
@@ -935,7 +980,7 @@ vhp_status vhp_strip_epilogue_dev(vhp_context *ctx, int nx, int ny, int y0, int 
   if (!ctx || !d_light_sources || !d_vis_strip || !d_vg_strip || !d_h_strip || !d_came_strip ||
       !d_best || nx < 1 || ny < 1 || y0 < 0 || y1 > ny || y0 >= y1 || nb < 0)
     return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_strip_epilogue_dev: bad argument");
-  VHP_CUDA(ctx, cudaSetDevice(ctx->device));
+  VHP_ON_DEVICE(ctx);
   const int nblocks = vhp_strip_epilogue_blocks(ctx->sm_count);
   vhp_status st = ensure(ctx, ctx->b_misc, (size_t)nblocks * 16 + 64);
   if (st != VHP_OK) return st;
@@ -954,7 +999,7 @@ vhp_status vhp_planner_batch_dev(vhp_context *ctx, const uint8_t *d_occ, int nma
   static const vhp_planner_out none = {};
   vhp_status st = check_common(ctx, d_occ, nmaps, nx, ny, d_se_xy, nprob, dtype, ctx);
   if (st != VHP_OK) return st;
-  VHP_CUDA(ctx, cudaSetDevice(ctx->device));
+  VHP_ON_DEVICE(ctx);
   return planner_dev(ctx, d_occ, nmaps, nx, ny, d_se_xy, d_prob_map, nprob, threshold, max_iter,
                      ls_cap, dtype, d_out ? *d_out : none);
 }
@@ -971,7 +1016,7 @@ vhp_status vhp_planner_batch(vhp_context *ctx, const uint8_t *occ, int nmaps, in
     if ((st = check_points(ctx, nullptr, 0, prob_map, nprob, nmaps, nx, ny, "vhp_planner_batch")) != VHP_OK)
       return st;
   if (nprob == 0) return VHP_OK;
-  VHP_CUDA(ctx, cudaSetDevice(ctx->device));
+  VHP_ON_DEVICE(ctx);
   const size_t cells = (size_t)nx * ny, esz = dtype == VHP_F32 ? 4 : 8;
   if ((st = ensure(ctx, ctx->b_occ, (size_t)nmaps * cells)) != VHP_OK) return st;
   if ((st = ensure(ctx, ctx->b_src, (size_t)nprob * 16)) != VHP_OK) return st;

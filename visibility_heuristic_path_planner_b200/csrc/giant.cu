@@ -557,7 +557,10 @@ vhp_status vhp_giant_solve(vhp_giant *g, const int32_t *se_xy, double threshold,
   if ((o.vg || o.vis) && dtype != VHP_F64)
     return vhp_i_fail(g->ctx, VHP_ERR_UNSUPPORTED, "vhp_giant_solve: strip fields are exported as fp64 only");
   vhp_context *ctx = g->ctx;
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
   GCUDA(g, cudaSetDevice(ctx->device));
+  struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore_{prev_dev};
   const auto t_begin = std::chrono::steady_clock::now();
   vhp_status st = alloc_small(g, ls_cap);
   if (st != VHP_OK) return st;

@@ -91,6 +91,12 @@ bool apply(vhp_config *cfg, const KeySpec &k, const std::string &key, const std:
       }
       store_int(cfg, k, v);
     } catch (...) {
+      // the reference's minHeight branch only prints the first line and keeps parsing
+      // (src/parser.cpp:117-127); every other key of this kind is fatal
+      if (key == "minHeight") {
+        invalid(key, value, nullptr);
+        return true;
+      }
       invalid(key, value, "It must be a positive integer\n");
       return false;
     }

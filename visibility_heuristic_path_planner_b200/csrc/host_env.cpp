@@ -23,6 +23,8 @@
 
 namespace {
 
+constexpr int kMaxImageSide = 16384; // largest grid side the library supports
+
 struct Rgba {
   int w = 0, h = 0;
   std::vector<unsigned char> px; // RGBA8, row-major, top-left origin
@@ -67,6 +69,7 @@ bool decode_png(const std::vector<unsigned char> &buf, Rgba &img) {
     pos += 12 + (size_t)len;
   }
   if (!have_ihdr || interlace != 0 || img.w <= 0 || img.h <= 0) return false;
+  if (img.w > kMaxImageSide || img.h > kMaxImageSide) return false; // beyond the supported grid
   int channels;
   switch (ctype) {
   case 0: channels = 1; break;
@@ -151,6 +154,7 @@ bool decode_pnm(const std::vector<unsigned char> &buf, Rgba &img) {
   };
   unsigned w, h, maxv;
   if (!next_uint(w) || !next_uint(h) || !next_uint(maxv) || maxv != 255) return false;
+  if (w == 0 || h == 0 || w > (unsigned)kMaxImageSide || h > (unsigned)kMaxImageSide) return false;
   ++pos; // single whitespace
   const int ch = buf[1] == '6' ? 3 : 1;
   if (pos + (size_t)w * h * ch > buf.size()) return false;
@@ -204,7 +208,13 @@ vhp_status vhp_environment_load_image(const char *filename, uint8_t *occ, int *n
   if (!filename || !nx || !ny) return VHP_ERR_INVALID_ARG;
   std::vector<unsigned char> buf;
   Rgba img;
-  if (!read_file(filename, buf) || !(decode_png(buf, img) || decode_pnm(buf, img))) {
+  bool ok = false;
+  try { // a corrupt file must not throw through the C boundary
+    ok = read_file(filename, buf) && (decode_png(buf, img) || decode_pnm(buf, img));
+  } catch (...) {
+    ok = false;
+  }
+  if (!ok) {
     std::cout << "Error: Failed to load image" << std::endl;
     return VHP_ERR_IO;
   }

@@ -233,7 +233,14 @@ vhp_status time_sweep_and_raycast(vhp_solver *s, const uint8_t *occ, int nx, int
   uint8_t *d_occ = nullptr;
   int32_t *d_src = nullptr;
   double *d_out = nullptr;
-  auto cleanup = [&]() { cudaFree(d_occ); cudaFree(d_src); cudaFree(d_out); };
+  // (the bit planes the context cached for d_occ must not outlive it: a later allocation may get
+  // the same address)
+  auto cleanup = [&]() { vhp_release_maps_dev(s->ctx); cudaFree(d_occ); cudaFree(d_src); cudaFree(d_out); };
+  // allocate on the context's device, whatever the caller's current device is; restore it after
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
+  if (cudaSetDevice(vhp_context_device(s->ctx)) != cudaSuccess) return VHP_ERR_CUDA;
+  struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore_{prev_dev};
   if (cudaMalloc(&d_occ, cells) != cudaSuccess || cudaMalloc(&d_src, 8) != cudaSuccess ||
       cudaMalloc(&d_out, cells * 8) != cudaSuccess) {
     cleanup();

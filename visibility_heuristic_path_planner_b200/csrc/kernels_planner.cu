@@ -268,40 +268,9 @@ __global__ void __launch_bounds__(256) strip_best_kernel(const Best *partial, in
   }
 }
 
-// ---- one LARGE problem on the whole GPU ("grid planner"): the loop of solve() driven from
-// the host, one iteration = grid-mode sweep (kernels_sweep_tile.cu) + strip epilogue over the
-// whole map + the control kernels below.  ctl = {done, next x, next y, status, nb_of_sources}
-// is read back by the host after every iteration (20 bytes).
-__global__ void grid_planner_reset_kernel(double *vg, double *hc, int32_t *came, size_t cells) {
-  for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < cells;
-       c += (size_t)gridDim.x * blockDim.x) { // reset(), :42-60
-    vg[c] = 0.0;
-    hc[c] = __longlong_as_double(0x7ff0000000000000ll);
-    came[c] = VHP_NO_PARENT;
-  }
-}
-
-__global__ void grid_planner_begin_kernel(const uint32_t *rowbits, int wx, int nx, int ny, int stx,
-                                          int sty, int ex, int ey, double thr, int32_t *ls,
-                                          int32_t *came, int *ctl) {
-  const int st = planner_validate(rowbits, wx, nx, ny, stx, sty, ex, ey);
-  int done = 1;
-  if (st == VHP_OK) {
-    ls[0] = stx; ls[1] = sty;                 // lightSources_[0] = start, :121
-    came[(size_t)sty * nx + stx] = 0;         // :122
-    done = !(0.0 <= thr);                     // visibility_global_(end) = 0 (:123), loop test :127
-  }
-  ctl[0] = done; ctl[1] = stx; ctl[2] = sty; ctl[3] = st; ctl[4] = 0;
-}
-
-__global__ void grid_planner_step_kernel(const Best *best, int nx, int ex, int ey, double thr,
-                                         int max_iter, const double *vg, int32_t *ls, int *ctl) {
-  int tx, ty, d, st = ctl[3];
-  const int nnb = planner_next_source(*best, ctl[1], ctl[2], ctl[4], max_iter, thr,
-                                      __ldcg(vg + (size_t)ey * nx + ex), ls, tx, ty, d, st);
-  ctl[0] = d; ctl[1] = tx; ctl[2] = ty; ctl[3] = st; ctl[4] = nnb;
-}
-
+// ---- one LARGE problem on the whole GPU: the loop runs in the strip engine (giant.cu,
+// kernels_giant.cu: one strip = the whole map); ctl = {done, next x, next y, status,
+// nb_of_sources, ...} stays on the device.
 // tail of solve(): outputs of problem q; vis keeps the zeros of reset() if no sweep ran;
 // optional fp32 exports
 __global__ void grid_planner_finish_kernel(const int *ctl, int nx, int ny, int ex, int ey, int ls_cap,
@@ -328,27 +297,6 @@ __global__ void grid_planner_finish_kernel(const int *ctl, int nx, int ny, int e
 }
 
 } // namespace
-
-cudaError_t vhp_launch_grid_planner_begin(const VhpTilePlanes &pl, int nx, int ny, int stx, int sty,
-                                          int ex, int ey, double thr, double *d_vg, double *d_hc,
-                                          int32_t *d_came, int32_t *d_ls, int *d_ctl,
-                                          cudaStream_t st, int64_t *launches) {
-  grid_planner_reset_kernel<<<148 * 8, 256, 0, st>>>(d_vg, d_hc, d_came, (size_t)nx * ny);
-  grid_planner_begin_kernel<<<1, 1, 0, st>>>(pl.rowF, pl.wx, nx, ny, stx, sty, ex, ey, thr, d_ls,
-                                             d_came, d_ctl);
-  if (launches) *launches += 2;
-  return cudaGetLastError();
-}
-
-cudaError_t vhp_launch_grid_planner_step(const unsigned long long *d_best, int nx, int ex, int ey,
-                                         double thr, int max_iter, const double *d_vg,
-                                         int32_t *d_ls, int *d_ctl, cudaStream_t st,
-                                         int64_t *launches) {
-  grid_planner_step_kernel<<<1, 1, 0, st>>>(reinterpret_cast<const Best *>(d_best), nx, ex, ey, thr,
-                                            max_iter, d_vg, d_ls, d_ctl);
-  if (launches) *launches += 1;
-  return cudaGetLastError();
-}
 
 cudaError_t vhp_launch_grid_planner_finish(const int *d_ctl, int nx, int ny, int ex, int ey,
                                            int ls_cap, int32_t *d_ls, const int32_t *d_came,

@@ -180,17 +180,8 @@ cudaError_t vhp_launch_sweep_window(const VhpTilePlanes &pl, int nx, int ny, int
                                     void *d_grid_ws, int grid_ctas, cudaStream_t st,
                                     int64_t *launches, int qmask = 0xF,
                                     const int *d_src_ctl = nullptr);
-// one LARGE planner problem on the whole GPU, host-driven loop (capi.cu: planner_grid_one):
-// reset + validity checks; next-source selection after each sweep + epilogue; outputs.
-// d_ctl = int[5] {done, next x, next y, status, nb_of_sources}
-cudaError_t vhp_launch_grid_planner_begin(const VhpTilePlanes &pl, int nx, int ny, int stx, int sty,
-                                          int ex, int ey, double thr, double *d_vg, double *d_hc,
-                                          int32_t *d_came, int32_t *d_ls, int *d_ctl,
-                                          cudaStream_t st, int64_t *launches);
-cudaError_t vhp_launch_grid_planner_step(const unsigned long long *d_best, int nx, int ex, int ey,
-                                         double thr, int max_iter, const double *d_vg,
-                                         int32_t *d_ls, int *d_ctl, cudaStream_t st,
-                                         int64_t *launches);
+// one LARGE planner problem on the whole GPU (capi.cu: planner_grid_one -> giant.cu): outputs
+// from the loop state d_ctl = {done, next x, next y, status, nb_of_sources, ...}
 cudaError_t vhp_launch_grid_planner_finish(const int *d_ctl, int nx, int ny, int ex, int ey,
                                            int ls_cap, int32_t *d_ls, const int32_t *d_came,
                                            double *d_vis, const double *d_vg, int32_t *d_status,
