@@ -841,6 +841,42 @@ def main():
                                    "d2h_bytes_per_step": int(d2h_plain)},
                "api": "vhp_visibility_batch (host buffers; pinned output; H2D + kernel + D2H (+ host expansion) "
                       "inside the timed region; %d result pairs compared with the device-resident run)" % len(probe)}
+        # ---- the same call with the thresholded, bit-packed result (vhp_visibility_batch_bin)
+        wpr = (nx + 31) // 32
+        bits_h = torch.empty((n, ny, wpr), dtype=torch.int32, pin_memory=True)
+        bits_np = bits_h.numpy().view(np.uint32)
+        thr_bin = 0.5
+
+        def bin_step():
+            st = lib.vhp_visibility_batch_bin(host_ctx.h, maps.ctypes.data, nmaps, nx, ny, src.ctypes.data,
+                                              None if smap is None else smap.ctypes.data, n, thr_bin,
+                                              bits_np.ctypes.data)
+            assert st == 0, host_ctx.lib.vhp_last_error(host_ctx.h)
+        bin_step()
+        for p_ in probe:
+            bits_np[p_].fill(0xA5A5A5A5)
+        barrier()
+        kb = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(kb):
+            bin_step()
+        torch.cuda.synchronize()
+        t_bin = (time.perf_counter() - t0) / kb
+        if world > 1:
+            tt = torch.tensor([t_bin], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_bin = float(tt.item())
+        for p_ in probe:  # against the device-resident fp32 run: exact wherever fp32 cannot move a cell across 0.5
+            want = out_t[p_].cpu().numpy() >= thr_bin
+            assert np.array_equal(vhp.unpack_bits(bits_np[p_], nx), want), f"binary e2e result differs (pair {p_})"
+        e2e["binary"] = {"value": cells_e2e * world / t_bin / 1e9, "unit": "Gcells/s", "ms_per_step": t_bin * 1e3,
+                         "steps": kb, "threshold": thr_bin,
+                         "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],
+                         "d2h_bytes_per_step": int(n) * ny * wpr * 4,
+                         "api": "vhp_visibility_batch_bin (host buffers, pinned output): H2D, fp64 sweeps, threshold + "
+                                "bit packing on the device, D2H of 1 bit per cell, all inside the timed region; bit-exact "
+                                "against the fp64 field compared with >= threshold (tests/test_gpu_sweep.py)"}
+        del bits_h
         n, src, smap = n_full, src_full, smap_full
 
     # ---- the same grid and batch size with obstacles (kernel-only, rank-local): how the

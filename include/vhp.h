@@ -112,6 +112,20 @@ vhp_status vhp_visibility_batch_dev(vhp_context *ctx, const uint8_t *d_occ,
                                     const int32_t *d_src_xy,
                                     const int32_t *d_src_map, int64_t npairs,
                                     vhp_dtype dtype, void *d_out);
+/* Thresholded binary visibility, bit-packed: the part of the result that decides (which cells a
+ * light source sees), 32 x smaller than fp32 fields -- 125 KB instead of 4 MB per 1000 x 1000 sweep,
+ * so the host-buffer call is no longer bound by the host's memory system and scales with the
+ * GPUs' PCIe links.
+ *   out_bits[p][y][w], w < ceil(nx / 32): bit b of word w = visibility_(32w + b, y) >= threshold
+ * decided on the fp64 value, i.e. bit-exact against the reference's fp64 field compared with
+ * `>= threshold` (the test the planner applies, :419); bits beyond nx are 0. */
+vhp_status vhp_visibility_batch_bin(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx,
+                                    int ny, const int32_t *src_xy, const int32_t *src_map,
+                                    int64_t npairs, double threshold, uint32_t *out_bits);
+vhp_status vhp_visibility_batch_bin_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps,
+                                        int nx, int ny, const int32_t *d_src_xy,
+                                        const int32_t *d_src_map, int64_t npairs,
+                                        double threshold, uint32_t *d_out_bits);
 /* Optional, for repeated _dev calls on the same maps: packs the maps into the
  * bit-plane layout the sweep kernel reads (row- and column-major bit maps, forward
  * and mirrored, plus a free-block summary) once, so later vhp_visibility_batch_dev calls with the same d_occ pointer,

@@ -210,3 +210,36 @@ def test_raycast_vs_oracle(ctx, vhp, oracle):
     out = ctx.raycast_batch(occ, srcs, dtype=vhp.F32)
     for s, o in zip(srcs, out):
         assert np.array_equal(o, oracle.raycast_all(occ, *s).astype(np.float32)), s
+
+
+def test_binary_visibility_bit_exact(ctx, vhp, oracle):
+    """vhp_visibility_batch_bin: bit b of word w = (fp64 visibility >= threshold), bit-exact
+    against the oracle's field for thresholds that occur exactly in the field (0.5, 1.0), the
+    planner's defaults and the degenerate 0; several maps, odd widths, host and device entry."""
+    import torch
+    rng = np.random.default_rng(11)
+    for nx, ny, nobs, seed in ((101, 101, 10, 7), (77, 133, 14, 3), (260, 40, 9, 5), (33, 31, 2, 1)):
+        occ = np.stack([rect_map(nx, ny, nobs, seed + k, 3, 14) for k in range(3)])
+        n = 12
+        smap = rng.integers(0, 3, n).astype(np.int32)
+        src = np.stack([rng.integers(0, nx, n), rng.integers(0, ny, n)], 1).astype(np.int32)
+        src[0] = (nx // 2, ny // 2)
+        ref = np.stack([oracle.compute_visibility(occ[m], sx, sy) for (sx, sy), m in zip(src, smap)])
+        for thr in (0.5, 0.25, 1.0, 0.0, 1e-300, 0.49999999999999994):
+            bits = ctx.visibility_batch_bin(occ, src, thr, src_map=smap)
+            assert bits.shape == (n, ny, (nx + 31) // 32) and bits.dtype == np.uint32
+            assert np.array_equal(vhp.unpack_bits(bits, nx), ref >= thr), (nx, ny, thr)
+            pad = np.unpackbits(bits.view(np.uint8), axis=-1, bitorder="little")[..., nx:]
+            assert not pad.any()  # bits beyond nx are 0
+        dev = torch.device("cuda", 0)
+        out_t = torch.full((n, ny, (nx + 31) // 32), -1, dtype=torch.int32, device=dev)
+        ctx.visibility_batch_bin_dev(torch.from_numpy(occ != 0).to(torch.uint8).to(dev), torch.from_numpy(src).to(dev),
+                                     0.5, out_t, torch.from_numpy(smap).to(dev))
+        ctx.synchronize()
+        assert np.array_equal(vhp.unpack_bits(out_t.cpu().numpy().view(np.uint32), nx), ref >= 0.5)
+    # the strict-IEEE flip cell of SURVEY 8c: 0.49999999999999989 < 0.5 must read "not visible"
+    g = load_golden("sweep.npz")
+    seed, x, y = map(int, g["kat_flip"])
+    occ = oracle.generate_environment(101, 101, 10, 10, 20, 10, 20, seed)
+    bits = vhp.unpack_bits(ctx.visibility_batch_bin(occ, [(50, 50)], 0.5), 101)[0]
+    assert not bits[y, x] and oracle.compute_visibility(occ, 50, 50)[y, x] < 0.5

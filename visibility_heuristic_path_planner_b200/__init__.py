@@ -89,6 +89,10 @@ def load_library(build_if_missing: bool = True):
     for name in ("vhp_visibility_batch", "vhp_visibility_batch_dev", "vhp_raycast_batch",
                  "vhp_raycast_batch_dev"):
         getattr(lib, name).argtypes = batch
+    lib.vhp_visibility_batch_bin.argtypes = [vp, vp, i32, i32, i32, vp, vp, i64, C.c_double, vp]
+    lib.vhp_visibility_batch_bin_dev.argtypes = [vp, vp, i32, i32, i32, vp, vp, i64, C.c_double, vp]
+    lib.vhp_release_maps_dev.argtypes = [vp]
+    lib.vhp_context_device.argtypes = [vp]
     lib.vhp_prepare_maps_dev.argtypes = [vp, vp, i32, i32, i32]
     plan = [vp, vp, i32, i32, i32, vp, vp, i64, C.c_double, C.c_int32, C.c_int32, i32,
             C.POINTER(PlannerOut)]
@@ -227,6 +231,30 @@ class Context:
         array to fill instead of a new one (pinned host memory gets the fastest transport)."""
         return self._batch_host(self.lib.vhp_visibility_batch, occ, src_xy, src_map, dtype, out)
 
+    def visibility_batch_bin(self, occ, src_xy, threshold, src_map=None, out=None):
+        """Thresholded binary visibility, bit-packed (vhp_visibility_batch_bin): uint32
+        (npairs, ny, ceil(nx/32)), bit b of word w = visibility(32w + b, y) >= threshold."""
+        occ = _occ_u8(occ)
+        nmaps, ny, nx = occ.shape
+        xy = np.ascontiguousarray(src_xy, dtype=np.int32).reshape(-1, 2)
+        n = xy.shape[0]
+        mp = None if src_map is None else np.ascontiguousarray(src_map, dtype=np.int32)
+        wpr = (nx + 31) // 32
+        if out is None:
+            out = np.empty((n, ny, wpr), dtype=np.uint32)
+        elif out.dtype != np.uint32 or out.shape != (n, ny, wpr) or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous uint32 (npairs, ny, ceil(nx/32)) array")
+        self._check(self.lib.vhp_visibility_batch_bin(self.h, _np_ptr(occ), nmaps, nx, ny, _np_ptr(xy),
+                                                      _np_ptr(mp), n, float(threshold), _np_ptr(out)))
+        return out
+
+    def visibility_batch_bin_dev(self, occ_t, src_xy_t, threshold, out_bits_t, src_map_t=None):
+        nmaps, ny, nx = occ_t.shape
+        self._check(self.lib.vhp_visibility_batch_bin_dev(
+            self.h, occ_t.data_ptr(), nmaps, nx, ny, src_xy_t.data_ptr(),
+            None if src_map_t is None else src_map_t.data_ptr(), src_xy_t.shape[0], float(threshold),
+            out_bits_t.data_ptr()))
+
     def raycast_batch(self, occ, src_xy, src_map=None, dtype=F64, out=None):
         return self._batch_host(self.lib.vhp_raycast_batch, occ, src_xy, src_map, dtype, out)
 
@@ -290,6 +318,12 @@ class Context:
     def prepare_maps_dev(self, occ_t):
         nmaps, ny, nx = occ_t.shape
         self._check(self.lib.vhp_prepare_maps_dev(self.h, occ_t.data_ptr(), nmaps, nx, ny))
+
+
+def unpack_bits(bits, nx):
+    """uint32 (..., ceil(nx/32)) bit-packed rows -> bool (..., nx)."""
+    b = np.ascontiguousarray(bits).view(np.uint8)
+    return np.unpackbits(b, axis=-1, bitorder="little")[..., :nx].astype(bool)
 
 
 def torch_context(device: int, stream) -> Context:

@@ -243,10 +243,12 @@ vhp_status run_host_plain(vhp_context *ctx, Op op, int nmaps, int nx, int ny, co
   const size_t buf_bytes = (size_t)chunk * cells * esz;
   if ((st = ensure(ctx, ctx->b_out[0], buf_bytes)) != VHP_OK) return st;
   if (n - p_begin > chunk && (st = ensure(ctx, ctx->b_out[1], buf_bytes)) != VHP_OK) return st;
-  // pin the caller's buffer for full-rate async copies (ignore "already pinned")
-  const size_t out_bytes = (size_t)n * cells * esz;
-  const bool registered =
-      cudaHostRegister(out, out_bytes, cudaHostRegisterDefault) == cudaSuccess;
+  // pin the caller's buffer for full-rate async copies (ignore "already pinned").  Page-locking
+  // costs milliseconds: small results (a single 101 x 101 sweep is 80 KB) are copied as they are.
+  const size_t out_bytes = (size_t)(n - p_begin) * cells * esz;
+  char *const out_first = (char *)out + (size_t)p_begin * cells * esz;
+  const bool registered = out_bytes >= ((size_t)32 << 20) &&
+                          cudaHostRegister(out_first, out_bytes, cudaHostRegisterDefault) == cudaSuccess;
   (void)cudaGetLastError();
   vhp_status result = VHP_OK;
   int it = 0;
@@ -273,7 +275,7 @@ vhp_status run_host_plain(vhp_context *ctx, Op op, int nmaps, int nx, int ny, co
   }
   cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream);
   cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-  if (registered) cudaHostUnregister(out);
+  if (registered) cudaHostUnregister(out_first);
   if (result != VHP_OK) return result;
   if (e1 != cudaSuccess) return cuda_fail(ctx, e1, "sync copy stream");
   if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "sync stream");
@@ -527,6 +529,94 @@ vhp_status run_host(vhp_context *ctx, Op op, const uint8_t *occ, int nmaps, int 
   return check_device_error(ctx);
 }
 
+// ---- thresholded binary visibility ------------------------------------------------------------
+// Chunks of pairs: fp64 sweep into a device buffer, threshold_bits_kernel, and for host callers
+// the D2H of chunk c (copy stream, two bit buffers) under the sweeps of chunk c + 1.
+int64_t bin_chunk_pairs(size_t cells, int64_t n) {
+  return std::min<int64_t>(n, std::max<int64_t>(1, (int64_t)(((size_t)4 << 30) / (cells * 8))));
+}
+
+vhp_status run_bin_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx, int ny,
+                       const int32_t *d_xy, const int32_t *d_map, int64_t n, double thr,
+                       uint32_t *d_bits) {
+  const size_t cells = (size_t)nx * ny, wpr = (size_t)(nx + 31) / 32;
+  const int64_t chunk = bin_chunk_pairs(cells, n);
+  vhp_status st = ensure(ctx, ctx->b_bin, (size_t)chunk * cells * 8);
+  if (st != VHP_OK) return st;
+  for (int64_t p0 = 0; p0 < n; p0 += chunk) {
+    const int64_t np = std::min(chunk, n - p0);
+    st = run_dev(ctx, Op::Sweep, d_occ, nmaps, nx, ny, d_xy + 2 * p0, d_map ? d_map + p0 : nullptr, np,
+                 VHP_F64, ctx->b_bin.p);
+    if (st != VHP_OK) return st;
+    VHP_CUDA(ctx, vhp_launch_threshold_bits((const double *)ctx->b_bin.p, np * ny, nx, thr,
+                                            d_bits + (size_t)p0 * ny * wpr, ctx->sm_count, ctx->stream,
+                                            &ctx->launches));
+  }
+  return VHP_OK;
+}
+
+vhp_status run_bin_host(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx, int ny,
+                        const int32_t *xy, const int32_t *maps, int64_t n, double thr,
+                        uint32_t *out_bits) {
+  vhp_status st = check_common(ctx, occ, nmaps, nx, ny, xy, n, VHP_F64, out_bits);
+  if (st != VHP_OK) return st;
+  if ((st = check_points(ctx, xy, 2, maps, n, nmaps, nx, ny, "vhp_visibility_batch_bin")) != VHP_OK) return st;
+  ctx->last_d2h_bytes = ctx->last_result_bytes = 0;
+  ctx->last_transport_packed = 0;
+  if (n == 0) return VHP_OK;
+  VHP_ON_DEVICE(ctx);
+  const size_t cells = (size_t)nx * ny, wpr = (size_t)(nx + 31) / 32, occ_bytes = (size_t)nmaps * cells;
+  if ((st = ensure(ctx, ctx->b_occ, occ_bytes)) != VHP_OK) return st;
+  if ((st = ensure(ctx, ctx->b_src, (size_t)n * 8)) != VHP_OK) return st;
+  if (maps && (st = ensure(ctx, ctx->b_map, (size_t)n * 4)) != VHP_OK) return st;
+  VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_occ.p, occ, occ_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_src.p, xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (maps) VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_map.p, maps, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->planes_sticky = false;
+  ctx->tile_src = nullptr;
+  if (ctx->sweep_impl == 0 && (vhp_sweep_tile_supported(nx, ny) || vhp_sweep_grid_supported(nx, ny))) {
+    if ((st = pack_tile(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, true)) != VHP_OK) return st;
+    ctx->planes_sticky = true;
+  }
+  const int32_t *d_xy = (const int32_t *)ctx->b_src.p;
+  const int32_t *d_map = maps ? (const int32_t *)ctx->b_map.p : nullptr;
+  const int64_t chunk = bin_chunk_pairs(cells, n);
+  const size_t pair_words = (size_t)ny * wpr, chunk_bytes = (size_t)chunk * pair_words * 4;
+  vhp_status result = ensure(ctx, ctx->b_bin, (size_t)chunk * cells * 8);
+  for (int b = 0; b < 2 && result == VHP_OK; ++b)
+    if (b == 0 || n > chunk) result = ensure(ctx, ctx->b_out[b], chunk_bytes);
+  int it = 0;
+  for (int64_t p0 = 0; p0 < n && result == VHP_OK; p0 += chunk, ++it) {
+    const int b = it & 1;
+    const int64_t np = std::min(chunk, n - p0);
+    cudaError_t e = cudaSuccess;
+    if (it >= 2) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0); // bit buffer b is free again
+    if (e != cudaSuccess) { result = cuda_fail(ctx, e, "cudaStreamWaitEvent"); break; }
+    result = run_dev(ctx, Op::Sweep, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, d_xy + 2 * p0,
+                     d_map ? d_map + p0 : nullptr, np, VHP_F64, ctx->b_bin.p);
+    if (result != VHP_OK) break;
+    e = vhp_launch_threshold_bits((const double *)ctx->b_bin.p, np * ny, nx, thr, (uint32_t *)ctx->b_out[b].p,
+                                  ctx->sm_count, ctx->stream, &ctx->launches);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_done[b], ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(out_bits + (size_t)p0 * pair_words, ctx->b_out[b].p, (size_t)np * pair_words * 4,
+                          cudaMemcpyDeviceToHost, ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream);
+    if (e != cudaSuccess) { result = cuda_fail(ctx, e, "binary visibility: enqueue"); break; }
+    ctx->last_d2h_bytes += (int64_t)((size_t)np * pair_words * 4);
+  }
+  cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream);
+  cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+  ctx->planes_sticky = false;
+  ctx->tile_src = nullptr;
+  ctx->last_result_bytes = (int64_t)((size_t)n * pair_words * 4);
+  if (result != VHP_OK) return result;
+  if (e1 != cudaSuccess) return cuda_fail(ctx, e1, "sync copy stream");
+  if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "sync stream");
+  return check_device_error(ctx);
+}
+
 // ---- planner ------------------------------------------------------------------
 // One LARGE problem on the whole GPU: solve() (src/visibilityBasedSolver.cpp:76-160) as the
 // one-strip case of the strip engine (giant.cu).  Per iteration: grid-mode sweep of the whole
@@ -744,7 +834,7 @@ void vhp_context_destroy(vhp_context *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   VhpDevBuf *bufs[] = {&ctx->b_occ, &ctx->b_src, &ctx->b_map, &ctx->b_out[0], &ctx->b_out[1],
-                       &ctx->b_scratch, &ctx->b_planner, &ctx->b_misc, &ctx->b_grid};
+                       &ctx->b_scratch, &ctx->b_planner, &ctx->b_misc, &ctx->b_grid, &ctx->b_bin};
   for (VhpDevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   delete ctx->expand_pool;
@@ -811,6 +901,21 @@ vhp_status vhp_visibility_batch(vhp_context *ctx, const uint8_t *occ, int nmaps,
                                 const int32_t *src_xy, const int32_t *src_map, int64_t npairs,
                                 vhp_dtype dtype, void *out) {
   return run_host(ctx, Op::Sweep, occ, nmaps, nx, ny, src_xy, src_map, npairs, dtype, out);
+}
+
+vhp_status vhp_visibility_batch_bin(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx, int ny,
+                                    const int32_t *src_xy, const int32_t *src_map, int64_t npairs,
+                                    double threshold, uint32_t *out_bits) {
+  return run_bin_host(ctx, occ, nmaps, nx, ny, src_xy, src_map, npairs, threshold, out_bits);
+}
+
+vhp_status vhp_visibility_batch_bin_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx,
+                                        int ny, const int32_t *d_src_xy, const int32_t *d_src_map,
+                                        int64_t npairs, double threshold, uint32_t *d_out_bits) {
+  vhp_status st = check_common(ctx, d_occ, nmaps, nx, ny, d_src_xy, npairs, VHP_F64, d_out_bits);
+  if (st != VHP_OK) return st;
+  VHP_ON_DEVICE(ctx);
+  return run_bin_dev(ctx, d_occ, nmaps, nx, ny, d_src_xy, d_src_map, npairs, threshold, d_out_bits);
 }
 
 vhp_status vhp_raycast_batch_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx,

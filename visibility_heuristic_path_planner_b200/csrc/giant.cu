@@ -137,6 +137,10 @@ vhp_status enqueue_iteration(vhp_giant *g, unsigned long long cond, int use_cond
   const int n = g->loc.n, nx = g->nx, ny = g->ny, last = g->nstrips - 1;
   const size_t row2 = 2 * (size_t)nx;
   vhp_status st;
+  if (g->nstrips == 1) {
+    // one strip: nothing to hand over, all four quadrants in one launch
+    if ((st = sweep_strip(g, 0, 0xF, S, g->ws[0])) != VHP_OK) return st;
+  } else {
   GCUDA(g, cudaEventRecord(g->ev_fork, S));
   GCUDA(g, cudaStreamWaitEvent(D, g->ev_fork, 0));
   // ---- UP chain: +y quadrants, ascending strips, stream S
@@ -185,6 +189,7 @@ vhp_status enqueue_iteration(vhp_giant *g, unsigned long long cond, int use_cond
   }
   GCUDA(g, cudaEventRecord(g->ev_join, D));
   GCUDA(g, cudaStreamWaitEvent(S, g->ev_join, 0));
+  }
   // ---- epilogue + arg-min per strip, exchange, loop control
   for (int s = 0; s < n; ++s) {
     const GiantStripDev &sd = g->loc.s[s];
@@ -240,7 +245,7 @@ int launches_per_iteration(const vhp_giant *g) {
   int n = 0;
   for (int s = 0; s < g->loc.n; ++s) {
     const int ctas = vhp_i_grid_ctas(g->ctx, g->nx, g->ny, g->loc.s[s].y1 - g->loc.s[s].y0);
-    n += 2 * (ctas > 1 ? 2 : 1) + 2;                 // two sweeps, epilogue + its reduction
+    n += (g->nstrips == 1 ? 1 : 2) * (ctas > 1 ? 2 : 1) + 2; // sweep(s), epilogue + its reduction
     if (g->k0 + s > 0) n += 1;                       // halo rows handed up / down (local copy
     if (g->k0 + s < g->nstrips - 1) n += 1;          // or the gather in front of a send)
   }

@@ -147,3 +147,46 @@ cudaError_t vhp_launch_pack_results(const void *d_in, int64_t nunits, int elem_b
   if (launches) *launches += 1;
   return cudaGetLastError();
 }
+
+
+// ---- thresholded binary visibility (VHP binary output) ----------------------------------------
+// bits[p][y][w], w < ceil(nx / 32): bit b of word w = (vis[p][y][32w + b] >= thr), decided on the
+// fp64 value the sweep computed (the reference's `visibility_ >= threshold`, bit-exact; an fp32
+// round trip could flip cells that sit on the threshold).  One warp per two words: 2 x 256
+// bytes of coalesced loads, two ballots.
+namespace {
+
+__global__ void __launch_bounds__(256)
+threshold_bits_kernel(const double *__restrict__ vis, const int64_t nrows, const int nx, const int wpr,
+                      const double thr, uint32_t *__restrict__ bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int pairs_per_row = (wpr + 1) >> 1;
+  const int64_t total = nrows * pairs_per_row;
+  for (int64_t t = warp0; t < total; t += nwarps) {
+    const int64_t row = t / pairs_per_row;
+    const int w0 = 2 * (int)(t - row * pairs_per_row);
+    const double *r = vis + row * nx;
+    const int xa = 32 * w0 + lane, xb = xa + 32;
+    const double a = xa < nx ? __ldcs(r + xa) : -1.0, b = xb < nx ? __ldcs(r + xb) : -1.0;
+    const uint32_t ma = __ballot_sync(kAllLanes, xa < nx && a >= thr);
+    const uint32_t mb = __ballot_sync(kAllLanes, xb < nx && b >= thr);
+    if (lane == 0) bits[row * wpr + w0] = ma;
+    if (lane == 1 && w0 + 1 < wpr) bits[row * wpr + w0 + 1] = mb;
+  }
+}
+
+} // namespace
+
+cudaError_t vhp_launch_threshold_bits(const double *d_vis, int64_t nrows, int nx, double thr,
+                                      uint32_t *d_bits, int sm_count, cudaStream_t st, int64_t *launches) {
+  const int wpr = (nx + 31) / 32;
+  const int64_t warps = nrows * ((wpr + 1) / 2);
+  int64_t blocks = (warps + 7) / 8;
+  if (blocks > (int64_t)sm_count * 16) blocks = (int64_t)sm_count * 16;
+  if (blocks < 1) blocks = 1;
+  threshold_bits_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_vis, nrows, nx, wpr, thr, d_bits);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}

@@ -58,6 +58,10 @@ cudaError_t vhp_launch_pack_results(const void *d_in, int64_t nunits, int elem_b
                                     int gpu_share, int sm_count, cudaStream_t st,
                                     int64_t *launches);
 
+// thresholded binary visibility: bits[row][ceil(nx/32)] from fp64 rows (result_transport.cu)
+cudaError_t vhp_launch_threshold_bits(const double *d_vis, int64_t nrows, int nx, double thr,
+                                      uint32_t *d_bits, int sm_count, cudaStream_t st, int64_t *launches);
+
 // host threads that expand packed chunks into the caller's buffer (FIFO, each job is spread
 // over all threads)
 class VhpExpandPool {
@@ -86,7 +90,7 @@ struct vhp_context {
   // device-side error word (bit 0: a source / start / end outside the grid)
   int *d_err = nullptr;
   // workspace buffers (grown on demand, reused across calls)
-  VhpDevBuf b_occ, b_src, b_map, b_out[2], b_scratch, b_planner, b_misc, b_grid;
+  VhpDevBuf b_occ, b_src, b_map, b_out[2], b_scratch, b_planner, b_misc, b_grid, b_bin;
   cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   // 1/k table {rh, rl} of the tile kernel (double-double reciprocal), device resident
   double *rcp2_table = nullptr;
