@@ -86,12 +86,7 @@ __global__ void __launch_bounds__(NWK * 32, MINB) planner_kernel(const PlannerPa
   int32_t *ls = p.ls + q * (size_t)p.ls_cap * 2;
   const double thr = p.thr;
 
-  // reset(): :42-60 (every sweep writes all of `vis`, border cells included)
-  for (size_t c = tid; c < cells; c += blockDim.x) {
-    vg[c] = 0.0;
-    hc[c] = __longlong_as_double(0x7ff0000000000000ll);
-    came[c] = VHP_NO_PARENT;
-  }
+  // reset() (:42-60) happens inside the first sweep's epilogue (epilogue_cell_first)
   if (tid == 0) {
     s_ctl[3] = planner_validate(rowbits, p.fp.pl.wx, nx, ny, stx, sty, ex, ey);
     s_ctl[1] = stx;
@@ -104,7 +99,7 @@ __global__ void __launch_bounds__(NWK * 32, MINB) planner_kernel(const PlannerPa
   if (status == VHP_OK) {
     if (tid == 0) {
       ls[0] = stx; ls[1] = sty;                 // lightSources_[0] = start, :121
-      came[(size_t)sty * nx + stx] = 0;         // :122
+      // cameFrom_(start) = 0 (:122) is part of the first epilogue;
       // visibility_global_(end) = 0 (:123) holds after the reset; loop test :127
       s_ctl[0] = !(0.0 <= thr);
     }
@@ -116,37 +111,44 @@ __global__ void __launch_bounds__(NWK * 32, MINB) planner_kernel(const PlannerPa
     while (!done) {
       // ---- 1. sweep (visibility_.reset() + the DP of updateVisibility)
       tile_sweep_cta<double, NWK>(p.fp, map, sx, sy, vis, smem_raw);
-      // ---- 2. per-cell epilogue + arg-min
+      // ---- 2. per-cell epilogue + arg-min: a warp per grid row, kEpiU cells per lane in flight
+      // (one CTA has few threads for a whole map: with one cell in flight per thread the pass was
+      // latency-bound at ~1 TB/s in total)
       Best best{~0ull, ~0ull};
-      {
-        // cell c = tid + k * blockDim.x, walked incrementally, kEpiU cells per round: all their
-        // field loads are issued before the first is used (one CTA has few threads for a whole
-        // map; with one cell in flight per thread the pass was latency-bound at ~1 TB/s in total)
+      if (nb == 0) {
+        // first sweep: the fields are still uninitialised workspace; nothing is loaded, everything
+        // stored (reset() :42-60 and the first epilogue in one pass)
+        for (int Y = warp; Y < ny; Y += NW) {
+          const size_t row = (size_t)Y * nx;
+#pragma unroll 2
+          for (int X = lane; X < nx; X += 32)
+            epilogue_cell_first(X, Y, row + X, __ldcg(vis + row + X), sx, sy, ex, ey, thr, scale, ls, vg, hc,
+                                came, best);
+        }
+      } else {
         constexpr int kEpiU = 4;
-        int X = tid % nx, Y = tid / nx;
-        const int bdx = blockDim.x % nx, bdy = blockDim.x / nx;
-        for (size_t c0 = tid; c0 < cells; c0 += (size_t)kEpiU * blockDim.x) {
-          double v[kEpiU], h[kEpiU], g0[kEpiU];
-          int cf[kEpiU];
+        for (int Y = warp; Y < ny; Y += NW) {
+          const size_t row = (size_t)Y * nx;
+          for (int X0 = lane; X0 < nx; X0 += 32 * kEpiU) {
+            double v[kEpiU], h[kEpiU], g0[kEpiU];
+            int cf[kEpiU];
 #pragma unroll
-          for (int u = 0; u < kEpiU; ++u) {
-            const size_t c = c0 + (size_t)u * blockDim.x;
-            if (c < cells) {
-              v[u] = __ldcg(vis + c);
-              h[u] = __ldcg(hc + c);
-              g0[u] = __ldcg(vg + c);
-              cf[u] = __ldcg(came + c);
+            for (int u = 0; u < kEpiU; ++u) {
+              const int X = X0 + 32 * u;
+              if (X < nx) {
+                v[u] = __ldcg(vis + row + X);
+                h[u] = __ldcg(hc + row + X);
+                g0[u] = __ldcg(vg + row + X);
+                cf[u] = __ldcg(came + row + X);
+              }
             }
-          }
 #pragma unroll
-          for (int u = 0; u < kEpiU; ++u) {
-            const size_t c = c0 + (size_t)u * blockDim.x;
-            if (c < cells)
-              epilogue_cell_loaded(X, Y, c, v[u], h[u], g0[u], cf[u], sx, sy, ex, ey, thr, scale, nb,
-                                   ls, vg, hc, came, best);
-            X += bdx;
-            Y += bdy;
-            if (X >= nx) { X -= nx; ++Y; }
+            for (int u = 0; u < kEpiU; ++u) {
+              const int X = X0 + 32 * u;
+              if (X < nx)
+                epilogue_cell_loaded(X, Y, row + X, v[u], h[u], g0[u], cf[u], sx, sy, ex, ey, thr, scale, nb,
+                                     ls, vg, hc, came, best);
+            }
           }
         }
       }
@@ -190,8 +192,13 @@ __global__ void __launch_bounds__(NWK * 32, MINB) planner_kernel(const PlannerPa
     }
   }
 
-  if (nb == 0) // no sweep ran: visibility_ keeps the zeros of reset() (:43)
-    for (size_t c = tid; c < cells; c += blockDim.x) vis[c] = 0.0;
+  if (nb == 0) { // no sweep ran: the fields keep the state of reset() (:42-60, :122)
+    for (size_t c = tid; c < cells; c += blockDim.x) {
+      vis[c] = 0.0;
+      vg[c] = 0.0;
+      came[c] = (status == VHP_OK && c == (size_t)sty * nx + stx) ? 0 : VHP_NO_PARENT;
+    }
+  }
   if (tid == 0) {
     p.status[q] = status;
     p.nb[q] = nb;
@@ -368,7 +375,7 @@ cudaError_t vhp_launch_planner(const VhpTilePlanes &pl, int nx, int ny, const in
     return e ? std::atoi(e) : 0;
   }();
   int nw = 8; // measured on the 1024 x 256^2 batch: 8 warps 240k solves/s, 4 warps 206k, 2 warps slower still
-  if (forced == 2 || forced == 4 || forced == 8) nw = forced;
+  if (forced == 2 || forced == 4 || forced == 8 || forced == 12 || forced == 16) nw = forced;
   auto go = [&](auto kern, int nwarps) -> cudaError_t {
     const size_t smem = tile_smem_bytes<double>(nx, ny, nwarps);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -379,5 +386,7 @@ cudaError_t vhp_launch_planner(const VhpTilePlanes &pl, int nx, int ny, const in
   };
   if (nw == 2) return go(planner_kernel<2>, 2);
   if (nw == 4) return go(planner_kernel<4>, 4);
+  if (nw == 12) return go(planner_kernel<12, 2>, 12);  // 2 CTAs per SM: <= 80 registers
+  if (nw == 16) return go(planner_kernel<16, 2>, 16);  // 2 CTAs per SM: 64 registers
   return go(planner_kernel<8, 2>, 8);               // 2 CTAs per SM (<= 128 registers)
 }

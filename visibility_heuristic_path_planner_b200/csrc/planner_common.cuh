@@ -72,6 +72,44 @@ __device__ __forceinline__ void epilogue_cell_loaded(const int X, const int Y, c
   }
 }
 
+// The same cell in the FIRST sweep of a problem (nb == 0), where the fields still hold whatever
+// the workspace held: nothing is loaded -- vg is 0, the cached heuristic +inf and the parent
+// "none" (0 at the start cell, :122) after reset() :42-60 -- and all three are stored for every
+// cell, the never-visited border included.  This replaces a reset pass over the fields and the
+// first sweep's loads of them (a problem runs 1.8 sweeps on average in the batch of bench.py).
+__device__ __forceinline__ void epilogue_cell_first(const int X, const int Y, const size_t c,
+                                                    const double v, const int sx, const int sy,
+                                                    const int ex, const int ey, const double thr,
+                                                    const double scale, const int32_t *__restrict__ ls,
+                                                    double *vg, double *hc, int32_t *came, Best &best) {
+  int cf = (X == sx && Y == sy) ? 0 : VHP_NO_PARENT; // the first source is the start cell
+  double h = __longlong_as_double((long long)kHInf), g = 0.0;
+  const bool visited = !((X == 0 && sx > 0) || (Y == 0 && sy > 0));
+  if (visited && (v > 0.0 || thr <= 0.0)) {
+    g = v > 0.0 ? v : 0.0; // std::max(v, 0)
+    if (v >= thr && cf == VHP_NO_PARENT) cf = 0;
+    if (cf != VHP_NO_PARENT) {
+      const int px = __ldcg(ls), py = __ldcg(ls + 1);
+      h = __dadd_rn(__dmul_rn(scale, g), __dadd_rn(eval_d(X, Y, ex, ey), eval_d(X, Y, px, py)));
+    }
+  }
+  vg[c] = g;
+  came[c] = cf;
+  hc[c] = h;
+  if (!visited) return;
+  const unsigned long long hb = (unsigned long long)__double_as_longlong(h);
+  if (hb <= best.h && hb != kHInf) {
+    const int dx = X - sx, dy = Y - sy;
+    unsigned long long qd, i, j;
+    if (dx >= 0 && dy >= 0) { qd = 0; i = dx; j = dy; }
+    else if (dx < 0 && dy >= 0) { qd = 1; i = -dx; j = dy; }
+    else if (dx <= 0 && (dx < 0 || sx >= 1)) { qd = 2; i = -dx; j = -dy; }
+    else { qd = 3; i = dx; j = -dy; }
+    const Best cand{hb, (qd << 40) | (i << 20) | j};
+    if (better(cand, best)) best = cand;
+  }
+}
+
 __device__ __forceinline__ void epilogue_cell(const int X, const int Y, const size_t c, const int sx,
                                               const int sy, const int ex, const int ey,
                                               const double thr, const double scale, const int nb,
