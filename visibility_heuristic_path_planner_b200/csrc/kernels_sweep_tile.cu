@@ -191,7 +191,10 @@ int tile_warps_for(int nx, int ny, int64_t npairs) {
       forced == 16)
     return forced;
   if (std::max(nx, ny) > 512) return 8;
-  return npairs >= 148 * 16 ? 1 : 4; // enough pairs to fill the SMs with single-warp CTAs?
+  // a handful of small sweeps is a latency problem: 8 warps finish one 101 x 101 sweep in 20-25 us,
+  // 4 warps in 29-33 us (tools/c1_probe.py); enough pairs fill the SMs with single-warp CTAs
+  if (npairs <= 148 * 2) return 8;
+  return npairs >= 148 * 16 ? 1 : 4;
 }
 
 template <typename OutT>
