@@ -126,6 +126,39 @@ vhp_status vhp_visibility_batch_bin_dev(vhp_context *ctx, const uint8_t *d_occ, 
                                         int nx, int ny, const int32_t *d_src_xy,
                                         const int32_t *d_src_map, int64_t npairs,
                                         double threshold, uint32_t *d_out_bits);
+/* ---- opt-in variants of the sweep: the paper's MATLAB algorithm and the reference's
+ * early-terminating queue variant.  Same layouts as vhp_visibility_batch.
+ *   VHP_VARIANT_MATLAB  getAccessibilityMap.m (MATLAB_code/visibility/getAccessibilityMap.m:1-118):
+ *       every cell v = alpha * (a - c*(a - b)) * occ with c = (j*fac)/i for i > j*fac, i/(j*fac) for
+ *       j*fac > i, v = alpha * q(i-1, j-1) * occ where i == j*fac; the source holds
+ *       light_strength * occ; every cell of the grid is computed (no never-written border).
+ *       alpha = fac = light_strength = 1 is the reference's sweep with the diagonal taken from
+ *       (i-1, j-1) -- what MATLAB and computeVisibilityUsingQueue (:750-751) do -- instead of the
+ *       C++ sweep's (i, j-1).
+ *   VHP_VARIANT_QUEUE   computeVisibilityUsingQueue() (src/visibilityBasedSolver.cpp:701-893, the
+ *       variant README.md:13 recommends for dense maps) as an order-free rule: a free cell is
+ *       computed iff a cell that pushes it holds more than `cutoff` (0.001 in the reference) or it
+ *       touches the source; all other cells are 0; diagonal from (i-1, j-1); the source holds 1
+ *       whatever its occupancy.  The reference's function is a FIFO search whose result depends
+ *       on the queue order where a cell is reached before one of its upstream neighbours; this
+ *       entry computes what the search computes when every upstream cell is visited first and is
+ *       bit-identical to the compiled reference wherever that holds (about three maps in four of
+ *       the random test family, tests/test_oracle_golden.py).
+ * alpha, fac and light_strength are ignored by VHP_VARIANT_QUEUE, cutoff by VHP_VARIANT_MATLAB. */
+typedef enum vhp_variant_model { VHP_VARIANT_MATLAB = 1, VHP_VARIANT_QUEUE = 2 } vhp_variant_model;
+typedef struct vhp_sweep_variant {
+  int32_t model;
+  double alpha, fac, light_strength, cutoff;
+} vhp_sweep_variant;
+vhp_status vhp_visibility_variant_batch(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx,
+                                        int ny, const int32_t *src_xy, const int32_t *src_map,
+                                        int64_t npairs, const vhp_sweep_variant *variant,
+                                        vhp_dtype dtype, void *out);
+vhp_status vhp_visibility_variant_batch_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps,
+                                            int nx, int ny, const int32_t *d_src_xy,
+                                            const int32_t *d_src_map, int64_t npairs,
+                                            const vhp_sweep_variant *variant, vhp_dtype dtype,
+                                            void *d_out);
 /* Optional, for repeated _dev calls on the same maps: packs the maps into the
  * bit-plane layout the sweep kernel reads (row- and column-major bit maps, forward
  * and mirrored, plus a free-block summary) once, so later vhp_visibility_batch_dev calls with the same d_occ pointer,

@@ -106,6 +106,28 @@ class _Base:
 
 
 class Oracle(_Base):
+    def accessibility_map(self, occ, sx, sy, alpha=1.0, fac=1.0, light_strength=1.0):
+        """getAccessibilityMap.m restated (unpinned: MATLAB cannot run here)."""
+        occ = _f64(occ)
+        ny, nx = occ.shape
+        vis = np.zeros((ny, nx))
+        f = self.lib.vhp_oracle_accessibility_map
+        f.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _dp]
+        f.restype = None
+        f(occ, nx, ny, int(sx), int(sy), float(alpha), float(fac), float(light_strength), vis)
+        return vis
+
+    def visibility_cutoff(self, occ, sx, sy, cutoff=0.001):
+        """computeVisibilityUsingQueue() as an order-free rule (vhp_oracle.h)."""
+        occ = _f64(occ)
+        ny, nx = occ.shape
+        vis = np.zeros((ny, nx))
+        f = self.lib.vhp_oracle_visibility_cutoff
+        f.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _dp]
+        f.restype = None
+        f(occ, nx, ny, int(sx), int(sy), float(cutoff), vis)
+        return vis
+
     prefix = "vhp_oracle_"
 
     def generate_environment_counter(self, nx, ny, nb_of_obstacles, min_w, max_w, min_h, max_h,
@@ -168,6 +190,17 @@ class Oracle(_Base):
 
 class Ref(_Base):
     prefix = "ref_"
+
+    def compute_visibility_queue(self, occ, sx, sy, vis_init=None):
+        """computeVisibilityUsingQueue() (:701-893) of the compiled reference."""
+        occ = _f64(occ)
+        ny, nx = occ.shape
+        vis = np.zeros((ny, nx)) if vis_init is None else _f64(vis_init).copy()
+        f = self.lib.ref_compute_visibility_queue
+        f.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp]
+        f.restype = None
+        f(occ, nx, ny, int(sx), int(sy), vis)
+        return vis
 
     @staticmethod
     def path(kind="strict"):

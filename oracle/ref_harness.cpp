@@ -133,6 +133,22 @@ void ref_compute_visibility(const double *occ, int nx, int ny, int sx, int sy,
   std::memcpy(vis, s.visibility_.data_.get(), n * sizeof(double));
 }
 
+// computeVisibilityUsingQueue() (:701-893, the early-terminating BFS variant the README
+// recommends for dense maps; its only call site :219 is commented out) on a caller-provided
+// (in/out) visibility_ field.
+void ref_compute_visibility_queue(const double *occ, int nx, int ny, int sx, int sy,
+                                  double *vis) {
+  vbs::Config c = makeConfig(nx, ny);
+  vbs::environment env(c);
+  loadOccupancy(env, occ, nx, ny);
+  vbs::visibilityBasedSolver s(env);
+  const std::size_t n = static_cast<std::size_t>(nx) * ny;
+  std::memcpy(s.visibility_.data_.get(), vis, n * sizeof(double));
+  s.ls_ = {sx, sy};
+  s.computeVisibilityUsingQueue();
+  std::memcpy(vis, s.visibility_.data_.get(), n * sizeof(double));
+}
+
 // resetQueue() + updateVisibility() + heap_->top() on caller-provided state.
 long ref_update_visibility(const double *occ, int nx, int ny, int sx, int sy,
                            int ex, int ey, double thr, double *vis, double *vg,

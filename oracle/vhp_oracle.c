@@ -325,3 +325,98 @@ void vhp_oracle_generate_environment_counter(double *occ, int nx, int ny,
       for (long y = row_1; y < row_2; ++y) occ[IDX(x, y)] = 0.0;
   }
 }
+
+
+/* ---- variants ------------------------------------------------------------------------------ */
+
+/* getAccessibilityMap.m:10-117, one quadrant (dx, dy = +-1); i outer, j inner as in the .m file */
+static void accessibility_quadrant(const double *occ, int nx, int ny, int sx, int sy, int dx,
+                                   int dy, double alpha, double fac, double ls, double *vis) {
+  const int Ex = dx > 0 ? nx - 1 - sx : sx, Ey = dy > 0 ? ny - 1 - sy : sy;
+  for (int i = 0; i <= Ex; ++i) {
+    const int X = sx + dx * i;
+    for (int j = 0; j <= Ey; ++j) {
+      const int Y = sy + dy * j;
+      const size_t c0 = (size_t)X + (size_t)Y * nx;
+      double v;
+      const double jf = (double)j * fac;
+      if (i == 0 && j == 0) {
+        v = ls;
+      } else if (i == 0) {
+        v = alpha * vis[(size_t)X + (size_t)(Y - dy) * nx];
+      } else if (j == 0) {
+        v = alpha * vis[(size_t)(X - dx) + (size_t)Y * nx];
+      } else if ((double)i == jf) {
+        v = alpha * vis[(size_t)(X - dx) + (size_t)(Y - dy) * nx];
+      } else if ((double)i > jf) {
+        const double c = jf / (double)i;
+        const double a = vis[(size_t)(X - dx) + (size_t)Y * nx];
+        const double b = vis[(size_t)(X - dx) + (size_t)(Y - dy) * nx];
+        const double f = a - c * (a - b);
+        v = alpha * f;
+      } else {
+        const double c = (double)i / jf;
+        const double a = vis[(size_t)X + (size_t)(Y - dy) * nx];
+        const double b = vis[(size_t)(X - dx) + (size_t)(Y - dy) * nx];
+        const double f = a - c * (a - b);
+        v = alpha * f;
+      }
+      vis[c0] = v * occ[c0];
+    }
+  }
+}
+
+void vhp_oracle_accessibility_map(const double *occ, int nx, int ny, int sx, int sy,
+                                  double alpha, double fac, double light_strength,
+                                  double *vis) {
+  for (size_t c = 0; c < (size_t)nx * ny; ++c) vis[c] = 0.0;
+  accessibility_quadrant(occ, nx, ny, sx, sy, 1, 1, alpha, fac, light_strength, vis);   /* %% 1 */
+  accessibility_quadrant(occ, nx, ny, sx, sy, -1, 1, alpha, fac, light_strength, vis);  /* %% 2 */
+  accessibility_quadrant(occ, nx, ny, sx, sy, -1, -1, alpha, fac, light_strength, vis); /* %% 3 */
+  accessibility_quadrant(occ, nx, ny, sx, sy, 1, -1, alpha, fac, light_strength, vis);  /* %% 4 */
+}
+
+/* computeVisibilityUsingQueue() as an order-free rule, see vhp_oracle.h.  Anti-diagonal order
+ * d = i + j: every cell a cell depends on (values and pushers) has a smaller d; the quadrants
+ * advance together because the axis cells belong to one quadrant each (dx >= 0 / dy >= 0 in the
+ * reference's tests :738, :777, :816, :855) and are read by its neighbour. */
+void vhp_oracle_visibility_cutoff(const double *occ, int nx, int ny, int sx, int sy,
+                                  double cutoff, double *vis) {
+  static const int qdx[4] = {1, -1, -1, 1}, qdy[4] = {1, 1, -1, -1};
+  for (size_t c = 0; c < (size_t)nx * ny; ++c) vis[c] = 0.0;
+  vis[(size_t)sx + (size_t)sy * nx] = 1.0; /* lightStrength_, :707 */
+  for (int d = 1; d <= nx + ny; ++d) {
+    for (int q = 0; q < 4; ++q) {
+      const int dx = qdx[q], dy = qdy[q];
+      const int Ex = dx > 0 ? nx - 1 - sx : sx, Ey = dy > 0 ? ny - 1 - sy : sy;
+      for (int i = (d > Ey ? d - Ey : 0); i <= Ex && i <= d; ++i) {
+        const int j = d - i;
+        if ((i == 0 && dx < 0) || (j == 0 && dy < 0)) continue; /* the axis belongs to the + side */
+        const int X = sx + dx * i, Y = sy + dy * j;
+        const size_t c0 = (size_t)X + (size_t)Y * nx;
+        if (occ[c0] == 0.0) continue; /* :732-734 */
+#define VAT(a, b) vis[(size_t)(sx + dx * (a)) + (size_t)(sy + dy * (b)) * nx]
+        int pushed = (i <= 1 && j <= 1); /* the eight neighbours of the source, :709-716 */
+        if (!pushed && i - 1 >= 1 && VAT(i - 1, j) > cutoff) pushed = 1;
+        if (!pushed && j - 1 >= 1 && VAT(i, j - 1) > cutoff) pushed = 1;
+        if (!pushed && i == j && VAT(i - 1, j - 1) > cutoff) pushed = 1;
+        if (!pushed) continue;
+        double v;
+        if (i == 0) v = VAT(0, j - 1);
+        else if (j == 0) v = VAT(i - 1, 0);
+        else if (i == j) v = VAT(i - 1, j - 1);
+        else if (i > j) {
+          const double c = (double)j / (double)i;
+          const double a = VAT(i - 1, j), b = VAT(i - 1, j - 1);
+          v = a - c * (a - b);
+        } else {
+          const double c = (double)i / (double)j;
+          const double a = VAT(i, j - 1), b = VAT(i - 1, j - 1);
+          v = a - c * (a - b);
+        }
+#undef VAT
+        vis[c0] = v * occ[c0];
+      }
+    }
+  }
+}

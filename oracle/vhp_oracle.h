@@ -106,6 +106,38 @@ void vhp_oracle_generate_environment_counter(double *occ, int nx, int ny,
                                              unsigned long long seed,
                                              unsigned long long map);
 
+/* ---- variants of the sweep --------------------------------------
+ *
+ * getAccessibilityMap.m (MATLAB_code/visibility/getAccessibilityMap.m:1-118), the paper's
+ * Algorithm 1: every cell of the grid is computed (no never-written border), the diagonal
+ * branch `i == j*fac` takes the value of (i-1, j-1), `alpha` multiplies every cell (decay) and
+ * `fac` bends the octant boundary (c = (j*fac)/i for i > j*fac, i/(j*fac) for j*fac > i).
+ * 0-based restatement; `vis` must hold nx*ny doubles and is completely overwritten.
+ * Parity status of THIS function: UNPINNED -- MATLAB / Octave cannot run in the build
+ * container, so it is checked only against its own reading of the .m file (and, for
+ * alpha = fac = 1, against the reference's C++ sweep away from the diagonal and the border). */
+void vhp_oracle_accessibility_map(const double *occ, int nx, int ny, int sx, int sy,
+                                  double alpha, double fac, double light_strength,
+                                  double *vis);
+
+/* computeVisibilityUsingQueue(), visibilityBasedSolver.cpp:701-893, as an ORDER-FREE rule:
+ *   - the source holds lightStrength_ = 1 whatever its occupancy (:707);
+ *   - a free cell is computed iff a cell that pushes it holds a value > cutoff (0.001 in the
+ *     reference) -- its neighbour (i-1, j) unless that lies on the i == 0 axis, (i, j-1) unless
+ *     that lies on the j == 0 axis, (i-1, j-1) for diagonal cells -- or it is one of the eight
+ *     neighbours of the source (:709-716); every other cell keeps 0;
+ *   - the value is the DP value of computeVisibility with the diagonal taken from (i-1, j-1)
+ *     (:750-751) and no never-written border, upstream cells that were not computed reading 0.
+ * The reference's function is a FIFO breadth-first search: a cell is computed when it is first
+ * popped, from whatever its upstream neighbours hold AT THAT MOMENT.  Where an upstream
+ * neighbour is itself reached only by a detour it may still be unvisited (0) then, so the
+ * reference's output depends on the queue order; this rule is what the search computes when
+ * every upstream cell is visited first, and equals it bit for bit on maps where the order does
+ * not matter (tests/test_oracle_golden.py states how often, and pins the rule to the compiled
+ * reference there).  `vis` is completely overwritten. */
+void vhp_oracle_visibility_cutoff(const double *occ, int nx, int ny, int sx, int sy,
+                                  double cutoff, double *vis);
+
 /* eval_d(), include/solver/visibilityBasedSolver.h:112-115 */
 double vhp_oracle_eval_d(int sx, int sy, int tx, int ty);
 

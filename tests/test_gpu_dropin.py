@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import ROOT, load_golden
+from conftest import ROOT, load_golden, rect_map
 
 pytestmark = pytest.mark.gpu
 CLI = os.path.join(ROOT, "visibility_heuristic_path_planner_b200", "bin", "visibility_heuristic_planner")
@@ -194,3 +194,47 @@ def test_device_environment_batch_matches_oracle(oracle):
     for k in (0, 7):
         assert np.array_equal(out[k].cpu().numpy(), oracle.compute_visibility(occ[k].astype(np.float64), 5, 5))
     ctx.close()
+
+
+def test_benchmark_series_file(tmp_path, capfd):
+    """benchmarkSeries() (:295-374): the first sizes of the 60 log-spaced grids 50 ... 5000, one
+    un-warmed sweep and one all-targets ray casting each, appended to output/benchmark_results.txt
+    as `t_vis_us t_ray_us ratio NxN` (the format of the reference's :368-373)."""
+    import ctypes as C
+    import visibility_heuristic_path_planner_b200 as vhp
+    lib = vhp.load_library()
+    cfg = vhp.Config()
+    lib.vhp_config_default(C.byref(cfg))
+    cfg.ncols = cfg.nrows = 64
+    cfg.start_x = cfg.start_y = 5
+    cfg.end_x = cfg.end_y = 60
+    cfg.silent, cfg.save_results = 1, 0
+    ctx = vhp.Context(0)
+    h = C.c_void_p()
+    occ8 = np.ones((64, 64), np.uint8)
+    lib.vhp_solver_create.argtypes = [C.c_void_p, C.POINTER(vhp.Config), C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    assert lib.vhp_solver_create(ctx.h, C.byref(cfg), occ8.ctypes.data, 64, 64, C.byref(h)) == 0
+    lib.vhp_solver_benchmark_series.argtypes = [C.c_void_p, C.c_int]
+    cwd = os.getcwd(); os.chdir(tmp_path)
+    try:
+        assert lib.vhp_solver_benchmark_series(h, 14) == 0
+        assert lib.vhp_solver_benchmark_series(h, 3) == 0      # appends
+    finally:
+        os.chdir(cwd)
+    lib.vhp_solver_destroy.argtypes = [C.c_void_p]
+    lib.vhp_solver_destroy(h)
+    # a sweep after the series still sees its own map (the series' temporary maps are released)
+    occ = rect_map(70, 60, 10, 3)
+    from oracle_py import Oracle
+    assert np.array_equal(ctx.visibility_batch(occ, [(9, 9)])[0], Oracle().compute_visibility(occ, 9, 9))
+    ctx.close()
+    lines = open(tmp_path / "output" / "benchmark_results.txt").read().splitlines()
+    assert len(lines) == 17
+    sizes = [int(round(50 * np.exp(np.log(100) * i / 59))) for i in range(60)]   # :311-315
+    for k, line in enumerate(lines):
+        tv, tr, ratio, dims = line.split()
+        n = sizes[k if k < 14 else k - 14]
+        assert dims == f"{n}x{n}" and float(tv) > 0 and float(tr) > 0
+        assert abs(float(ratio) - float(tr) / float(tv)) <= 1e-3 * float(ratio)
+    out = capfd.readouterr().out
+    assert "For grid size: 50x50" in out and "Ratios:" in out

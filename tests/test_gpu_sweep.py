@@ -243,3 +243,45 @@ def test_binary_visibility_bit_exact(ctx, vhp, oracle):
     occ = oracle.generate_environment(101, 101, 10, 10, 20, 10, 20, seed)
     bits = vhp.unpack_bits(ctx.visibility_batch_bin(occ, [(50, 50)], 0.5), 101)[0]
     assert not bits[y, x] and oracle.compute_visibility(occ, 50, 50)[y, x] < 0.5
+
+
+def test_sweep_variants_equal_oracle(vhp, oracle):
+    """vhp_visibility_variant_batch: getAccessibilityMap.m (alpha decay, fac curve factor) and the
+    early-terminating computeVisibilityUsingQueue rule, bit-exact against their C restatements."""
+    c = vhp.Context(0)
+    rng = np.random.default_rng(21)
+    for nx, ny, nobs, seed in ((64, 48, 12, 3), (101, 101, 25, 7), (33, 77, 8, 9), (260, 130, 40, 2)):
+        occ = np.stack([rect_map(nx, ny, nobs, seed + k, 2, 11) for k in range(2)])
+        n = 6
+        smap = rng.integers(0, 2, n).astype(np.int32)
+        src = np.stack([rng.integers(0, nx, n), rng.integers(0, ny, n)], 1).astype(np.int32)
+        src[0] = (0, 0); src[1] = (nx - 1, ny - 1); src[2] = (nx // 2, 0)
+        for alpha, fac, ls in ((1.0, 1.0, 1.0), (0.97, 1.0, 1.0), (1.0, 0.5, 1.0), (0.999, 2.0, 0.5), (1.0, 1.3, 1.0)):
+            out = c.visibility_variant_batch(occ, src, vhp.VARIANT_MATLAB, alpha=alpha, fac=fac,
+                                             light_strength=ls, src_map=smap)
+            for k in range(n):
+                ref = oracle.accessibility_map(occ[smap[k]], *src[k], alpha=alpha, fac=fac, light_strength=ls)
+                assert np.array_equal(out[k], ref), (nx, ny, alpha, fac, k)
+        for cutoff in (0.001, 0.0, 0.05):
+            out = c.visibility_variant_batch(occ, src, vhp.VARIANT_QUEUE, cutoff=cutoff, src_map=smap)
+            out32 = c.visibility_variant_batch(occ, src, vhp.VARIANT_QUEUE, cutoff=cutoff, src_map=smap, dtype=vhp.F32)
+            for k in range(n):
+                ref = oracle.visibility_cutoff(occ[smap[k]], *src[k], cutoff=cutoff)
+                assert np.array_equal(out[k], ref), (nx, ny, cutoff, k)
+                assert np.array_equal(out32[k], ref.astype(np.float32))
+    # the reference's own output (golden fixture) where its queue order does not matter
+    g = load_golden("queue.npz")
+    done = 0
+    for row in g["cases"][:40]:
+        t, nx, ny, nobs, sx, sy = (int(v) for v in row[:6])
+        if not g["agree"][t]:
+            continue
+        out = c.visibility_variant_batch(rect_map(nx, ny, nobs, t, 1, 9), [(sx, sy)], vhp.VARIANT_QUEUE)[0]
+        assert np.array_equal(out, g[f"ref_{t}"]), t
+        done += 1
+    assert done >= 25
+    with pytest.raises(vhp.VhpError):
+        c.visibility_variant_batch(occ, src, 3)
+    with pytest.raises(vhp.VhpError):
+        c.visibility_variant_batch(occ, src, vhp.VARIANT_MATLAB, fac=0.0)
+    c.close()

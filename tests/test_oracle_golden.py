@@ -180,3 +180,79 @@ def test_counter_environment_generator(oracle):
             c1, c2, r1, r2 = min(c1, nx - 1), min(c2, nx - 1), min(r1, ny - 1), min(r2, ny - 1)
             occ[r1:r2, c1:c2] = 0
         assert np.array_equal(occ, oracle.generate_environment_counter(nx, ny, nb, lw, hw, lh, hh, seed, m))
+
+
+# ---- sweep variants -----------------------------------------------------
+def _queue_family(n):
+    rng = np.random.default_rng(0)
+    for t in range(n):
+        nx, ny = int(rng.integers(8, 70)), int(rng.integers(8, 70))
+        nobs = int(rng.integers(0, 25))
+        sx, sy = int(rng.integers(0, nx)), int(rng.integers(0, ny))
+        yield t, nx, ny, nobs, sx, sy
+
+
+def test_queue_rule_against_reference_goldens(oracle):
+    """vhp_oracle_visibility_cutoff (the order-free statement of computeVisibilityUsingQueue,
+    :701-893) reproduces the compiled reference's FIFO search bit for bit on every case the
+    fixture marks "agree" (304 of 400 random maps); the others are the order-dependent ones."""
+    g = load_golden("queue.npz")
+    agree = g["agree"]
+    assert int(agree.sum()) == 304 and len(agree) == 400
+    checked = 0
+    for t, nx, ny, nobs, sx, sy in _queue_family(40):
+        row = g["cases"][t]
+        assert tuple(row[:6]) == (t, nx, ny, nobs, sx, sy)
+        mine = oracle.visibility_cutoff(rect_map(nx, ny, nobs, t, 1, 9), sx, sy)
+        ndiff = int((mine != g[f"ref_{t}"]).sum())
+        assert ndiff == int(row[6]) and (ndiff == 0) == bool(agree[t]), t
+        checked += bool(agree[t])
+    assert checked >= 25
+
+
+def test_queue_rule_against_live_reference(oracle, ref_strict):
+    g = load_golden("queue.npz")
+    for t, nx, ny, nobs, sx, sy in _queue_family(120):
+        occ = rect_map(nx, ny, nobs, t, 1, 9)
+        same = np.array_equal(oracle.visibility_cutoff(occ, sx, sy), ref_strict.compute_visibility_queue(occ, sx, sy))
+        assert same == bool(g["agree"][t]), t
+
+
+def test_queue_rule_properties(oracle):
+    # empty map: everything lit, border included (no never-written column / row in this variant)
+    assert (oracle.visibility_cutoff(np.ones((40, 57)), 20, 9) == 1.0).all()
+    # an occupied source still shines (:707 stores lightStrength_ unconditionally)
+    occ = np.ones((20, 20)); occ[5, 5] = 0
+    v = oracle.visibility_cutoff(occ, 5, 5)
+    assert v[5, 5] == 1.0 and (v == 1.0).all()
+    # cutoff 0 never terminates early: free cells follow the DP with the MATLAB diagonal
+    occ = rect_map(50, 44, 9, 3, 2, 7)
+    a = oracle.visibility_cutoff(occ, 10, 12, cutoff=0.0)
+    b = oracle.accessibility_map(occ, 10, 12)
+    lit = a > 0
+    assert np.array_equal(a[lit], b[lit])
+    # the early termination only removes light: cutoff 0.001 <= cutoff 0 everywhere
+    assert (oracle.visibility_cutoff(occ, 10, 12) <= a).all()
+
+
+def test_accessibility_map_properties(oracle):
+    """getAccessibilityMap.m restated (UNPINNED: no MATLAB here) -- properties that follow from
+    the .m file alone."""
+    # empty map, fac = 1: v = alpha^max(|dx|, |dy|) as the running product alpha * alpha * ...
+    nx, ny, sx, sy, alpha = 37, 29, 11, 20, 0.93
+    v = oracle.accessibility_map(np.ones((ny, nx)), sx, sy, alpha=alpha)
+    pw = np.multiply.accumulate(np.concatenate([[1.0], np.full(40, alpha)]))
+    yy, xx = np.mgrid[0:ny, 0:nx]
+    assert np.array_equal(v, pw[np.maximum(np.abs(xx - sx), np.abs(yy - sy))])
+    # alpha = fac = 1 with obstacles: equal to the C++ sweep wherever no diagonal cell and no
+    # never-written border cell lies upstream -- in particular on the two axes through the source
+    occ = rect_map(60, 50, 12, 5, 3, 8)
+    occ[25, :] = 1; occ[:, 30] = 1
+    m, c = oracle.accessibility_map(occ, 30, 25), oracle.compute_visibility(occ, 30, 25)
+    assert np.array_equal(m[25, 1:], c[25, 1:]) and np.array_equal(m[1:, 30], c[1:, 30])
+    assert m[25, 0] == 1.0 and c[25, 0] == 0.0  # MATLAB's loops reach the border, the C++ port's do not
+    # light strength scales linearly (power of two: exact), occupied cells are 0 for any fac
+    for fac in (0.5, 1.0, 1.7, 3.0):
+        a1 = oracle.accessibility_map(occ, 7, 9, alpha=0.99, fac=fac)
+        a2 = oracle.accessibility_map(occ, 7, 9, alpha=0.99, fac=fac, light_strength=0.5)
+        assert np.array_equal(a2, 0.5 * a1) and not a1[occ == 0].any() and a1.max() <= 1.0

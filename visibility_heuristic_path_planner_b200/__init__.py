@@ -42,6 +42,16 @@ class PlannerOut(C.Structure):
                 ("came", C.c_void_p), ("vis", C.c_void_p)]
 
 
+class SweepVariant(C.Structure):
+    """struct vhp_sweep_variant: model 1 = getAccessibilityMap.m (alpha, fac, light_strength),
+    model 2 = computeVisibilityUsingQueue as an order-free rule (cutoff)."""
+    _fields_ = [("model", C.c_int32), ("alpha", C.c_double), ("fac", C.c_double),
+                ("light_strength", C.c_double), ("cutoff", C.c_double)]
+
+
+VARIANT_MATLAB, VARIANT_QUEUE = 1, 2
+
+
 class Config(C.Structure):
     """struct vhp_config (mirror of the reference's struct Config)."""
     _fields_ = [("mode", C.c_int32), ("ncols", C.c_int64), ("nrows", C.c_int64),
@@ -91,6 +101,8 @@ def load_library(build_if_missing: bool = True):
         getattr(lib, name).argtypes = batch
     lib.vhp_visibility_batch_bin.argtypes = [vp, vp, i32, i32, i32, vp, vp, i64, C.c_double, vp]
     lib.vhp_visibility_batch_bin_dev.argtypes = [vp, vp, i32, i32, i32, vp, vp, i64, C.c_double, vp]
+    lib.vhp_visibility_variant_batch.argtypes = [vp, vp, i32, i32, i32, vp, vp, i64, C.POINTER(SweepVariant), i32, vp]
+    lib.vhp_visibility_variant_batch_dev.argtypes = [vp, vp, i32, i32, i32, vp, vp, i64, C.POINTER(SweepVariant), i32, vp]
     lib.vhp_release_maps_dev.argtypes = [vp]
     lib.vhp_context_device.argtypes = [vp]
     lib.vhp_prepare_maps_dev.argtypes = [vp, vp, i32, i32, i32]
@@ -254,6 +266,17 @@ class Context:
             self.h, occ_t.data_ptr(), nmaps, nx, ny, src_xy_t.data_ptr(),
             None if src_map_t is None else src_map_t.data_ptr(), src_xy_t.shape[0], float(threshold),
             out_bits_t.data_ptr()))
+
+    def visibility_variant_batch(self, occ, src_xy, model, alpha=1.0, fac=1.0, light_strength=1.0,
+                                 cutoff=0.001, src_map=None, dtype=F64):
+        """Opt-in sweep variants (vhp_visibility_variant_batch): VARIANT_MATLAB =
+        getAccessibilityMap.m with decay alpha / curve factor fac, VARIANT_QUEUE = the
+        early-terminating computeVisibilityUsingQueue rule."""
+        var = SweepVariant(int(model), float(alpha), float(fac), float(light_strength), float(cutoff))
+
+        def fn(h, occ_p, nmaps, nx, ny, xy_p, mp_p, n, dt, out_p):
+            return self.lib.vhp_visibility_variant_batch(h, occ_p, nmaps, nx, ny, xy_p, mp_p, n, C.byref(var), dt, out_p)
+        return self._batch_host(fn, occ, src_xy, src_map, dtype, None)
 
     def raycast_batch(self, occ, src_xy, src_map=None, dtype=F64, out=None):
         return self._batch_host(self.lib.vhp_raycast_batch, occ, src_xy, src_map, dtype, out)

@@ -617,6 +617,34 @@ vhp_status run_bin_host(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx,
   return check_device_error(ctx);
 }
 
+// ---- opt-in sweep variants ------------------------------------------------------------------------
+vhp_status check_variant(vhp_context *ctx, const vhp_sweep_variant *v) {
+  if (!v) return fail(ctx, VHP_ERR_INVALID_ARG, "sweep variant: null descriptor");
+  if (v->model != VHP_VARIANT_MATLAB && v->model != VHP_VARIANT_QUEUE)
+    return fail(ctx, VHP_ERR_INVALID_ARG, "sweep variant: model is VHP_VARIANT_MATLAB or VHP_VARIANT_QUEUE");
+  if (v->model == VHP_VARIANT_MATLAB && !(v->fac > 0.0))
+    return fail(ctx, VHP_ERR_INVALID_ARG, "sweep variant: fac must be positive");
+  return VHP_OK;
+}
+
+vhp_status run_variant_dev(vhp_context *ctx, const uint8_t *d_occ, int nx, int ny, const int32_t *d_xy,
+                           const int32_t *d_map, int64_t n, const vhp_sweep_variant &v, vhp_dtype dtype,
+                           void *d_out) {
+  const size_t cells = (size_t)nx * ny;
+  const int64_t chunk = dtype == VHP_F64 ? n : bin_chunk_pairs(cells, n);
+  vhp_status st;
+  if (dtype == VHP_F32 && (st = ensure(ctx, ctx->b_bin, (size_t)chunk * cells * 8)) != VHP_OK) return st;
+  for (int64_t p0 = 0; p0 < n; p0 += chunk) {
+    const int64_t np = std::min(chunk, n - p0);
+    double *buf = dtype == VHP_F64 ? (double *)d_out + (size_t)p0 * cells : (double *)ctx->b_bin.p;
+    float *o32 = dtype == VHP_F32 ? (float *)d_out + (size_t)p0 * cells : nullptr;
+    VHP_CUDA(ctx, vhp_launch_sweep_variant(d_occ, nx, ny, d_xy + 2 * p0, d_map ? d_map + p0 : nullptr, np,
+                                           v.model, v.alpha, v.fac, v.light_strength, v.cutoff, buf, o32,
+                                           ctx->d_err, ctx->stream, &ctx->launches));
+  }
+  return VHP_OK;
+}
+
 // ---- planner ------------------------------------------------------------------
 // One LARGE problem on the whole GPU: solve() (src/visibilityBasedSolver.cpp:76-160) as the
 // one-strip case of the strip engine (giant.cu).  Per iteration: grid-mode sweep of the whole
@@ -901,6 +929,54 @@ vhp_status vhp_visibility_batch(vhp_context *ctx, const uint8_t *occ, int nmaps,
                                 const int32_t *src_xy, const int32_t *src_map, int64_t npairs,
                                 vhp_dtype dtype, void *out) {
   return run_host(ctx, Op::Sweep, occ, nmaps, nx, ny, src_xy, src_map, npairs, dtype, out);
+}
+
+vhp_status vhp_visibility_variant_batch_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx,
+                                            int ny, const int32_t *d_src_xy, const int32_t *d_src_map,
+                                            int64_t npairs, const vhp_sweep_variant *variant,
+                                            vhp_dtype dtype, void *d_out) {
+  vhp_status st = check_common(ctx, d_occ, nmaps, nx, ny, d_src_xy, npairs, dtype, d_out);
+  if (st != VHP_OK) return st;
+  if ((st = check_variant(ctx, variant)) != VHP_OK) return st;
+  VHP_ON_DEVICE(ctx);
+  if (npairs == 0) return VHP_OK;
+  return run_variant_dev(ctx, d_occ, nx, ny, d_src_xy, d_src_map, npairs, *variant, dtype, d_out);
+}
+
+vhp_status vhp_visibility_variant_batch(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx, int ny,
+                                        const int32_t *src_xy, const int32_t *src_map, int64_t npairs,
+                                        const vhp_sweep_variant *variant, vhp_dtype dtype, void *out) {
+  vhp_status st = check_common(ctx, occ, nmaps, nx, ny, src_xy, npairs, dtype, out);
+  if (st != VHP_OK) return st;
+  if ((st = check_variant(ctx, variant)) != VHP_OK) return st;
+  if ((st = check_points(ctx, src_xy, 2, src_map, npairs, nmaps, nx, ny, "vhp_visibility_variant_batch")) != VHP_OK)
+    return st;
+  if (npairs == 0) return VHP_OK;
+  VHP_ON_DEVICE(ctx);
+  const size_t cells = (size_t)nx * ny, esz = dtype == VHP_F32 ? 4 : 8, occ_bytes = (size_t)nmaps * cells;
+  if ((st = ensure(ctx, ctx->b_occ, occ_bytes)) != VHP_OK) return st;
+  if ((st = ensure(ctx, ctx->b_src, (size_t)npairs * 8)) != VHP_OK) return st;
+  if (src_map && (st = ensure(ctx, ctx->b_map, (size_t)npairs * 4)) != VHP_OK) return st;
+  VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_occ.p, occ, occ_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_src.p, src_xy, (size_t)npairs * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (src_map)
+    VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_map.p, src_map, (size_t)npairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->planes_sticky = false; // b_occ content changed
+  ctx->tile_src = nullptr;
+  // results leave in chunks of at most 1 GB through one device buffer
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(npairs, (int64_t)(((size_t)1 << 30) / (cells * esz))));
+  if ((st = ensure(ctx, ctx->b_out[0], (size_t)chunk * cells * esz)) != VHP_OK) return st;
+  for (int64_t p0 = 0; p0 < npairs; p0 += chunk) {
+    const int64_t np = std::min(chunk, npairs - p0);
+    st = run_variant_dev(ctx, (const uint8_t *)ctx->b_occ.p, nx, ny, (const int32_t *)ctx->b_src.p + 2 * p0,
+                         src_map ? (const int32_t *)ctx->b_map.p + p0 : nullptr, np, *variant, dtype,
+                         ctx->b_out[0].p);
+    if (st != VHP_OK) return st;
+    VHP_CUDA(ctx, cudaMemcpyAsync((char *)out + (size_t)p0 * cells * esz, ctx->b_out[0].p, (size_t)np * cells * esz,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    VHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return check_device_error(ctx);
 }
 
 vhp_status vhp_visibility_batch_bin(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx, int ny,

@@ -172,6 +172,13 @@ cudaError_t vhp_launch_sweep_tile(const VhpTilePlanes &pl, int nx, int ny, const
                                   void *d_out, const double *d_rcp2, int *d_err, cudaStream_t st,
                                   int64_t *launches);
 
+// opt-in sweep variants (kernels_sweep_variant.cu): model 1 getAccessibilityMap.m (alpha, fac),
+// model 2 computeVisibilityUsingQueue as an order-free rule (cutoff)
+cudaError_t vhp_launch_sweep_variant(const uint8_t *d_occ, int nx, int ny, const int32_t *d_src_xy,
+                                     const int32_t *d_src_map, int64_t npairs, int model, double alpha,
+                                     double fac, double light_strength, double cutoff, double *d_buf,
+                                     float *d_out32, int *d_err, cudaStream_t st, int64_t *launches);
+
 // giant-map path: one sweep of map 0 restricted to the rows [y0, y1) of a strip, and the
 // planner epilogue + arg-min over a strip (whole GPU)
 void vhp_window_halo_rows(int nx, int ny, int sx, int sy, int y0, int y1, int32_t rows[4]);
