@@ -303,7 +303,11 @@ vhp_status vhp_strip_epilogue_dev(vhp_context *ctx, int nx, int ny, int y0, int 
  * into world * strips_per_rank contiguous strips, rank r owns strips [r * spr, (r + 1) * spr).
  * Per planner iteration (updateVisibility :379-565 + the loop of solve() :127-140):
  *   - two chains of strip sweeps, the +y quadrants upwards and the -y quadrants downwards, on two
- *     streams; neighbours exchange 2 x nx doubles per chain with ncclSend / ncclRecv over NVLink;
+ *     streams.  With one strip per rank the ranks map each other's sweep workspaces (CUDA IPC) and
+ *     a boundary is handed over tile by tile by peer stores over NVLink from inside the sweep
+ *     kernel, so the strips of a chain run as one wavefront; otherwise (several strips per rank,
+ *     no peer mapping, env VHP_GIANT_P2P=0) neighbours exchange 2 x nx doubles per chain with
+ *     ncclSend / ncclRecv;
  *   - epilogue + arg-min per strip, ncclAllGather of 32 bytes per rank {h bits, push-order key,
  *     vg(end) bits}; every rank takes the lexicographic minimum = priority_queue::top()'s
  *     first-pushed tie-break and runs the loop control on the device.
@@ -336,6 +340,9 @@ typedef struct vhp_giant_stats {
   int64_t nccl_ops, nccl_ops_timed;
   int64_t halo_bytes_sent;  /* bytes this rank sent to its neighbours in the iterations that ran */
   int64_t launches;         /* kernels launched by the call */
+  int32_t peer_handover;    /* 1: strip boundaries travelled tile by tile through peer memory (NVLink
+                             * stores inside the sweep kernels), 0: as finished rows by ncclSend/Recv */
+  int32_t reserved;
 } vhp_giant_stats;
 vhp_status vhp_giant_unique_id(void *id);
 vhp_status vhp_giant_create(vhp_context *ctx, const uint8_t *occ, int nx, int ny, int rank,

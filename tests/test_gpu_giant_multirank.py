@@ -19,12 +19,14 @@ def _gpus():
     return torch.cuda.device_count()
 
 
-def _run(nproc, size, queries, spr=1, port=29541):
+def _run(nproc, size, queries, spr=1, port=29541, p2p=True):
+    env = dict(os.environ)
+    env["VHP_GIANT_P2P"] = "1" if p2p else "0"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tools", "giant_multi_gpu.py"), "--size", str(size), "--queries", str(queries),
            "--spr", str(spr), "--max-iter", "40"]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
     line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
     return json.loads(line)
@@ -33,10 +35,15 @@ def _run(nproc, size, queries, spr=1, port=29541):
 def test_two_ranks_equal_single_gpu():
     if _gpus() < 2:
         pytest.skip("needs >= 2 GPUs")
+    # strip boundaries tile by tile through peer memory (NVLink stores inside the sweep kernels)
     r = _run(2, 1536, 3)
     assert r["all_ranks_equal"] and all(q["equal_single_gpu"] for q in r["queries"])
-    assert all(q["halo_bytes_sent"] > 0 for q in r["queries"] if q["iterations"] > 0)
-    r = _run(2, 1024, 2, spr=3, port=29542)   # remote and local strip boundaries mixed
+    assert all(q["peer_handover"] == 1 for q in r["queries"])
+    # ... and as finished rows by ncclSend / ncclRecv
+    r = _run(2, 1536, 3, port=29544, p2p=False)
+    assert r["all_ranks_equal"] and all(q["equal_single_gpu"] for q in r["queries"])
+    assert all(q["peer_handover"] == 0 and q["halo_bytes_sent"] > 0 for q in r["queries"] if q["iterations"] > 0)
+    r = _run(2, 1024, 2, spr=3, port=29542)   # remote and local strip boundaries mixed (NCCL hand-over)
     assert r["all_ranks_equal"]
 
 
@@ -45,4 +52,6 @@ def test_all_gpus_equal_single_gpu():
     if n < 4:
         pytest.skip("needs >= 4 GPUs")
     r = _run(n, 4096, 2, port=29543)
+    assert r["all_ranks_equal"] and all(q["equal_single_gpu"] for q in r["queries"])
+    r = _run(n, 4096, 2, port=29545, p2p=False)
     assert r["all_ranks_equal"] and all(q["equal_single_gpu"] for q in r["queries"])

@@ -74,7 +74,8 @@ def main():
         rec = dict(start=start, end=end, status=r["status"], nb=r["nb_of_sources"], iterations=st["iterations"],
                    path_length=r["path_length"], ms=dt * 1e3, loop_ms=st["loop_ms"],
                    ms_per_iteration=st["loop_ms"] / max(1, st["iterations"]), nccl_ms=st["nccl_ms"],
-                   nccl_ops=st["nccl_ops"], halo_bytes_sent=st["halo_bytes_sent"], loop_mode=st["loop_mode"])
+                   nccl_ops=st["nccl_ops"], halo_bytes_sent=st["halo_bytes_sent"], loop_mode=st["loop_mode"],
+                   peer_handover=st["peer_handover"])
         if ref_ctx is not None:
             t0 = time.perf_counter()
             ref = ref_ctx.planner_batch(occ, [start + end], threshold=args.thr, max_iter=args.max_iter)

@@ -21,6 +21,14 @@
 //   * then the per-cell epilogue + arg-min per strip, an ncclAllGather of 32 bytes per rank
 //     {h bits, push-order key, vg(end) bits}, and the loop control of solve() on every rank.
 //
+// One strip per rank (the production layout): the ranks map each other's sweep workspaces
+// (cudaIpc*) and a strip boundary is handed over TILE BY TILE through peer memory: the warp that
+// finishes a tile of the row below the neighbour's first tile row stores its top row into the
+// neighbour's boundary row over NVLink and raises the neighbour's progress flag, so all strips
+// of a chain run as ONE wavefront, one tile apart, and the sweep's critical path is that of a
+// single GPU (sweep_tile_body.cuh, TileArgs::x_edges).  ncclSend / ncclRecv of finished rows
+// remains the fallback (several strips per rank, peer mapping unavailable, VHP_GIANT_P2P=0).
+//
 // No host round trip inside the loop.  One process: the iteration is captured once as the
 // body of a CUDA-graph WHILE node whose condition the step kernel sets.  Several ranks (NCCL
 // between the launches): the host enqueues iterations in batches and reads a 48-byte snapshot
@@ -69,6 +77,12 @@ struct vhp_giant {
   size_t h_out_cap = 0;
   const VhpNccl *nccl = nullptr;
   vhpNcclComm comm_up = nullptr, comm_dn = nullptr;
+  // peer hand-over of the strip boundaries (one strip per rank): both sweep workspaces in one
+  // IPC-shareable allocation; the neighbours' copies mapped into this process
+  bool p2p = false;
+  char *p2p_buf = nullptr;
+  size_t p2p_stride = 0;
+  void *peer_next = nullptr, *peer_prev = nullptr; // p2p_buf of rank + 1 / rank - 1
   // loop: 0 automatic (graph for one process, batches otherwise), 1 graph, 2 batches,
   // 3 one host read-back per iteration (the round-1 behaviour; kept for A/B measurements)
   int loop_mode = 0;
@@ -109,14 +123,21 @@ void strip_bounds(int ny, int nstrips, std::vector<int> &b) {
 
 double *halo_of(const vhp_giant *g, int s) { return g->halo + (size_t)s * 4 * g->nx; }
 
-vhp_status sweep_strip(vhp_giant *g, int s, int qmask, cudaStream_t st, void *ws) {
+vhp_status sweep_strip(vhp_giant *g, int s, int qmask, cudaStream_t st, void *ws,
+                       const VhpSweepPeer *peer = nullptr) {
   const GiantStripDev &sd = g->loc.s[s];
   const double *h[4];
-  for (int q = 0; q < 4; ++q) h[q] = halo_of(g, s) + (size_t)q * g->nx;
-  const int ctas = vhp_i_grid_ctas(g->ctx, g->nx, g->ny, sd.y1 - sd.y0);
+  for (int q = 0; q < 4; ++q) // (a boundary that arrives through peer memory has no halo row)
+    h[q] = (peer && ((peer->remote_mask >> q) & 1)) ? nullptr : halo_of(g, s) + (size_t)q * g->nx;
+  int ctas = vhp_i_grid_ctas(g->ctx, g->nx, g->ny, sd.y1 - sd.y0);
+  if (qmask == 0xF && ctas > 1) // all four quadrants in one launch: twice the warps of one chain's launch
+    ctas = std::min(2 * g->ctx->sm_count, 2 * ctas);
+  if (peer) // grid mode whatever the size, and at most one CTA per SM: the two chains' kernels must
+            // be resident together (each may be waiting for the other GPU's other chain)
+    ctas = std::max(2, std::min(g->ctx->sm_count, (4 * ((sd.y1 - sd.y0) / 32 + 2) + 7) / 8));
   GCUDA(g, vhp_launch_sweep_window(g->pl, g->nx, g->ny, 0, 0, sd.y0, sd.y1, h, VHP_F64, sd.vis,
                                    g->ctx->rcp2_table, g->ctx->d_err, ctas > 1 ? ws : nullptr, ctas, st,
-                                   &g->ctx->launches, qmask, g->ctl));
+                                   &g->ctx->launches, qmask, g->ctl, peer));
   return VHP_OK;
 }
 
@@ -140,6 +161,25 @@ vhp_status enqueue_iteration(vhp_giant *g, unsigned long long cond, int use_cond
   if (g->nstrips == 1) {
     // one strip: nothing to hand over, all four quadrants in one launch
     if ((st = sweep_strip(g, 0, 0xF, S, g->ws[0])) != VHP_OK) return st;
+  } else if (g->p2p) {
+    // one strip per rank, boundaries through peer memory: both chains start at once on every
+    // rank and synchronise tile by tile inside the kernels
+    const int k = g->k0;
+    size_t foff, fbytes;
+    vhp_sweep_grid_ws_flags(nx, ny, &foff, &fbytes);
+    GCUDA(g, cudaEventRecord(g->ev_fork, S));
+    GCUDA(g, cudaStreamWaitEvent(D, g->ev_fork, 0));
+    VhpSweepPeer up, dn;
+    if (k < last) { up.x_ws = (char *)g->peer_next; up.x_y0 = g->bounds[k + 1]; up.x_y1 = g->bounds[k + 2]; }
+    up.remote_mask = k > 0 ? 0x3 : 0;
+    if (k > 0) { dn.x_ws = (char *)g->peer_prev + g->p2p_stride; dn.x_y0 = g->bounds[k - 1]; dn.x_y1 = g->bounds[k]; }
+    dn.remote_mask = k < last ? 0xC : 0;
+    if ((st = sweep_strip(g, 0, 0x3, S, g->ws[0], &up)) != VHP_OK) return st;
+    GCUDA(g, cudaMemsetAsync((char *)g->ws[0] + foff, 0, fbytes, S)); // flags the neighbour raised
+    if ((st = sweep_strip(g, 0, 0xC, D, g->ws[1], &dn)) != VHP_OK) return st;
+    GCUDA(g, cudaMemsetAsync((char *)g->ws[1] + foff, 0, fbytes, D));
+    GCUDA(g, cudaEventRecord(g->ev_join, D));
+    GCUDA(g, cudaStreamWaitEvent(S, g->ev_join, 0));
   } else {
   GCUDA(g, cudaEventRecord(g->ev_fork, S));
   GCUDA(g, cudaStreamWaitEvent(D, g->ev_fork, 0));
@@ -338,7 +378,7 @@ vhp_status alloc_small(vhp_giant *g, int ls_cap) {
   GCUDA(g, cudaMemsetAsync(g->small_buf, 0, off, g->ctx->stream));
   char *b = g->small_buf;
   g->halo = (double *)(b + o_halo); g->send_up = (double *)(b + o_su); g->send_dn = (double *)(b + o_sd);
-  g->ws[0] = b + o_ws0; g->ws[1] = b + o_ws1;
+  if (!g->p2p) { g->ws[0] = b + o_ws0; g->ws[1] = b + o_ws1; }
   g->bests = (unsigned long long *)(b + o_bests); g->partial = (unsigned long long *)(b + o_part);
   g->key_send = (unsigned long long *)(b + o_ks); g->key_all = (unsigned long long *)(b + o_ka);
   g->ctl = (int *)(b + o_ctl);
@@ -367,12 +407,75 @@ vhp_status create_common(vhp_giant *g) {
   return VHP_OK;
 }
 
+// Map the neighbours' sweep workspaces (one strip per rank).  Every rank must take the same
+// decision, so the outcome is agreed with an all-reduce; on any failure all ranks keep the
+// ncclSend / ncclRecv hand-over.
+vhp_status setup_p2p(vhp_giant *g) {
+  g->p2p = false;
+  if (g->spr != 1) return VHP_OK;
+  if (const char *e = std::getenv("VHP_GIANT_P2P"))
+    if (std::atoi(e) == 0) return VHP_OK;
+  cudaStream_t S = g->ctx->stream;
+  const size_t stride = (vhp_sweep_grid_ws_bytes(g->nx, g->ny) + 4095) & ~(size_t)4095;
+  int ok = 1;
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  if (cudaMalloc(&g->p2p_buf, 2 * stride) != cudaSuccess || cudaMemset(g->p2p_buf, 0, 2 * stride) != cudaSuccess ||
+      cudaIpcGetMemHandle(&mine, g->p2p_buf) != cudaSuccess)
+    ok = 0;
+  (void)cudaGetLastError();
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  // all-gather of the handles and of the verdicts through device memory
+  char *d_x = nullptr;
+  const size_t xb = 64 + 64 * (size_t)g->world + 16;
+  GCUDA(g, cudaMalloc(&d_x, xb));
+  std::vector<char> h_all(64 * (size_t)g->world);
+  vhp_status st = VHP_OK;
+  auto fin = [&](vhp_status r) { cudaFree(d_x); return r; };
+  GCUDA(g, cudaMemcpyAsync(d_x, &mine, 64, cudaMemcpyHostToDevice, S));
+  { const int r = g->nccl->AllGather(d_x, d_x + 64, 8, kNcclUint64, g->comm_up, S);
+    if (r != 0) return fin(vhp_i_fail(g->ctx, VHP_ERR_CUDA, std::string("ncclAllGather: ") + g->nccl->GetErrorString(r))); }
+  GCUDA(g, cudaMemcpyAsync(h_all.data(), d_x + 64, h_all.size(), cudaMemcpyDeviceToHost, S));
+  GCUDA(g, cudaStreamSynchronize(S));
+  auto open_peer = [&](int r, void **out) {
+    if (!ok || r < 0 || r >= g->world) return;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, h_all.data() + 64 * (size_t)r, 64);
+    if (cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      *out = nullptr;
+      ok = 0;
+      (void)cudaGetLastError();
+    }
+  };
+  open_peer(g->rank + 1, &g->peer_next);
+  open_peer(g->rank - 1, &g->peer_prev);
+  // agree: min over the ranks of "everything worked here"
+  int *d_ok = reinterpret_cast<int *>(d_x + 64 + 64 * (size_t)g->world);
+  int neg = ok ? 0 : 1; // all-reduce (max) of the failure flags
+  GCUDA(g, cudaMemcpyAsync(d_ok, &neg, sizeof(int), cudaMemcpyHostToDevice, S));
+  { const int r = g->nccl->AllReduce(d_ok, d_ok, 1, kNcclInt32, kNcclMax, g->comm_up, S);
+    if (r != 0) return fin(vhp_i_fail(g->ctx, VHP_ERR_CUDA, std::string("ncclAllReduce: ") + g->nccl->GetErrorString(r))); }
+  GCUDA(g, cudaMemcpyAsync(&neg, d_ok, sizeof(int), cudaMemcpyDeviceToHost, S));
+  GCUDA(g, cudaStreamSynchronize(S));
+  (void)st;
+  if (neg == 0) {
+    g->p2p = true;
+    g->p2p_stride = stride;
+    g->ws[0] = g->p2p_buf;
+    g->ws[1] = g->p2p_buf + stride;
+  }
+  return fin(VHP_OK);
+}
+
 void destroy_giant(vhp_giant *g) {
   if (!g) return;
   cudaSetDevice(g->ctx->device);
   cudaStreamSynchronize(g->ctx->stream);
   if (g->s_dn) cudaStreamSynchronize(g->s_dn);
   drop_graph(g);
+  if (g->peer_next) cudaIpcCloseMemHandle(g->peer_next);
+  if (g->peer_prev) cudaIpcCloseMemHandle(g->peer_prev);
+  if (g->p2p_buf) cudaFree(g->p2p_buf);
   if (g->nccl) {
     if (g->comm_dn) g->nccl->CommDestroy(g->comm_dn);
     if (g->comm_up) g->nccl->CommDestroy(g->comm_up);
@@ -522,6 +625,7 @@ vhp_status vhp_giant_create(vhp_context *ctx, const uint8_t *occ, int nx, int ny
     int r = g->nccl->CommInitRank(&g->comm_up, world, uid, rank);
     if (r == 0) r = g->nccl->CommSplit(g->comm_up, 0, rank, &g->comm_dn, nullptr);
     if (r != 0) return bail(vhp_i_fail(ctx, VHP_ERR_CUDA, std::string("NCCL communicator: ") + g->nccl->GetErrorString(r)));
+    GTRY(setup_p2p(g));
   }
 #undef GTRY
 #undef GTRYC
@@ -649,12 +753,16 @@ vhp_status vhp_giant_solve(vhp_giant *g, const int32_t *se_xy, double threshold,
       stats->halo_bytes_sent = (int64_t)small[3] * sends * 2 * nx * 8;
     }
     stats->launches = ctx->launches - launches0;
+    stats->peer_handover = g->p2p ? 1 : 0;
+    if (g->p2p) stats->halo_bytes_sent = 0; // rows travel as peer stores inside the sweep kernels, tile by tile
     stats->solve_ms = 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
   }
   int flag = 0;
   GCUDA(g, cudaMemcpy(&flag, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
   if (flag) {
     cudaMemset(ctx->d_err, 0, sizeof(int));
+    if (flag & 2)
+      return vhp_i_fail(ctx, VHP_ERR_CUDA, "strip planner: a neighbouring rank did not deliver its boundary rows (peer hand-over timed out)");
     return vhp_i_fail(ctx, VHP_ERR_INVALID_ARG, "a source / start / end point lies outside the grid");
   }
   return VHP_OK;

@@ -286,6 +286,7 @@ cudaError_t vhp_launch_sweep_tile(const VhpTilePlanes &pl, int nx, int ny, const
   p.g_lm = p.g_prog = p.g_next_row = nullptr;
   p.qmask = 0xF;
   p.src_ctl = nullptr;
+  p.x_edges = nullptr; p.x_prog = nullptr; p.x_y0 = p.x_y1 = 0; p.remote_mask = 0;
   const cudaError_t e = dtype == VHP_F32 ? launch_tile<float>(p, npairs, st)
                                          : launch_tile<double>(p, npairs, st);
   if (launches) *launches += 1;
@@ -298,6 +299,13 @@ void vhp_window_halo_rows(int nx, int ny, int sx, int sy, int y0, int y1, int32_
     tile_window_of(q, nx, ny, sx, sy, y0, y1, &jw0, &jw1, &Jlo, &Jhi, &hy);
     rows[q] = hy;
   }
+}
+
+// offset and size of the progress flags inside a grid workspace (reset between sweeps when a peer
+// raises them, see VhpSweepPeer)
+void vhp_sweep_grid_ws_flags(int nx, int ny, size_t *offset, size_t *bytes) {
+  *offset = sizeof(double) * (size_t)tile_edge_doubles(nx, kTileWarps) + sizeof(int) * 4 * (size_t)tile_lm_cap(ny);
+  *bytes = sizeof(int) * 4 * (size_t)tile_lm_cap(ny);
 }
 
 size_t vhp_sweep_grid_ws_bytes(int nx, int ny) {
@@ -347,7 +355,8 @@ cudaError_t vhp_launch_sweep_window(const VhpTilePlanes &pl, int nx, int ny, int
                                     int y1, const double *const d_halo[4], vhp_dtype dtype,
                                     void *d_out_strip, const double *d_rcp2, int *d_err,
                                     void *d_grid_ws, int grid_ctas, cudaStream_t st,
-                                    int64_t *launches, int qmask, const int *d_src_ctl) {
+                                    int64_t *launches, int qmask, const int *d_src_ctl,
+                                    const VhpSweepPeer *peer) {
   TileArgs p;
   p.pl = pl;
   p.nx = nx;
@@ -364,6 +373,17 @@ cudaError_t vhp_launch_sweep_window(const VhpTilePlanes &pl, int nx, int ny, int
   for (int q = 0; q < 4; ++q) p.halo[q] = d_halo ? d_halo[q] : nullptr;
   p.qmask = qmask;
   p.src_ctl = d_src_ctl;
+  p.x_edges = nullptr; p.x_prog = nullptr; p.x_y0 = p.x_y1 = 0; p.remote_mask = 0;
+  if (peer && d_grid_ws && grid_ctas > 1) { // peer hand-over exists in grid mode only
+    const int lmcap = tile_lm_cap(ny);
+    if (peer->x_ws) {
+      p.x_edges = static_cast<double *>(peer->x_ws);
+      p.x_prog = reinterpret_cast<int *>(p.x_edges + tile_edge_doubles(nx, kTileWarps)) + 4 * lmcap;
+      p.x_y0 = peer->x_y0;
+      p.x_y1 = peer->x_y1;
+    }
+    p.remote_mask = peer->remote_mask;
+  }
   return dtype == VHP_F32 ? launch_window<float>(p, sx, sy, d_grid_ws, grid_ctas, st, launches)
                           : launch_window<double>(p, sx, sy, d_grid_ws, grid_ctas, st, launches);
 }

@@ -111,6 +111,8 @@ namespace {
 constexpr int kDiagUnroll = VHP_DIAG_UNROLL, kFillUnroll = VHP_FILL_UNROLL;
 constexpr int kTileWarps = 8;          // warps per CTA (default; small maps use fewer)
 constexpr int kTile = 32;              // tile side
+constexpr int kTileHdr = 256;          // shared-memory header: quadrant geometry (4 x TQuad), the row counter
+                                       // (+240) and the export tile rows of grid mode (4 x int16, +244)
 constexpr int kStagePitch = 33;        // staging tile pitch (elements)
 constexpr int kWarpScratch = 136;      // doubles per warp: bottom stream [34] (row-octant tiles: new left
                                        // column), left stream [34], 1/k table of the tile [33 x double2]
@@ -140,6 +142,22 @@ struct TileArgs {
   // from there and the launch is a no-op once `done` is set, so a planner iteration can be
   // enqueued (or captured in a CUDA graph) before the host knows the next source.
   const int *src_ctl;
+  // grid mode across GPUs (strip-partitioned planner, one strip per rank): the boundary between
+  // two strips is handed over tile by tile through peer memory instead of as a finished row.
+  //   exporter: x_edges / x_prog = the boundary rows and progress flags of the NEIGHBOUR's
+  //     workspace (a peer-mapped pointer, stores travel over NVLink); [x_y0, x_y1) = its window.
+  //     The warp that owns the tile row just below the neighbour's first one copies every top row
+  //     it finishes into the neighbour's boundary row and raises the neighbour's flag
+  //     (system-scope fence + atomicMax), so the neighbour's first tile row runs one tile behind
+  //     it, exactly like the next tile row on the same GPU, and the sweep's critical path does not
+  //     grow with the number of strips;
+  //   consumer: bit q of remote_mask = the boundary below quadrant q's first tile row arrives
+  //     this way (its flag is raised with atomicMax by both sides, its boundary row is
+  //     initialised only over the lit tiles, which nobody sends).
+  double *x_edges;
+  int *x_prog;
+  int x_y0, x_y1;
+  int remote_mask;
 };
 
 // how tile_sweep_cta is used
@@ -208,13 +226,13 @@ __host__ __device__ inline int tile_lm_cap(int ny) { return (ny - 1) / kTile + 4
 // grid mode keeps the boundary rows in global memory
 template <typename OutT>
 __host__ __device__ inline size_t tile_smem_bytes_grid(int nx, int ny, int nwarps = kTileWarps) {
-  return 256 + tile_sum_bytes(nx, ny) + 32 * (size_t)tile_lm_cap(ny) +
+  return kTileHdr + tile_sum_bytes(nx, ny) + 32 * (size_t)tile_lm_cap(ny) +
          (size_t)nwarps * (kTile * kStagePitch * sizeof(OutT) + kWarpScratch * sizeof(double));
 }
 
 template <typename OutT>
 __host__ __device__ inline size_t tile_smem_bytes(int nx, int ny, int nwarps = kTileWarps) {
-  return 256 + tile_sum_bytes(nx, ny) + 32 * (size_t)tile_lm_cap(ny) +
+  return kTileHdr + tile_sum_bytes(nx, ny) + 32 * (size_t)tile_lm_cap(ny) +
          sizeof(double) * (size_t)tile_edge_doubles(nx, nwarps) +
          (size_t)nwarps * (kTile * kStagePitch * sizeof(OutT) + kWarpScratch * sizeof(double));
 }
@@ -336,6 +354,12 @@ __device__ __forceinline__ void st_release_gpu(int *a, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(a), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ int ld_acquire_sys(const int *a) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
+  return v;
+}
+
 // One tile (I, J) of quadrant g by one warp.  Lv (lane r: q(i0-1, j0+r)) and cor
 // (q(i0-1, j0-1)) are the left inputs; on return they hold the same for tile (I+1, J).
 // GE: the boundary rows (edges) and the progress flag are in global memory and shared with
@@ -345,7 +369,8 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
                                              const int sx, const int sy, const int I, const int J,
                                              OutT *__restrict__ out, double *edges,
                                              OutT *stage, double *wscr, const int lane,
-                                             double &Lv, double &cor, int *done_flag) {
+                                             double &Lv, double &cor, int *done_flag,
+                                             int *xflag = nullptr) {
   // the row above may start its tile I as soon as rowE holds this tile's top row: publish
   // before the global stores
   constexpr int kStepUnroll = NW == 1 ? VHP_STEP_UNROLL_1W : VHP_STEP_UNROLL;
@@ -355,6 +380,17 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
     if (lane == 0) {
       if (GE) st_release_gpu(done_flag, I + 1);
       else st_release_shared(done_flag, I + 1);
+    }
+    if (GE && xflag) {
+      // hand this tile's top row to the strip on the next GPU (see TileArgs::x_edges); its boundary
+      // row of the quadrant lies at the same offset as here (rowOff depends on the source alone)
+      const int wi_ = I ? kTile : g.a;
+      const int i0_ = tile_start(g.a, I);
+      const double top = __ldcg(edges + g.rowOff + i0_ + lane);
+      if (lane < wi_) p.x_edges[g.rowOff + i0_ + lane] = top;
+      __threadfence_system();
+      __syncwarp();
+      if (lane == 0) atomicMax_system(xflag, I + 1);
     }
   };
   const int nx = p.nx;
@@ -580,12 +616,12 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
   // next tile row to hand out (NW > 1)
   int *next_row = GE ? p.g_next_row : reinterpret_cast<int *>(smem_raw + 240);
   static_assert(4 * sizeof(TQuad) <= 240, "quadrant geometry overlaps the row counter");
-  uint32_t *bsum = reinterpret_cast<uint32_t *>(smem_raw + 256);
+  uint32_t *bsum = reinterpret_cast<uint32_t *>(smem_raw + kTileHdr);
   const int nsum = tile_sum_words(nx) * ((ny + 31) >> 5);
   const int lmcap = tile_lm_cap(ny);
-  int *Lm = reinterpret_cast<int *>(smem_raw + 256 + tile_sum_bytes(nx, ny));
+  int *Lm = reinterpret_cast<int *>(smem_raw + kTileHdr + tile_sum_bytes(nx, ny));
   int *prog = GE ? p.g_prog : Lm + 4 * lmcap; // tiles finished (or lit) at the head of tile row (q, J)
-  double *const edges_s = reinterpret_cast<double *>(smem_raw + 256 + tile_sum_bytes(nx, ny) + 32 * lmcap);
+  double *const edges_s = reinterpret_cast<double *>(smem_raw + kTileHdr + tile_sum_bytes(nx, ny) + 32 * lmcap);
   double *edges = GE ? p.g_edges : edges_s;
   const int nedge = tile_edge_doubles(nx, NW);
   unsigned char *wbase = reinterpret_cast<unsigned char *>(GE ? edges_s : edges_s + nedge);
@@ -618,9 +654,21 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
       if (g.Jhi < g.Jlo || !((p.qmask >> q) & 1)) g.TX = g.TY = 0; // nothing of this quadrant to do
       quads[q] = g;
     }
+    if (GE) {
+      // export plan: the tile row just below the neighbour's first one, per quadrant (from ITS window)
+      short *xJ = reinterpret_cast<short *>(smem_raw + 244);
+      for (int q = 0; q < 4; ++q) {
+        const TQuad &g = quads[q];
+        xJ[q] = -1;
+        if (!p.x_edges) continue;
+        int jw0, jw1, Jlo2, Jhi2, hy;
+        tile_window_of(q, nx, ny, sx, sy, p.x_y0, p.x_y1, &jw0, &jw1, &Jlo2, &Jhi2, &hy);
+        if (g.TX && Jhi2 >= Jlo2 && Jlo2 > 0 && Jlo2 - 1 >= g.Jlo && Jlo2 - 1 <= g.Jhi) xJ[q] = (short)(Jlo2 - 1);
+      }
+    }
   }
   for (int i = tid; i < nsum; i += blockDim.x) bsum[i] = __ldg(p.pl.bsum + (size_t)map * nsum + i);
-  if (MODE != kSweepGridWork)
+  if (MODE == kSweepCta)
     for (int i = tid; i < nedge; i += blockDim.x) edges[i] = 1.0; // virtual boundary
   __syncthreads();
   if (MODE == kSweepGridWork) { // the staircase was computed by the init kernel
@@ -652,9 +700,30 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
     for (int J = 0; J < g.TY; ++J) {
       m = min(m, Lm[tid * lmcap + J]);
       Lm[tid * lmcap + J] = m;
-      prog[tid * lmcap + J] = J < g.Jlo ? g.TX : m; // rows below the window count as finished
+      if (GE && ((p.remote_mask >> tid) & 1) && J == g.Jlo - 1)
+        atomicMax_system(prog + tid * lmcap + J, m); // the row below arrives tile by tile from the neighbour
+      else
+        prog[tid * lmcap + J] = J < g.Jlo ? g.TX : m; // rows below the window count as finished
       if (GE) p.g_lm[tid * lmcap + J] = m;
     }
+  }
+  if (MODE == kSweepGridInit) {
+    // virtual boundary -- except where the neighbouring strip writes the boundary row itself
+    // (beyond the lit tiles of the row below this quadrant's first one)
+    __syncthreads();
+    for (int i = tid; i < nedge; i += blockDim.x) {
+      bool mine = true;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const TQuad &g = quads[q];
+        if (((p.remote_mask >> q) & 1) && g.TX && g.Jlo > 0) {
+          const int lit = tile_start(g.a, Lm[q * lmcap + g.Jlo - 1]);
+          if (i >= g.rowOff + lit && i < g.rowOff + g.TX * kTile) mine = false;
+        }
+      }
+      if (mine) edges[i] = 1.0;
+    }
+    __syncthreads();
   }
   if (NW > 1) { // boundary row below the first tile row of the window = the neighbour's halo row
     for (int q = 0; q < 4; ++q) {
@@ -728,6 +797,8 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
     const uint32_t *rowpl = (g.dirx > 0 ? p.pl.rowF : p.pl.rowR) + (size_t)map * p.pl.row_plane;
     const uint32_t *colpl = (g.diry > 0 ? p.pl.colF : p.pl.colR) + (size_t)map * p.pl.col_plane;
     double Lv = 1.0, cor = 1.0; // left of the first tile: lit tiles or the virtual boundary
+    int *xflag = nullptr; // grid mode across GPUs: the neighbour's flag of this row, if it is the exported one
+    if (GE && reinterpret_cast<const short *>(smem_raw + 244)[q] == J) xflag = p.x_prog + q * lmcap + J;
     TilePre pre = tile_prefetch(p, g, rowpl, colpl, bsum, sx, sy, I0, J, lane);
 #if VHP_DARK_TAIL
     // rows of this tile row that hold cells to compute (lane <-> row j0 + lane), as in process_tile
@@ -781,7 +852,19 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
 #endif
       const TilePre cur = pre;
       if (I + 1 < g.TX) pre = tile_prefetch(p, g, rowpl, colpl, bsum, sx, sy, I + 1, J, lane);
-      if (NW > 1 && J > 0) { // tile (I, J-1) must be finished
+      if (GE && J > 0 && ((p.remote_mask >> q) & 1) && J == g.Jlo) {
+        // the row below lives on the neighbouring GPU: its flag arrives over NVLink.  A watchdog
+        // (a few seconds) turns a lost neighbour into an error instead of a hung GPU.
+        const int *flag = prog + q * lmcap + J - 1;
+        unsigned polls = 0;
+        while (ld_acquire_sys(flag) <= I) {
+          __nanosleep(200);
+          if (++polls > (1u << 24)) {
+            if (lane == 0) atomicOr(p.err, 2);
+            break;
+          }
+        }
+      } else if (NW > 1 && J > 0) { // tile (I, J-1) must be finished
         const int *flag = prog + q * lmcap + J - 1;
 #if VHP_POLL_BACKOFF
         for (unsigned ns = VHP_POLL_NS0; (GE ? ld_acquire_gpu(flag) : ld_acquire_shared(flag)) <= I;
@@ -792,7 +875,7 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
 #endif
       }
       process_tile<OutT, NW, GE>(p, g, cur, sx, sy, I, J, out, edges, stage, wscr, lane, Lv, cor,
-                             prog + q * lmcap + J);
+                             prog + q * lmcap + J, xflag);
       __syncwarp();
     }
   };

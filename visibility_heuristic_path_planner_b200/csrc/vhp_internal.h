@@ -185,12 +185,22 @@ void vhp_window_halo_rows(int nx, int ny, int sx, int sy, int y0, int y1, int32_
 // d_grid_ws (vhp_sweep_grid_ws_bytes bytes) with grid_ctas > 1: the sweep is spread over that
 // many CTAs (two launches), else a single CTA does it.
 size_t vhp_sweep_grid_ws_bytes(int nx, int ny);
+void vhp_sweep_grid_ws_flags(int nx, int ny, size_t *offset, size_t *bytes);
+// Strip boundaries across GPUs, handed over tile by tile through peer memory (grid mode only; see
+// TileArgs::x_edges in sweep_tile_body.cuh).  x_ws: the neighbour's grid workspace of this chain
+// (peer-mapped, null: nothing to export), [x_y0, x_y1): its window; remote_mask: quadrants whose
+// lower boundary this sweep receives that way.
+struct VhpSweepPeer {
+  void *x_ws = nullptr;
+  int x_y0 = 0, x_y1 = 0;
+  int remote_mask = 0;
+};
 cudaError_t vhp_launch_sweep_window(const VhpTilePlanes &pl, int nx, int ny, int sx, int sy, int y0,
                                     int y1, const double *const d_halo[4], vhp_dtype dtype,
                                     void *d_out_strip, const double *d_rcp2, int *d_err,
                                     void *d_grid_ws, int grid_ctas, cudaStream_t st,
                                     int64_t *launches, int qmask = 0xF,
-                                    const int *d_src_ctl = nullptr);
+                                    const int *d_src_ctl = nullptr, const VhpSweepPeer *peer = nullptr);
 // one LARGE planner problem on the whole GPU (capi.cu: planner_grid_one -> giant.cu): outputs
 // from the loop state d_ctl = {done, next x, next y, status, nb_of_sources, ...}
 cudaError_t vhp_launch_grid_planner_finish(const int *d_ctl, int nx, int ny, int ex, int ey,

@@ -22,7 +22,8 @@ ID_BYTES = 128
 class GiantStats(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("loop_mode", C.c_int32), ("solve_ms", C.c_double),
                 ("loop_ms", C.c_double), ("nccl_ms", C.c_double), ("nccl_ops", C.c_int64),
-                ("nccl_ops_timed", C.c_int64), ("halo_bytes_sent", C.c_int64), ("launches", C.c_int64)]
+                ("nccl_ops_timed", C.c_int64), ("halo_bytes_sent", C.c_int64), ("launches", C.c_int64),
+                ("peer_handover", C.c_int32), ("reserved", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
