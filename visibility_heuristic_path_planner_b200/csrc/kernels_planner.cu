@@ -118,12 +118,20 @@ __global__ void __launch_bounds__(NWK * 32, MINB) planner_kernel(const PlannerPa
       if (nb == 0) {
         // first sweep: the fields are still uninitialised workspace; nothing is loaded, everything
         // stored (reset() :42-60 and the first epilogue in one pass)
+        constexpr int kFirstU = 4; // cells in flight per lane
         for (int Y = warp; Y < ny; Y += NW) {
           const size_t row = (size_t)Y * nx;
-#pragma unroll 2
-          for (int X = lane; X < nx; X += 32)
-            epilogue_cell_first(X, Y, row + X, __ldcg(vis + row + X), sx, sy, ex, ey, thr, scale, ls, vg, hc,
-                                came, best);
+          for (int X0 = lane; X0 < nx; X0 += 32 * kFirstU) {
+            double v[kFirstU];
+#pragma unroll
+            for (int u = 0; u < kFirstU; ++u)
+              if (X0 + 32 * u < nx) v[u] = __ldcg(vis + row + X0 + 32 * u);
+#pragma unroll
+            for (int u = 0; u < kFirstU; ++u)
+              if (X0 + 32 * u < nx)
+                epilogue_cell_first(X0 + 32 * u, Y, row + X0 + 32 * u, v[u], sx, sy, ex, ey, thr, scale, ls, vg, hc,
+                                    came, best);
+          }
         }
       } else {
         constexpr int kEpiU = 4;
