@@ -877,6 +877,44 @@ def main():
                                 "bit packing on the device, D2H of 1 bit per cell, all inside the timed region; bit-exact "
                                 "against the fp64 field compared with >= threshold (tests/test_gpu_sweep.py)"}
         del bits_h
+        # ---- ... and as row runs (vhp_visibility_batch_runs): transition columns per row
+        rc_h = torch.empty((n, ny), dtype=torch.int16, pin_memory=True)
+        pp_h = torch.empty(n + 1, dtype=torch.int64, pin_memory=True)
+        cap = 16 * n * ny
+        tr_h = torch.empty(cap, dtype=torch.int16, pin_memory=True)
+        rc_np, pp_np, tr_np = rc_h.numpy().view(np.uint16), pp_h.numpy().view(np.uint64), tr_h.numpy().view(np.uint16)
+        used = C.c_int64(0)
+
+        def runs_step():
+            st = lib.vhp_visibility_batch_runs(host_ctx.h, maps.ctypes.data, nmaps, nx, ny, src.ctypes.data,
+                                               None if smap is None else smap.ctypes.data, n, thr_bin,
+                                               rc_np.ctypes.data, pp_np.ctypes.data, tr_np.ctypes.data, cap,
+                                               C.byref(used))
+            assert st == 0, host_ctx.lib.vhp_last_error(host_ctx.h)
+        runs_step()
+        rc_np.fill(0)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(kb):
+            runs_step()
+        torch.cuda.synchronize()
+        t_runs = (time.perf_counter() - t0) / kb
+        if world > 1:
+            tt = torch.tensor([t_runs], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_runs = float(tt.item())
+        for p_ in probe:  # rebuild the probe pairs' bit maps from their runs
+            lo, hi = int(pp_np[p_]), int(pp_np[p_ + 1])
+            got = vhp.runs_to_bits(rc_np[p_:p_ + 1], np.array([0, hi - lo], np.uint64), tr_np[lo:hi], nx)[0]
+            assert np.array_equal(vhp.unpack_bits(got, nx), out_t[p_].cpu().numpy() >= thr_bin), f"row runs differ (pair {p_})"
+        d2h_runs, _, _ = host_ctx.last_transport()
+        e2e["runs"] = {"value": cells_e2e * world / t_runs / 1e9, "unit": "Gcells/s", "ms_per_step": t_runs * 1e3,
+                       "steps": kb, "threshold": thr_bin, "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],
+                       "d2h_bytes_per_step": int(d2h_runs), "transition_columns": int(pp_np[n]),
+                       "api": "vhp_visibility_batch_runs (host buffers, pinned outputs): H2D, fp64 sweeps, threshold + run "
+                              "encoding on the device (transition columns per row), D2H, all inside the timed region; "
+                              "bit-exact against the fp64 field compared with >= threshold (tests/test_gpu_sweep.py)"}
+        del rc_h, pp_h, tr_h
         n, src, smap = n_full, src_full, smap_full
 
     # ---- the same grid and batch size with obstacles (kernel-only, rank-local): how the

@@ -126,6 +126,27 @@ vhp_status vhp_visibility_batch_bin_dev(vhp_context *ctx, const uint8_t *d_occ, 
                                         int nx, int ny, const int32_t *d_src_xy,
                                         const int32_t *d_src_map, int64_t npairs,
                                         double threshold, uint32_t *d_out_bits);
+/* The same thresholded visibility as ROW RUNS: the visible set of row y of pair p,
+ * {x : visibility_(x, y) >= threshold}, as its sorted transition columns t0 < t1 < ... -- visible on
+ * [t0, t1), [t2, t3), ...; a run that reaches the last cell ends at nx, so every row holds an even
+ * number of columns.  A visibility polygon crosses a row a handful of times: 6 bytes per row on an
+ * empty 1000 x 1000 map against 125 bytes of bits and 4000 bytes of fp32, which takes the host-buffer
+ * call off the box's PCIe / host-memory path (bench.py: e2e.runs).  A caller can test a cell by a binary
+ * search in its row, or rebuild the bit map with vhp_runs_to_bits.
+ *   row_count[p * ny + y]  number of transition columns of the row (uint16)
+ *   pair_ptr[p]            index into trans of the first column of pair p; pair_ptr[npairs] = total
+ *   trans[...]             the columns, rows of a pair back to back (uint16; nx <= 16384)
+ * trans_cap = capacity of trans in elements; the call fails with VHP_ERR_INVALID_ARG and *trans_used =
+ * the elements needed (so far) when it is too small.  Decided on the fp64 value like the bit form. */
+vhp_status vhp_visibility_batch_runs(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx,
+                                     int ny, const int32_t *src_xy, const int32_t *src_map,
+                                     int64_t npairs, double threshold, uint16_t *row_count,
+                                     uint64_t *pair_ptr, uint16_t *trans, int64_t trans_cap,
+                                     int64_t *trans_used);
+/* host utility: row runs -> bit maps (the layout of vhp_visibility_batch_bin) */
+vhp_status vhp_runs_to_bits(const uint16_t *row_count, const uint64_t *pair_ptr, const uint16_t *trans,
+                            int64_t npairs, int nx, int ny, uint32_t *out_bits);
+
 /* ---- opt-in variants of the sweep: the paper's MATLAB algorithm and the reference's
  * early-terminating queue variant.  Same layouts as vhp_visibility_batch.
  *   VHP_VARIANT_MATLAB  getAccessibilityMap.m (MATLAB_code/visibility/getAccessibilityMap.m:1-118):

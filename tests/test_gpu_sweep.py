@@ -285,3 +285,41 @@ def test_sweep_variants_equal_oracle(vhp, oracle):
     with pytest.raises(vhp.VhpError):
         c.visibility_variant_batch(occ, src, vhp.VARIANT_MATLAB, fac=0.0)
     c.close()
+
+
+def test_row_runs_bit_exact(vhp, oracle):
+    """vhp_visibility_batch_runs: the thresholded visibility as transition columns per row, equal to
+    the bit form and to the oracle's fp64 field compared with >= threshold; widths that fill their
+    last word, that do not, and rows wider than 1024 cells."""
+    c = vhp.Context(0)
+    rng = np.random.default_rng(5)
+    for nx, ny, nobs, seed in ((101, 101, 10, 7), (64, 40, 6, 3), (96, 33, 0, 1), (1100, 37, 30, 2), (33, 31, 2, 1)):
+        occ = np.stack([rect_map(nx, ny, nobs, seed + k, 3, 14) for k in range(2)])
+        n = 9
+        smap = rng.integers(0, 2, n).astype(np.int32)
+        src = np.stack([rng.integers(0, nx, n), rng.integers(0, ny, n)], 1).astype(np.int32)
+        src[0] = (nx - 1, ny - 1); src[1] = (0, 0)
+        ref = np.stack([oracle.compute_visibility(occ[m], sx, sy) for (sx, sy), m in zip(src, smap)])
+        for thr in (0.5, 1.0, 0.0, 0.01):
+            rc, pp, tr = c.visibility_batch_runs(occ, src, thr, src_map=smap)
+            assert rc.shape == (n, ny) and pp.shape == (n + 1,) and pp[0] == 0 and pp[n] == len(tr) == rc.sum()
+            assert (rc % 2 == 0).all()
+            bits = vhp.runs_to_bits(rc, pp, tr, nx)
+            assert np.array_equal(vhp.unpack_bits(bits, nx), ref >= thr), (nx, ny, thr)
+            assert np.array_equal(bits, c.visibility_batch_bin(occ, src, thr, src_map=smap))
+            # columns ascend strictly inside a row and end at most at nx
+            k = 0
+            for p in range(n):
+                assert pp[p] == k
+                for y in range(ny):
+                    t = tr[k:k + rc[p, y]].astype(int)
+                    assert (np.diff(t) > 0).all() and (len(t) == 0 or t[-1] <= nx)
+                    k += rc[p, y]
+    # too small a buffer: the call says how much it needs
+    import ctypes as C
+    occ = np.ones((1, 50, 50), np.uint8); src = np.array([[5, 5]], np.int32)
+    rc = np.zeros((1, 50), np.uint16); pp = np.zeros(2, np.uint64); tr = np.zeros(10, np.uint16); used = C.c_int64(0)
+    st = c.lib.vhp_visibility_batch_runs(c.h, occ.ctypes.data, 1, 50, 50, src.ctypes.data, None, 1, 0.5,
+                                         rc.ctypes.data, pp.ctypes.data, tr.ctypes.data, 10, C.byref(used))
+    assert st == -1 and used.value == 98   # rows 1..49: visible on [1, 50); row 0 is the never-written border
+    c.close()

@@ -103,6 +103,9 @@ def load_library(build_if_missing: bool = True):
     lib.vhp_visibility_batch_bin_dev.argtypes = [vp, vp, i32, i32, i32, vp, vp, i64, C.c_double, vp]
     lib.vhp_visibility_variant_batch.argtypes = [vp, vp, i32, i32, i32, vp, vp, i64, C.POINTER(SweepVariant), i32, vp]
     lib.vhp_visibility_variant_batch_dev.argtypes = [vp, vp, i32, i32, i32, vp, vp, i64, C.POINTER(SweepVariant), i32, vp]
+    lib.vhp_visibility_batch_runs.argtypes = [vp, vp, i32, i32, i32, vp, vp, i64, C.c_double, vp, vp, vp, i64,
+                                              C.POINTER(i64)]
+    lib.vhp_runs_to_bits.argtypes = [vp, vp, vp, i64, i32, i32, vp]
     lib.vhp_release_maps_dev.argtypes = [vp]
     lib.vhp_context_device.argtypes = [vp]
     lib.vhp_prepare_maps_dev.argtypes = [vp, vp, i32, i32, i32]
@@ -260,6 +263,34 @@ class Context:
                                                       _np_ptr(mp), n, float(threshold), _np_ptr(out)))
         return out
 
+    def visibility_batch_runs(self, occ, src_xy, threshold, src_map=None, trans_cap=None, out=None):
+        """Thresholded visibility as row runs (vhp_visibility_batch_runs).  Returns (row_count uint16
+        (npairs, ny), pair_ptr uint64 (npairs + 1), trans uint16 (total,)).  `out` = (row_count, pair_ptr,
+        trans) buffers to fill (e.g. pinned); the call is repeated with a larger buffer when the first
+        guess for trans is too small and no buffer was given."""
+        occ = _occ_u8(occ)
+        nmaps, ny, nx = occ.shape
+        xy = np.ascontiguousarray(src_xy, dtype=np.int32).reshape(-1, 2)
+        n = xy.shape[0]
+        mp = None if src_map is None else np.ascontiguousarray(src_map, dtype=np.int32)
+        if out is not None:
+            rc, pp, tr = out
+        else:
+            rc = np.empty((n, ny), np.uint16)
+            pp = np.empty(n + 1, np.uint64)
+            tr = np.empty(int(trans_cap) if trans_cap else max(1024, 16 * n * ny), np.uint16)
+        used = C.c_int64(0)
+        while True:
+            st = self.lib.vhp_visibility_batch_runs(self.h, _np_ptr(occ), nmaps, nx, ny, _np_ptr(xy), _np_ptr(mp), n,
+                                                    float(threshold), _np_ptr(rc), _np_ptr(pp), _np_ptr(tr), tr.size,
+                                                    C.byref(used))
+            if st == -1 and used.value > tr.size and out is None:
+                tr = np.empty(max(2 * tr.size, 2 * used.value), np.uint16)
+                continue
+            self._check(st)
+            break
+        return rc, pp, tr[: int(pp[n])]
+
     def visibility_batch_bin_dev(self, occ_t, src_xy_t, threshold, out_bits_t, src_map_t=None):
         nmaps, ny, nx = occ_t.shape
         self._check(self.lib.vhp_visibility_batch_bin_dev(
@@ -341,6 +372,21 @@ class Context:
     def prepare_maps_dev(self, occ_t):
         nmaps, ny, nx = occ_t.shape
         self._check(self.lib.vhp_prepare_maps_dev(self.h, occ_t.data_ptr(), nmaps, nx, ny))
+
+
+def runs_to_bits(row_count, pair_ptr, trans, nx):
+    """Row runs -> uint32 bit maps (npairs, ny, ceil(nx/32)) (vhp_runs_to_bits)."""
+    lib = load_library()
+    n, ny = row_count.shape
+    out = np.empty((n, ny, (nx + 31) // 32), np.uint32)
+    tr = np.ascontiguousarray(trans, dtype=np.uint16)
+    if tr.size == 0:
+        tr = np.zeros(1, np.uint16)
+    st = lib.vhp_runs_to_bits(_np_ptr(np.ascontiguousarray(row_count)), _np_ptr(np.ascontiguousarray(pair_ptr)),
+                              _np_ptr(tr), n, nx, ny, _np_ptr(out))
+    if st != 0:
+        raise VhpError(st, lib.vhp_last_error(None).decode())
+    return out
 
 
 def unpack_bits(bits, nx):

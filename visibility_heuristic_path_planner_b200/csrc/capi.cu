@@ -617,6 +617,93 @@ vhp_status run_bin_host(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx,
   return check_device_error(ctx);
 }
 
+// Row runs of the thresholded visibility (vhp_visibility_batch_runs): per chunk of pairs fp64 sweep,
+// threshold bits, transitions per row / pair, exclusive scan, transition columns; the total of a
+// chunk is read back (8 bytes) before its columns are written and copied.
+vhp_status run_runs_host(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx, int ny,
+                         const int32_t *xy, const int32_t *maps, int64_t n, double thr,
+                         uint16_t *row_count, uint64_t *pair_ptr, uint16_t *trans, int64_t trans_cap,
+                         int64_t *trans_used) {
+  vhp_status st = check_common(ctx, occ, nmaps, nx, ny, xy, n, VHP_F64, row_count);
+  if (st != VHP_OK) return st;
+  if (!pair_ptr || (!trans && trans_cap > 0) || trans_cap < 0)
+    return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_visibility_batch_runs: null buffer");
+  if ((st = check_points(ctx, xy, 2, maps, n, nmaps, nx, ny, "vhp_visibility_batch_runs")) != VHP_OK) return st;
+  ctx->last_d2h_bytes = ctx->last_result_bytes = 0;
+  ctx->last_transport_packed = 0;
+  if (trans_used) *trans_used = 0;
+  pair_ptr[0] = 0;
+  if (n == 0) return VHP_OK;
+  VHP_ON_DEVICE(ctx);
+  const size_t cells = (size_t)nx * ny, wpr = (size_t)(nx + 31) / 32, occ_bytes = (size_t)nmaps * cells;
+  if ((st = ensure(ctx, ctx->b_occ, occ_bytes)) != VHP_OK) return st;
+  if ((st = ensure(ctx, ctx->b_src, (size_t)n * 8)) != VHP_OK) return st;
+  if (maps && (st = ensure(ctx, ctx->b_map, (size_t)n * 4)) != VHP_OK) return st;
+  VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_occ.p, occ, occ_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_src.p, xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (maps) VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_map.p, maps, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->planes_sticky = false;
+  ctx->tile_src = nullptr;
+  if (ctx->sweep_impl == 0 && (vhp_sweep_tile_supported(nx, ny) || vhp_sweep_grid_supported(nx, ny))) {
+    if ((st = pack_tile(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, true)) != VHP_OK) return st;
+    ctx->planes_sticky = true;
+  }
+  const int32_t *d_xy = (const int32_t *)ctx->b_src.p;
+  const int32_t *d_map = maps ? (const int32_t *)ctx->b_map.p : nullptr;
+  const int64_t chunk = bin_chunk_pairs(cells, n);
+  vhp_status result = ensure(ctx, ctx->b_bin, (size_t)chunk * cells * 8);
+  if (result == VHP_OK) result = ensure(ctx, ctx->b_out[0], (size_t)chunk * ny * wpr * 4);
+  // small per-chunk arrays: row counts, pair totals, pair offsets
+  const size_t o_cnt = 0, o_tot = ((size_t)chunk * ny * 2 + 255) & ~(size_t)255;
+  const size_t o_ptr = o_tot + (((size_t)chunk * 4 + 255) & ~(size_t)255);
+  if (result == VHP_OK) result = ensure(ctx, ctx->b_misc, o_ptr + ((size_t)chunk + 1) * 8 + 256);
+  unsigned long long total = 0;
+  for (int64_t p0 = 0; p0 < n && result == VHP_OK; p0 += chunk) {
+    const int64_t np = std::min(chunk, n - p0);
+    result = run_dev(ctx, Op::Sweep, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, d_xy + 2 * p0,
+                     d_map ? d_map + p0 : nullptr, np, VHP_F64, ctx->b_bin.p);
+    if (result != VHP_OK) break;
+    char *misc = (char *)ctx->b_misc.p;
+    uint16_t *d_cnt = (uint16_t *)(misc + o_cnt);
+    uint32_t *d_tot = (uint32_t *)(misc + o_tot);
+    unsigned long long *d_ptr = (unsigned long long *)(misc + o_ptr);
+    cudaError_t e = vhp_launch_threshold_bits((const double *)ctx->b_bin.p, np * ny, nx, thr, (uint32_t *)ctx->b_out[0].p,
+                                              ctx->sm_count, ctx->stream, &ctx->launches);
+    if (e == cudaSuccess)
+      e = vhp_launch_runs_count((const uint32_t *)ctx->b_out[0].p, np, ny, nx, d_cnt, d_tot, total, d_ptr,
+                                ctx->sm_count, ctx->stream, &ctx->launches);
+    unsigned long long new_total = 0;
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(&new_total, d_ptr + np, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { result = cuda_fail(ctx, e, "row runs: count"); break; }
+    if (trans_used) *trans_used = (int64_t)new_total;
+    if ((int64_t)new_total > trans_cap) {
+      result = fail(ctx, VHP_ERR_INVALID_ARG, "vhp_visibility_batch_runs: trans_cap too small (see *trans_used)");
+      break;
+    }
+    const size_t chunk_elems = (size_t)(new_total - total);
+    if ((result = ensure(ctx, ctx->b_out[1], std::max<size_t>(chunk_elems * 2, 256))) != VHP_OK) break;
+    e = vhp_launch_runs_write((const uint32_t *)ctx->b_out[0].p, np, ny, nx, d_cnt, d_ptr, total,
+                              (uint16_t *)ctx->b_out[1].p, ctx->sm_count, ctx->stream, &ctx->launches);
+    if (e == cudaSuccess && chunk_elems)
+      e = cudaMemcpyAsync(trans + total, ctx->b_out[1].p, chunk_elems * 2, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(row_count + (size_t)p0 * ny, d_cnt, (size_t)np * ny * 2, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(pair_ptr + p0, d_ptr, ((size_t)np + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); // the device buffers are reused by the next chunk
+    if (e != cudaSuccess) { result = cuda_fail(ctx, e, "row runs: write"); break; }
+    ctx->last_d2h_bytes += (int64_t)(chunk_elems * 2 + (size_t)np * ny * 2 + ((size_t)np + 1) * 8 + 8);
+    total = new_total;
+  }
+  ctx->planes_sticky = false;
+  ctx->tile_src = nullptr;
+  ctx->last_result_bytes = ctx->last_d2h_bytes;
+  if (result != VHP_OK) return result;
+  return check_device_error(ctx);
+}
+
 // ---- opt-in sweep variants ------------------------------------------------------------------------
 vhp_status check_variant(vhp_context *ctx, const vhp_sweep_variant *v) {
   if (!v) return fail(ctx, VHP_ERR_INVALID_ARG, "sweep variant: null descriptor");
@@ -983,6 +1070,33 @@ vhp_status vhp_visibility_batch_bin(vhp_context *ctx, const uint8_t *occ, int nm
                                     const int32_t *src_xy, const int32_t *src_map, int64_t npairs,
                                     double threshold, uint32_t *out_bits) {
   return run_bin_host(ctx, occ, nmaps, nx, ny, src_xy, src_map, npairs, threshold, out_bits);
+}
+
+vhp_status vhp_visibility_batch_runs(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx, int ny,
+                                     const int32_t *src_xy, const int32_t *src_map, int64_t npairs,
+                                     double threshold, uint16_t *row_count, uint64_t *pair_ptr,
+                                     uint16_t *trans, int64_t trans_cap, int64_t *trans_used) {
+  return run_runs_host(ctx, occ, nmaps, nx, ny, src_xy, src_map, npairs, threshold, row_count, pair_ptr, trans,
+                       trans_cap, trans_used);
+}
+
+vhp_status vhp_runs_to_bits(const uint16_t *row_count, const uint64_t *pair_ptr, const uint16_t *trans,
+                            int64_t npairs, int nx, int ny, uint32_t *out_bits) {
+  if (!row_count || !pair_ptr || !out_bits || npairs < 0 || nx < 1 || ny < 1)
+    return fail(nullptr, VHP_ERR_INVALID_ARG, "vhp_runs_to_bits: bad argument");
+  const size_t wpr = (size_t)(nx + 31) / 32;
+  std::memset(out_bits, 0, (size_t)npairs * ny * wpr * 4);
+  for (int64_t p = 0; p < npairs; ++p) {
+    const uint16_t *t = trans + pair_ptr[p];
+    for (int y = 0; y < ny; ++y) {
+      const int c = row_count[(size_t)p * ny + y];
+      uint32_t *row = out_bits + ((size_t)p * ny + y) * wpr;
+      for (int k = 0; k + 1 < c; k += 2)
+        for (int x = t[k]; x < t[k + 1] && x < nx; ++x) row[x >> 5] |= 1u << (x & 31);
+      t += c;
+    }
+  }
+  return VHP_OK;
 }
 
 vhp_status vhp_visibility_batch_bin_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx,

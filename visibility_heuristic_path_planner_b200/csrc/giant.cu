@@ -430,7 +430,6 @@ vhp_status setup_p2p(vhp_giant *g) {
   const size_t xb = 64 + 64 * (size_t)g->world + 16;
   GCUDA(g, cudaMalloc(&d_x, xb));
   std::vector<char> h_all(64 * (size_t)g->world);
-  vhp_status st = VHP_OK;
   auto fin = [&](vhp_status r) { cudaFree(d_x); return r; };
   GCUDA(g, cudaMemcpyAsync(d_x, &mine, 64, cudaMemcpyHostToDevice, S));
   { const int r = g->nccl->AllGather(d_x, d_x + 64, 8, kNcclUint64, g->comm_up, S);
@@ -457,7 +456,6 @@ vhp_status setup_p2p(vhp_giant *g) {
     if (r != 0) return fin(vhp_i_fail(g->ctx, VHP_ERR_CUDA, std::string("ncclAllReduce: ") + g->nccl->GetErrorString(r))); }
   GCUDA(g, cudaMemcpyAsync(&neg, d_ok, sizeof(int), cudaMemcpyDeviceToHost, S));
   GCUDA(g, cudaStreamSynchronize(S));
-  (void)st;
   if (neg == 0) {
     g->p2p = true;
     g->p2p_stride = stride;

@@ -21,6 +21,7 @@
 // device can also take whole mask words: in direct mode the words w with w % 16 < gpu_share
 // (except the last word of the chunk) are stored completely by this kernel, uniform units
 // included, and skipped by the host.
+#include <algorithm>
 #include <cstdint>
 
 #include "vhp_internal.h"
@@ -187,6 +188,152 @@ cudaError_t vhp_launch_threshold_bits(const double *d_vis, int64_t nrows, int nx
   if (blocks > (int64_t)sm_count * 16) blocks = (int64_t)sm_count * 16;
   if (blocks < 1) blocks = 1;
   threshold_bits_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_vis, nrows, nx, wpr, thr, d_bits);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+
+// ---- thresholded binary visibility as row runs -------------------------------------------------
+// The visible set of a row, {x : vis(x, y) >= thr}, as its sorted transition columns
+// t0 < t1 < ...: visible on [t0, t1), [t2, t3), ... (an open last run ends at nx, so the count is
+// always even).  A visibility polygon crosses a row a handful of times, so this is 10-20 x smaller
+// than one bit per cell -- small enough that the host-buffer call is bound by the sweep again and
+// not by the box's PCIe / host-memory path, whatever the number of GPUs.
+//   pass 1  threshold_bits_kernel (above) -> bits[row][wpr]
+//   pass 2  runs_count_kernel: transitions per row (uint16) and per pair (uint32)
+//   pass 3  runs_scan_kernel: exclusive scan of the pair totals (one CTA; <= a few thousand pairs)
+//   pass 4  runs_write_kernel: positions, one warp per row
+namespace {
+
+__device__ __forceinline__ uint32_t transitions_of(const uint32_t w, const uint32_t prev_msb) {
+  return w ^ ((w << 1) | prev_msb); // bit b set: cell b differs from cell b - 1 (cell -1 of a row = 0)
+}
+
+// one warp per row; lane l handles words l, l + 32, ...
+__global__ void __launch_bounds__(256)
+runs_count_kernel(const uint32_t *__restrict__ bits, const int64_t nrows, const int ny, const int nx,
+                  const int wpr, uint16_t *__restrict__ row_cnt, uint32_t *__restrict__ pair_tot) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < nrows; row += nwarps) {
+    const uint32_t *r = bits + row * wpr;
+    int cnt = 0;
+    for (int w0 = 0; w0 < wpr; w0 += 32) {
+      const int w = w0 + lane;
+      const uint32_t cur = w < wpr ? r[w] : 0u;
+      const uint32_t prev = (w > 0 && w < wpr) ? r[w - 1] >> 31 : 0u;
+      cnt += __popc(transitions_of(cur, prev));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(kAllLanes, cnt, off);
+    // a run that reaches the last cell is closed at nx: the zero padding bit of the last word does
+    // that by itself unless the row fills its last word
+    if ((nx & 31) == 0) cnt += (int)(r[wpr - 1] >> 31);
+    if (lane == 0) {
+      row_cnt[row] = (uint16_t)cnt;
+      atomicAdd(pair_tot + row / ny, (uint32_t)cnt);
+    }
+  }
+}
+
+// pair_ptr[p] = base + sum of pair_tot[0 .. p), pair_ptr[npairs] = base + total (one CTA)
+__global__ void __launch_bounds__(1024)
+runs_scan_kernel(const uint32_t *__restrict__ pair_tot, const int npairs, const unsigned long long base,
+                 unsigned long long *__restrict__ pair_ptr) {
+  __shared__ unsigned long long s_part[1024];
+  const int t = threadIdx.x, per = (npairs + 1023) / 1024;
+  unsigned long long sum = 0;
+  for (int i = t * per; i < min(npairs, (t + 1) * per); ++i) sum += pair_tot[i];
+  s_part[t] = sum;
+  __syncthreads();
+  if (t == 0) {
+    unsigned long long run = base;
+    for (int i = 0; i < 1024; ++i) { const unsigned long long v = s_part[i]; s_part[i] = run; run += v; }
+    pair_ptr[npairs] = run;
+  }
+  __syncthreads();
+  unsigned long long run = s_part[t];
+  for (int i = t * per; i < min(npairs, (t + 1) * per); ++i) { pair_ptr[i] = run; run += pair_tot[i]; }
+}
+
+// one warp per row: write the transition columns at trans[pair_ptr[pair] - chunk_base + offset of the row]
+__global__ void __launch_bounds__(256)
+runs_write_kernel(const uint32_t *__restrict__ bits, const int64_t nrows, const int ny, const int nx,
+                  const int wpr, const uint16_t *__restrict__ row_cnt,
+                  const unsigned long long *__restrict__ pair_ptr, const unsigned long long chunk_base,
+                  uint16_t *__restrict__ trans) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < nrows; row += nwarps) {
+    const int64_t pair = row / ny;
+    const int y = (int)(row - pair * ny);
+    // offset of the row inside its pair: sum of the counts of the pair's earlier rows
+    unsigned long long off = 0;
+    {
+      const uint16_t *c = row_cnt + pair * ny;
+      unsigned int part = 0;
+      for (int i = lane; i < y; i += 32) part += c[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kAllLanes, part, o);
+      off = pair_ptr[pair] - chunk_base + part;
+    }
+    const uint32_t *r = bits + row * wpr;
+    uint16_t *out = trans + off;
+    int base = 0;
+    for (int w0 = 0; w0 < wpr; w0 += 32) {
+      const int w = w0 + lane;
+      const uint32_t cur = w < wpr ? r[w] : 0u;
+      const uint32_t prev = (w > 0 && w < wpr) ? r[w - 1] >> 31 : 0u;
+      uint32_t t = transitions_of(cur, prev);
+      const int n = __popc(t);
+      int pre = n; // inclusive warp scan
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(kAllLanes, pre, o);
+        if (lane >= o) pre += v;
+      }
+      int pos = base + pre - n;
+      while (t) {
+        const int b = __ffs(t) - 1;
+        t &= t - 1;
+        out[pos++] = (uint16_t)(32 * w + b);
+      }
+      base += __shfl_sync(kAllLanes, pre, 31);
+    }
+    if (lane == 0 && (nx & 31) == 0 && (r[wpr - 1] >> 31)) out[base] = (uint16_t)nx;
+  }
+}
+
+} // namespace
+
+// d_pair_tot: npairs uint32, zeroed here.  Leaves row_cnt and pair_ptr (npairs + 1 entries, starting
+// at `base`) on the device; the caller reads pair_ptr[npairs] to learn how many positions pass 4 writes.
+cudaError_t vhp_launch_runs_count(const uint32_t *d_bits, int64_t npairs, int ny, int nx, uint16_t *d_row_cnt,
+                                  uint32_t *d_pair_tot, unsigned long long base,
+                                  unsigned long long *d_pair_ptr, int sm_count, cudaStream_t st,
+                                  int64_t *launches) {
+  const int wpr = (nx + 31) / 32;
+  cudaError_t e = cudaMemsetAsync(d_pair_tot, 0, (size_t)npairs * sizeof(uint32_t), st);
+  if (e != cudaSuccess) return e;
+  const int64_t nrows = npairs * ny;
+  int64_t blocks = std::min<int64_t>((nrows + 7) / 8, (int64_t)sm_count * 16);
+  runs_count_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), 256, 0, st>>>(d_bits, nrows, ny, nx, wpr, d_row_cnt, d_pair_tot);
+  runs_scan_kernel<<<1, 1024, 0, st>>>(d_pair_tot, (int)npairs, base, d_pair_ptr);
+  if (launches) *launches += 2;
+  return cudaGetLastError();
+}
+
+cudaError_t vhp_launch_runs_write(const uint32_t *d_bits, int64_t npairs, int ny, int nx,
+                                  const uint16_t *d_row_cnt, const unsigned long long *d_pair_ptr,
+                                  unsigned long long chunk_base, uint16_t *d_trans, int sm_count,
+                                  cudaStream_t st, int64_t *launches) {
+  const int wpr = (nx + 31) / 32;
+  const int64_t nrows = npairs * ny;
+  int64_t blocks = std::min<int64_t>((nrows + 7) / 8, (int64_t)sm_count * 16);
+  runs_write_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), 256, 0, st>>>(d_bits, nrows, ny, nx, wpr, d_row_cnt,
+                                                                           d_pair_ptr, chunk_base, d_trans);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }

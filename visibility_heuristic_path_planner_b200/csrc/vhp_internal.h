@@ -62,6 +62,17 @@ cudaError_t vhp_launch_pack_results(const void *d_in, int64_t nunits, int elem_b
 cudaError_t vhp_launch_threshold_bits(const double *d_vis, int64_t nrows, int nx, double thr,
                                       uint32_t *d_bits, int sm_count, cudaStream_t st, int64_t *launches);
 
+// thresholded binary visibility as row runs (result_transport.cu): transitions per row / pair, then
+// the transition columns themselves
+cudaError_t vhp_launch_runs_count(const uint32_t *d_bits, int64_t npairs, int ny, int nx, uint16_t *d_row_cnt,
+                                  uint32_t *d_pair_tot, unsigned long long base,
+                                  unsigned long long *d_pair_ptr, int sm_count, cudaStream_t st,
+                                  int64_t *launches);
+cudaError_t vhp_launch_runs_write(const uint32_t *d_bits, int64_t npairs, int ny, int nx,
+                                  const uint16_t *d_row_cnt, const unsigned long long *d_pair_ptr,
+                                  unsigned long long chunk_base, uint16_t *d_trans, int sm_count,
+                                  cudaStream_t st, int64_t *launches);
+
 // host threads that expand packed chunks into the caller's buffer (FIFO, each job is spread
 // over all threads)
 class VhpExpandPool {
