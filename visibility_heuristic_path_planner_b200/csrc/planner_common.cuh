@@ -80,7 +80,7 @@ __device__ __forceinline__ void epilogue_cell_loaded(const int X, const int Y, c
 __device__ __forceinline__ void epilogue_cell_first(const int X, const int Y, const size_t c,
                                                     const double v, const int sx, const int sy,
                                                     const int ex, const int ey, const double thr,
-                                                    const double scale, const int32_t *__restrict__ ls,
+                                                    const double scale, const int32_t *__restrict__,
                                                     double *vg, double *hc, int32_t *came, Best &best) {
   int cf = (X == sx && Y == sy) ? 0 : VHP_NO_PARENT; // the first source is the start cell
   double h = __longlong_as_double((long long)kHInf), g = 0.0;
@@ -88,10 +88,8 @@ __device__ __forceinline__ void epilogue_cell_first(const int X, const int Y, co
   if (visited && (v > 0.0 || thr <= 0.0)) {
     g = v > 0.0 ? v : 0.0; // std::max(v, 0)
     if (v >= thr && cf == VHP_NO_PARENT) cf = 0;
-    if (cf != VHP_NO_PARENT) {
-      const int px = __ldcg(ls), py = __ldcg(ls + 1);
-      h = __dadd_rn(__dmul_rn(scale, g), __dadd_rn(eval_d(X, Y, ex, ey), eval_d(X, Y, px, py)));
-    }
+    if (cf != VHP_NO_PARENT) // the parent is light source 0 = the start cell = this sweep's source
+      h = __dadd_rn(__dmul_rn(scale, g), __dadd_rn(eval_d(X, Y, ex, ey), eval_d(X, Y, sx, sy)));
   }
   vg[c] = g;
   came[c] = cf;
