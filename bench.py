@@ -823,6 +823,34 @@ def main():
 
         t_e2e, k_e2e, d2h_b, packed = e2e_run(1)   # the default (automatic) transport
         t_plain, _, d2h_plain, _ = e2e_run(0)      # plain copies, for comparison
+        # the same call into an ordinary (pageable) caller buffer: the literal units are staged
+        # through pinned memory and scattered by the host threads (bounded to 1024 pairs: the
+        # buffer is touched for the first time inside the warm-up call)
+        n_pg = min(n, 1024)
+        out_pg = np.empty((n_pg, ny, nx), dtype=np.float32 if args.store == "f32" else np.float64)
+        src_pg = np.ascontiguousarray(src[:n_pg])
+        smap_pg = None if smap is None else np.ascontiguousarray(smap[:n_pg])
+
+        def pg_step():
+            st = lib.vhp_visibility_batch(host_ctx.h, maps.ctypes.data, nmaps, nx, ny, src_pg.ctypes.data,
+                                          None if smap_pg is None else smap_pg.ctypes.data, n_pg, dt,
+                                          out_pg.ctypes.data)
+            assert st == 0, host_ctx.lib.vhp_last_error(host_ctx.h)
+        host_ctx.set_result_transport(1)
+        pg_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            pg_step()
+        t_pg = (time.perf_counter() - t0) / 2
+        if world > 1:
+            tt = torch.tensor([t_pg], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_pg = float(tt.item())
+        assert np.array_equal(out_pg[n_pg // 2], out_t[n_pg // 2].cpu().numpy())
+        pageable = {"value": n_pg * nx * ny * world / t_pg / 1e9, "unit": "Gcells/s", "pairs_per_gpu": int(n_pg),
+                    "ms_per_step": t_pg * 1e3, "transport": ["plain", "packed (staged literal stream)", "packed (direct)"][host_ctx.last_transport()[2]]}
+        del out_pg
         e2e = {"value": cells_e2e * world / t_e2e / 1e9, "unit": "Gcells/s",
                "pairs_per_gpu": int(n),
                "h2d_bytes_per_step": int(maps.nbytes + src.nbytes + (0 if smap is None else smap.nbytes)),
@@ -839,6 +867,7 @@ def main():
                             if packed else "plain",
                "plain_transport": {"value": cells_e2e * world / t_plain / 1e9, "ms_per_step": t_plain * 1e3,
                                    "d2h_bytes_per_step": int(d2h_plain)},
+               "pageable_buffer": pageable,
                "api": "vhp_visibility_batch (host buffers; pinned output; H2D + kernel + D2H (+ host expansion) "
                       "inside the timed region; %d result pairs compared with the device-resident run)" % len(probe)}
         # ---- the same call with the thresholded, bit-packed result (vhp_visibility_batch_bin)

@@ -44,6 +44,13 @@
 #include "planner_common.cuh"
 #include "sweep_tile_body.cuh"
 
+#ifndef VHP_FIRST_U
+#define VHP_FIRST_U 4 // cells in flight per lane in the first sweep's epilogue
+#endif
+#ifndef VHP_EPI_U
+#define VHP_EPI_U 4   // ... and in the later ones (four loads per cell)
+#endif
+
 namespace {
 
 struct PlannerParams {
@@ -118,7 +125,7 @@ __global__ void __launch_bounds__(NWK * 32, MINB) planner_kernel(const PlannerPa
       if (nb == 0) {
         // first sweep: the fields are still uninitialised workspace; nothing is loaded, everything
         // stored (reset() :42-60 and the first epilogue in one pass)
-        constexpr int kFirstU = 4; // cells in flight per lane
+        constexpr int kFirstU = VHP_FIRST_U; // cells in flight per lane
         for (int Y = warp; Y < ny; Y += NW) {
           const size_t row = (size_t)Y * nx;
           for (int X0 = lane; X0 < nx; X0 += 32 * kFirstU) {
@@ -134,7 +141,7 @@ __global__ void __launch_bounds__(NWK * 32, MINB) planner_kernel(const PlannerPa
           }
         }
       } else {
-        constexpr int kEpiU = 4;
+        constexpr int kEpiU = VHP_EPI_U;
         for (int Y = warp; Y < ny; Y += NW) {
           const size_t row = (size_t)Y * nx;
           for (int X0 = lane; X0 < nx; X0 += 32 * kEpiU) {
@@ -384,7 +391,7 @@ cudaError_t vhp_launch_planner(const VhpTilePlanes &pl, int nx, int ny, const in
     return e ? std::atoi(e) : 0;
   }();
   int nw = 8; // measured on the 1024 x 256^2 batch: 8 warps 240k solves/s, 4 warps 206k, 2 warps slower still
-  if (forced == 2 || forced == 4 || forced == 8 || forced == 12 || forced == 16) nw = forced;
+  if (forced == 2 || forced == 4 || forced == 6 || forced == 8) nw = forced;
   auto go = [&](auto kern, int nwarps) -> cudaError_t {
     const size_t smem = tile_smem_bytes<double>(nx, ny, nwarps);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -395,7 +402,6 @@ cudaError_t vhp_launch_planner(const VhpTilePlanes &pl, int nx, int ny, const in
   };
   if (nw == 2) return go(planner_kernel<2>, 2);
   if (nw == 4) return go(planner_kernel<4>, 4);
-  if (nw == 12) return go(planner_kernel<12, 2>, 12);  // 2 CTAs per SM: <= 80 registers
-  if (nw == 16) return go(planner_kernel<16, 2>, 16);  // 2 CTAs per SM: 64 registers
+  if (nw == 6) return go(planner_kernel<6, 3>, 6);     // 3 CTAs per SM: <= 112 registers
   return go(planner_kernel<8, 2>, 8);               // 2 CTAs per SM (<= 128 registers)
 }
