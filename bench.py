@@ -37,7 +37,7 @@ METRIC = "Gcells/s visibility sweep (1000² grid, batched sources)"
 
 
 # ----------------------------------------------------------------------------
-def workload(name, rank, world=1):
+def workload(name, rank, world=1, use_device=True):
     """Synthetic batch for one rank: (maps uint8 [nmaps,ny,nx], src_xy, src_map, desc)."""
     if name == "c2":
         from visibility_heuristic_path_planner_b200.sharding import shard_batch
@@ -84,23 +84,45 @@ def workload(name, rank, world=1):
         return maps, src, None, ("1000x1000 grid with 400 random rectangles of 8-40 cells (%.1f%% occupied), "
                                  "4096 free-cell light sources per GPU" % (100.0 * (1.0 - maps.mean())))
     if name == "c4":
+        # BASELINE configs[3]: 16384 random 256 x 256 obstacle maps x 16 sources over 8 GPUs = 2048 maps
+        # (32768 pairs) per GPU.  The maps are generated ON THE DEVICE where there is one
+        # (vhp_environment_generate_batch_dev: the reference's rectangle rule, src/environment.cpp:57-79,
+        # with counter-based draws; map index = global index of the map) and read back once to pick
+        # 16 free source cells per map.
         nx = ny = 256
-        nmaps, per = 1024, 16
+        nmaps, per = 2048, 16
         g = np.random.default_rng(4321 + rank)
-        maps = np.ones((nmaps, ny, nx), dtype=np.uint8)
-        for m in range(nmaps):
-            for _ in range(12):
-                x, y = int(g.integers(1, nx)), int(g.integers(1, ny))
-                w, h = int(g.integers(8, 41)), int(g.integers(8, 41))
-                maps[m, y:y + h, x:x + w] = 0
+        maps = None
+        try:
+            import torch
+            if use_device and torch.cuda.is_available():
+                import visibility_heuristic_path_planner_b200 as vhp
+                dev_i = int(os.environ.get("LOCAL_RANK", "0"))
+                c = vhp.Context(dev_i)
+                t = torch.empty((nmaps, ny, nx), dtype=torch.uint8, device=torch.device("cuda", dev_i))
+                c.generate_environments_dev(t, 12, 8, 40, 8, 40, seed=4321, first_map=rank * nmaps)
+                c.synchronize()
+                maps = t.cpu().numpy()
+                c.close()
+        except Exception:
+            maps = None
+        if maps is None:  # no GPU (the reference arm's config string only needs the shape)
+            maps = np.ones((nmaps, ny, nx), dtype=np.uint8)
+            for m in range(nmaps):
+                for _ in range(12):
+                    x, y = int(g.integers(1, nx)), int(g.integers(1, ny))
+                    w, h = int(g.integers(8, 41)), int(g.integers(8, 41))
+                    maps[m, y:y + h, x:x + w] = 0
         src = np.zeros((nmaps * per, 2), dtype=np.int32)
         smap = np.repeat(np.arange(nmaps, dtype=np.int32), per)
+        flat = maps.reshape(nmaps, -1) != 0
         for m in range(nmaps):
-            free = np.argwhere(maps[m] != 0)
+            free = np.flatnonzero(flat[m])
             pick = free[g.integers(0, len(free), per)]
-            src[m * per:(m + 1) * per, 0] = pick[:, 1]
-            src[m * per:(m + 1) * per, 1] = pick[:, 0]
-        return maps, src, smap, "1024 random 256x256 maps (12 rectangles 8-40) x 16 free-cell sources per GPU"
+            src[m * per:(m + 1) * per, 0] = pick % nx
+            src[m * per:(m + 1) * per, 1] = pick // nx
+        return maps, src, smap, ("2048 random 256x256 maps (12 rectangles 8-40, generated on the device) x 16 "
+                                 "free-cell sources per GPU")
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -233,7 +255,7 @@ def run_reference(args, rank, world):
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     from oracle_py import Oracle, Ref
-    maps, src, smap, desc = workload(args.workload, 0, max(1, args.gpus))
+    maps, src, smap, desc = workload(args.workload, 0, max(1, args.gpus), use_device=False)  # (no GPU code in this arm)
     ny, nx = maps.shape[1:]
     cores = os.cpu_count() or 1
     per_step = min(len(src), 16 * cores)
