@@ -22,12 +22,20 @@ def vhp():
     return m
 
 
-@pytest.fixture(scope="module", params=["cta", "grid"])
+@pytest.fixture(scope="module", params=["cta", "first", "grid"])
 def ctx(vhp, request):
-    """Every test runs on both planner routes: one persistent CTA per problem (batches), and
-    one problem at a time on the whole GPU (grid-mode sweep + strip epilogue + control kernels,
-    what large single problems take by default; forced here for every size)."""
+    """Every test runs on all planner routes: one persistent CTA per problem (batches); the same
+    with the first sweep of every problem done batch-wide before it (what batches of many problems
+    take by default; forced here for every size); and one problem at a time on the whole GPU
+    (grid-mode sweep + strip epilogue + control kernels, what large single problems take by default;
+    forced here for every size)."""
+    import os
+    if request.param == "first":
+        os.environ["VHP_PLANNER_FIRST"] = "2"
+        os.environ["VHP_PLANNER_ROUNDS"] = "3"
     c = vhp.Context(0)
+    os.environ.pop("VHP_PLANNER_FIRST", None)
+    os.environ.pop("VHP_PLANNER_ROUNDS", None)
     c.set_grid_sweep(2 if request.param == "grid" else 0)
     yield c
     c.close()

@@ -774,7 +774,7 @@ vhp_status planner_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx
                           (o.came ? 0 : 4 * cells) + 8 * cells; // + the cached heuristic field
   const size_t small_pp = 4 + 4 + 8 + 4 + 2 * (size_t)ls_cap * 8 + 32;
   int64_t chunk = nprob;
-  const size_t ws_limit = (size_t)8 << 30;
+  const size_t ws_limit = (size_t)32 << 30; // (of 180 GB: fewer chunks, fewer kernel tails)
   if (per_prob) chunk = std::max<int64_t>(1, std::min<int64_t>(nprob, (int64_t)(ws_limit / per_prob)));
   const size_t field_bytes = (size_t)chunk * per_prob;
   const size_t small_bytes = (size_t)nprob * small_pp;
@@ -838,11 +838,16 @@ vhp_status planner_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx
       }
       continue;
     }
+    void *first_ws = nullptr;
+    if (ctx->planner_first == 2 || (ctx->planner_first == 1 && n >= (int64_t)8 * ctx->sm_count)) {
+      if ((st = ensure(ctx, ctx->b_misc, vhp_planner_first_ws_bytes(n))) != VHP_OK) return st;
+      first_ws = ctx->b_misc.p;
+    }
     VHP_CUDA(ctx, vhp_launch_planner(ctx->tile, nx, ny, d_se + 4 * q0, d_pmap ? d_pmap + q0 : nullptr,
                                      n, thr, max_iter, ls_cap, ctx->rcp2_table, vis, vg, ws_hc, came,
                                      status + q0, nb + q0, ls + 2 * (size_t)ls_cap * q0, plen + q0,
                                      pn + q0, path + 2 * (size_t)ls_cap * q0, vg32, vis32,
-                                     ctx->d_err, ctx->stream, &ctx->launches));
+                                     ctx->d_err, ctx->stream, &ctx->launches, first_ws, ctx->planner_first_rounds));
   }
   return VHP_OK;
 }
@@ -925,6 +930,8 @@ vhp_status vhp_context_create(int device, void *cuda_stream, vhp_context **out) 
   ctx->sweep_impl = 0;
   if (impl && std::strcmp(impl, "naive") == 0) ctx->sweep_impl = 1;
   if (const char *e = std::getenv("VHP_GRID_SWEEP")) ctx->grid_sweep = std::atoi(e);
+  if (const char *e = std::getenv("VHP_PLANNER_FIRST")) ctx->planner_first = std::atoi(e);
+  if (const char *e = std::getenv("VHP_PLANNER_ROUNDS")) ctx->planner_first_rounds = std::max(1, std::atoi(e));
   for (int i = 0; i < vhp_context::kPackSets; ++i) {
     CTX_TRY(cudaEventCreate(&ctx->ev_pack_meta[i]));
     CTX_TRY(cudaEventCreate(&ctx->ev_pack_t0[i]));

@@ -67,6 +67,9 @@ struct PlannerParams {
   double *path_len;
   // optional fp32 exports of vg / vis (NULL: none)
   float *vg32, *vis32;
+  // non-null: the first sweep and its epilogue were done batch-wide (planner_first_* kernels below);
+  // resume[5q ..] = {done, next x, next y, status, nb_of_sources} of problem q after it
+  const int *resume;
 };
 
 // NWK warps per CTA: 8 by default, capped at 128 registers so that two CTAs share an SM (the
@@ -95,16 +98,22 @@ __global__ void __launch_bounds__(NWK * 32, MINB) planner_kernel(const PlannerPa
 
   // reset() (:42-60) happens inside the first sweep's epilogue (epilogue_cell_first)
   if (tid == 0) {
-    s_ctl[3] = planner_validate(rowbits, p.fp.pl.wx, nx, ny, stx, sty, ex, ey);
-    s_ctl[1] = stx;
-    s_ctl[2] = sty;
-    s_ctl[0] = 0;
+    if (p.resume) { // the state after the batch-wide first sweep
+      const int *r = p.resume + 5 * q;
+      s_ctl[0] = r[0]; s_ctl[1] = r[1]; s_ctl[2] = r[2]; s_ctl[3] = r[3]; s_ctl[4] = r[4];
+    } else {
+      s_ctl[3] = planner_validate(rowbits, p.fp.pl.wx, nx, ny, stx, sty, ex, ey);
+      s_ctl[1] = stx;
+      s_ctl[2] = sty;
+      s_ctl[0] = 0;
+      s_ctl[4] = 0;
+    }
   }
   __syncthreads();
   int status = s_ctl[3];
-  int nb = 0;
+  int nb = s_ctl[4];
   if (status == VHP_OK) {
-    if (tid == 0) {
+    if (tid == 0 && !p.resume) {
       ls[0] = stx; ls[1] = sty;                 // lightSources_[0] = start, :121
       // cameFrom_(start) = 0 (:122) is part of the first epilogue;
       // visibility_global_(end) = 0 (:123) holds after the reset; loop test :127
@@ -113,7 +122,7 @@ __global__ void __launch_bounds__(NWK * 32, MINB) planner_kernel(const PlannerPa
     __syncthreads();
     const double scale =
         __dsqrt_rn((double)((unsigned long long)ny * ny + (unsigned long long)nx * nx)); // :49
-    int sx = stx, sy = sty;
+    int sx = s_ctl[1], sy = s_ctl[2];
     bool done = s_ctl[0] != 0;
     while (!done) {
       // ---- 1. sweep (visibility_.reset() + the DP of updateVisibility)
@@ -230,6 +239,117 @@ __global__ void __launch_bounds__(NWK * 32, MINB) planner_kernel(const PlannerPa
       if (p.vis32) p.vis32[q * cells + c] = __double2float_rn(__ldcg(vis + c));
     }
   }
+}
+
+// ---- large batches: the FIRST sweep of every problem batch-wide ---------------------------------
+// A problem of bench.py's batch runs 1.8 sweeps on average, so more than half of all sweeps are
+// first sweeps.  Inside the persistent kernel a sweep and its epilogue are bound by latency at
+// 16 warps per SM; as one launch of the batched sweep kernel (K1: one single-warp CTA per problem,
+// 24 per SM) followed by one launch of the epilogue over all problems at full occupancy they run
+// near the instruction / HBM limits instead.  The persistent kernel then resumes every problem
+// from its second sweep.  Same device functions, same results.
+constexpr int kFirstSlabs = 8; // CTAs per problem in the batch-wide epilogue
+
+__global__ void planner_first_begin_kernel(const VhpTilePlanes pl, int nx, int ny, const int32_t *se_xy,
+                                           const int32_t *prob_map, double thr, int32_t *ls_all, int ls_cap,
+                                           int32_t *src_xy, int *ctl, int64_t nprob) {
+  const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (q >= nprob) return;
+  const int stx = se_xy[4 * q], sty = se_xy[4 * q + 1], ex = se_xy[4 * q + 2], ey = se_xy[4 * q + 3];
+  const int map = prob_map ? prob_map[q] : 0;
+  const int st = planner_validate(pl.rowF + (size_t)map * pl.row_plane, pl.wx, nx, ny, stx, sty, ex, ey);
+  int done = 1;
+  if (st == VHP_OK) {
+    int32_t *ls = ls_all + q * (size_t)ls_cap * 2;
+    ls[0] = stx; ls[1] = sty;   // lightSources_[0] = start, :121
+    done = !(0.0 <= thr);       // loop test :127 with visibility_global_(end) = 0 (:123)
+  }
+  src_xy[2 * q] = done ? kSkipPair : stx;
+  src_xy[2 * q + 1] = sty;
+  int *c = ctl + 5 * q;
+  c[0] = done; c[1] = stx; c[2] = sty; c[3] = st; c[4] = 0;
+}
+
+struct FirstEpilogueParams {
+  int nx, ny, ls_cap;
+  double thr, scale;
+  const int32_t *se_xy, *ls;
+  const int *ctl;
+  const double *vis;
+  double *vg, *hc;
+  int32_t *came;
+  Best *partial; // [problem][kFirstSlabs]
+};
+
+template <bool FIRST>
+__global__ void __launch_bounds__(256) planner_first_epilogue_kernel(const FirstEpilogueParams p) {
+  __shared__ Best s_best[8];
+  const int64_t q = blockIdx.x / kFirstSlabs;
+  const int slab = blockIdx.x % kFirstSlabs;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (p.ctl[5 * q]) return; // no sweep ran for this problem
+  const size_t cells = (size_t)p.nx * p.ny;
+  const int sx = p.ctl[5 * q + 1], sy = p.ctl[5 * q + 2], nb = p.ctl[5 * q + 4]; // the sweep's source
+  const int ex = p.se_xy[4 * q + 2], ey = p.se_xy[4 * q + 3];
+  const double *vis = p.vis + q * cells;
+  double *vg = p.vg + q * cells, *hc = p.hc + q * cells;
+  int32_t *came = p.came + q * cells;
+  const int32_t *ls = p.ls + q * (size_t)p.ls_cap * 2;
+  const int rows = (p.ny + kFirstSlabs - 1) / kFirstSlabs;
+  const int y0 = slab * rows, y1 = min(p.ny, y0 + rows);
+  Best best{~0ull, ~0ull};
+  constexpr int kU = 4;
+  for (int Y = y0 + warp; Y < y1; Y += 8) {
+    const size_t row = (size_t)Y * p.nx;
+    for (int X0 = lane; X0 < p.nx; X0 += 32 * kU) {
+      double v[kU], h[kU], g0[kU];
+      int cf[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        if (X0 + 32 * u < p.nx) {
+          const size_t c = row + X0 + 32 * u;
+          v[u] = __ldcs(vis + c);
+          if (!FIRST) { h[u] = __ldcg(hc + c); g0[u] = __ldcg(vg + c); cf[u] = __ldcg(came + c); }
+        }
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        if (X0 + 32 * u < p.nx) {
+          const int X = X0 + 32 * u;
+          if (FIRST)
+            epilogue_cell_first(X, Y, row + X, v[u], sx, sy, ex, ey, p.thr, p.scale, ls, vg, hc, came, best);
+          else
+            epilogue_cell_loaded(X, Y, row + X, v[u], h[u], g0[u], cf[u], sx, sy, ex, ey, p.thr, p.scale, nb, ls, vg,
+                                 hc, came, best);
+        }
+    }
+  }
+  best = warp_best(best);
+  if (lane == 0) s_best[warp] = best;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    Best b = threadIdx.x < 8 ? s_best[threadIdx.x] : Best{~0ull, ~0ull};
+    b = warp_best(b);
+    if (threadIdx.x == 0) p.partial[q * kFirstSlabs + slab] = b;
+  }
+}
+
+__global__ void planner_first_step_kernel(const Best *partial, int nx, const int32_t *se_xy, double thr,
+                                          int max_iter, const double *vg_all, size_t cells, int32_t *ls_all,
+                                          int ls_cap, int *ctl, int32_t *src_xy, int64_t nprob) {
+  const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (q >= nprob) return;
+  int *c = ctl + 5 * q;
+  if (c[0]) return;
+  Best b{~0ull, ~0ull};
+  for (int s = 0; s < kFirstSlabs; ++s)
+    if (better(partial[q * kFirstSlabs + s], b)) b = partial[q * kFirstSlabs + s];
+  const int ex = se_xy[4 * q + 2], ey = se_xy[4 * q + 3];
+  int tx, ty, d, st = c[3];
+  const int nnb = planner_next_source(b, c[1], c[2], c[4], max_iter, thr, __ldcg(vg_all + q * cells + (size_t)ey * nx + ex),
+                                      ls_all + q * (size_t)ls_cap * 2, tx, ty, d, st);
+  c[0] = d; c[1] = tx; c[2] = ty; c[3] = st; c[4] = nnb;
+  src_xy[2 * q] = d ? kSkipPair : tx; // the next batch-wide sweep, if any, starts from the new source
+  src_xy[2 * q + 1] = ty;
 }
 
 // ---- strip epilogue (giant-map path): the same per-cell epilogue over the rows
@@ -356,6 +476,11 @@ cudaError_t vhp_launch_strip_epilogue(int nx, int ny, int y0, int y1, int sx, in
 
 bool vhp_planner_supported(int nx, int ny) { return vhp_sweep_tile_supported(nx, ny); }
 
+size_t vhp_planner_first_ws_bytes(int64_t nprob) {
+  return (((size_t)nprob * 8 + 255) & ~(size_t)255) + (((size_t)nprob * 20 + 255) & ~(size_t)255) +
+         (size_t)nprob * kFirstSlabs * sizeof(Best) + 256;
+}
+
 cudaError_t vhp_launch_planner(const VhpTilePlanes &pl, int nx, int ny, const int32_t *d_se_xy,
                                const int32_t *d_prob_map, int64_t nprob, double threshold,
                                int32_t max_iter, int32_t ls_cap, const double *d_rcp2,
@@ -363,8 +488,36 @@ cudaError_t vhp_launch_planner(const VhpTilePlanes &pl, int nx, int ny, const in
                                int32_t *d_status,
                                int32_t *d_nb, int32_t *d_ls, double *d_path_len, int32_t *d_path_n,
                                int32_t *d_path, float *d_vg32, float *d_vis32, int *d_err,
-                               cudaStream_t st, int64_t *launches) {
+                               cudaStream_t st, int64_t *launches, void *d_first_ws, int first_rounds) {
   if (!vhp_sweep_tile_supported(nx, ny)) return cudaErrorInvalidConfiguration;
+  // large batches: every problem's first sweep and epilogue batch-wide (see planner_first_* above)
+  const int *resume = nullptr;
+  if (d_first_ws) {
+    char *w = static_cast<char *>(d_first_ws);
+    int32_t *src = reinterpret_cast<int32_t *>(w);
+    int *ctl = reinterpret_cast<int *>(w + (((size_t)nprob * 8 + 255) & ~(size_t)255));
+    Best *partial = reinterpret_cast<Best *>(reinterpret_cast<char *>(ctl) + (((size_t)nprob * 20 + 255) & ~(size_t)255));
+    const unsigned nb1 = (unsigned)((nprob + 255) / 256);
+    planner_first_begin_kernel<<<nb1, 256, 0, st>>>(pl, nx, ny, d_se_xy, d_prob_map, threshold, d_ls, ls_cap, src, ctl, nprob);
+    FirstEpilogueParams f;
+    f.nx = nx; f.ny = ny; f.ls_cap = ls_cap; f.thr = threshold;
+    f.scale = std::sqrt((double)((unsigned long long)ny * ny + (unsigned long long)nx * nx)); // :49
+    f.se_xy = d_se_xy; f.ls = d_ls; f.ctl = ctl; f.vis = d_vis; f.vg = d_vg; f.hc = d_hc; f.came = d_came;
+    f.partial = partial;
+    for (int round = 0; round < std::max(1, first_rounds); ++round) {
+      cudaError_t e = vhp_launch_sweep_tile(pl, nx, ny, src, d_prob_map, nprob, VHP_F64, d_vis, d_rcp2, d_err, st, launches);
+      if (e != cudaSuccess) return e;
+      if (round == 0) planner_first_epilogue_kernel<true><<<(unsigned)(nprob * kFirstSlabs), 256, 0, st>>>(f);
+      else planner_first_epilogue_kernel<false><<<(unsigned)(nprob * kFirstSlabs), 256, 0, st>>>(f);
+      planner_first_step_kernel<<<nb1, 256, 0, st>>>(partial, nx, d_se_xy, threshold, max_iter, d_vg, (size_t)nx * ny,
+                                                     d_ls, ls_cap, ctl, src, nprob);
+      if (launches) *launches += 2;
+    }
+    if (launches) *launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    resume = ctl;
+  }
   PlannerParams p;
   p.fp.pl = pl;
   p.fp.nx = nx; p.fp.ny = ny;
@@ -386,6 +539,7 @@ cudaError_t vhp_launch_planner(const VhpTilePlanes &pl, int nx, int ny, const in
   p.status = d_status; p.nb = d_nb; p.ls = d_ls;
   p.path_len = d_path_len; p.path_n = d_path_n; p.path = d_path;
   p.vg32 = d_vg32; p.vis32 = d_vis32;
+  p.resume = resume;
   static const int forced = [] {
     const char *e = std::getenv("VHP_PLANNER_WARPS");
     return e ? std::atoi(e) : 0;

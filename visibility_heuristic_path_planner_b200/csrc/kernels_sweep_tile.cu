@@ -26,6 +26,7 @@ sweep_tile_kernel(const TileArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int64_t pair = blockIdx.x;
   const int sx = __ldg(p.src_xy + 2 * pair), sy = __ldg(p.src_xy + 2 * pair + 1);
+  if (sx == kSkipPair) return; // "no sweep for this item" (the planner's first batched sweep)
   if ((unsigned)sx >= (unsigned)p.nx || (unsigned)sy >= (unsigned)p.ny) { // uniform over the CTA
     if (threadIdx.x == 0) atomicOr(p.err, 1);
     return;

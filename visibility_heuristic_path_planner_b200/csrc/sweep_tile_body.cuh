@@ -108,6 +108,7 @@
 
 namespace {
 
+constexpr int kSkipPair = -0x7fffffff - 1; // source x of a pair the batched kernel leaves alone
 constexpr int kDiagUnroll = VHP_DIAG_UNROLL, kFillUnroll = VHP_FILL_UNROLL;
 constexpr int kTileWarps = 8;          // warps per CTA (default; small maps use fewer)
 constexpr int kTile = 32;              // tile side

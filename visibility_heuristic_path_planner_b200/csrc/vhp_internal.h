@@ -119,6 +119,11 @@ struct vhp_context {
   int sweep_impl = 0;
   // strip sweeps over many CTAs: 0 never, 1 for windows of >= 2^20 cells, 2 always
   int grid_sweep = 1;
+  // planner batches: first sweep of every problem batch-wide (0 never, 1 from 4 waves of problems on
+  // (default), 2 always; env VHP_PLANNER_FIRST)
+  int planner_first = 1;
+  int planner_first_rounds = 1; // sweeps per problem done batch-wide (env VHP_PLANNER_ROUNDS; measured: 1 is
+                                // fastest -- later rounds have too few active problems for whole-batch launches)
   // packed result transport of the host-buffer entry points: 0 plain D2H, 1 automatic
   // (packed when the results compress), 2 always packed (env VHP_RESULT_TRANSPORT)
   int result_transport = 1;
@@ -257,6 +262,10 @@ cudaError_t vhp_launch_planner(const VhpTilePlanes &pl, int nx, int ny, const in
                                int32_t *d_status,
                                int32_t *d_nb, int32_t *d_ls, double *d_path_len, int32_t *d_path_n,
                                int32_t *d_path, float *d_vg32, float *d_vis32, int *d_err,
-                               cudaStream_t st, int64_t *launches);
+                               cudaStream_t st, int64_t *launches, void *d_first_ws = nullptr,
+                               int first_rounds = 1);
+// d_first_ws (vhp_planner_first_ws_bytes(nprob) bytes): run every problem's first sweep and epilogue
+// batch-wide before the persistent kernel (worth it from a few waves of problems on)
+size_t vhp_planner_first_ws_bytes(int64_t nprob);
 
 #endif
