@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from bench import kernel_source_hash  # noqa: E402
 
-PAIRS = {"c2": 1184, "c2s": 1184, "c2d": 1184, "c4": 16384}
+PAIRS = {"c2": 1184, "c2s": 1184, "c2d": 1184, "c4": 32768}
 
 
 def main():
