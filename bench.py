@@ -932,9 +932,10 @@ def main():
                          "steps": kb, "threshold": thr_bin,
                          "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],
                          "d2h_bytes_per_step": int(n) * ny * wpr * 4,
-                         "api": "vhp_visibility_batch_bin (host buffers, pinned output): H2D, fp64 sweeps, threshold + "
-                                "bit packing on the device, D2H of 1 bit per cell, all inside the timed region; bit-exact "
-                                "against the fp64 field compared with >= threshold (tests/test_gpu_sweep.py)"}
+                         "api": "vhp_visibility_batch_bin (host buffers, pinned output): H2D, sweeps that compare in fp64 "
+                                "and write bits themselves (the field is never stored), D2H of 1 bit per cell, all inside "
+                                "the timed region; bit-exact against the fp64 field compared with >= threshold "
+                                "(tests/test_gpu_sweep.py)"}
         del bits_h
         # ---- ... and as row runs (vhp_visibility_batch_runs): transition columns per row
         rc_h = torch.empty((n, ny), dtype=torch.int16, pin_memory=True)
@@ -970,9 +971,10 @@ def main():
         e2e["runs"] = {"value": cells_e2e * world / t_runs / 1e9, "unit": "Gcells/s", "ms_per_step": t_runs * 1e3,
                        "steps": kb, "threshold": thr_bin, "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],
                        "d2h_bytes_per_step": int(d2h_runs), "transition_columns": int(pp_np[n]),
-                       "api": "vhp_visibility_batch_runs (host buffers, pinned outputs): H2D, fp64 sweeps, threshold + run "
-                              "encoding on the device (transition columns per row), D2H, all inside the timed region; "
-                              "bit-exact against the fp64 field compared with >= threshold (tests/test_gpu_sweep.py)"}
+                       "api": "vhp_visibility_batch_runs (host buffers, pinned outputs): H2D, sweeps that write bits "
+                              "themselves, run encoding on the device (transition columns per row), D2H, all inside the "
+                              "timed region; bit-exact against the fp64 field compared with >= threshold "
+                              "(tests/test_gpu_sweep.py)"}
         del rc_h, pp_h, tr_h
         n, src, smap = n_full, src_full, smap_full
 

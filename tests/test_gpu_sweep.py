@@ -287,6 +287,89 @@ def test_sweep_variants_equal_oracle(vhp, oracle):
     c.close()
 
 
+def test_binary_thresholds_on_field_values(vhp, oracle, monkeypatch):
+    """The binary outputs come from sweeps that write bits themselves (csrc/sweep_tile_body.cuh
+    kFmtBits, fp64 compare in the kernel): the bits must equal (fp64 value >= threshold) when the
+    threshold IS a value of the field, its fp64 neighbours, its fp32 roundings and their neighbours
+    -- where an fp32 round trip would flip -- and for thresholds <= 0, > 1, huge and denormal.  The
+    fp64-field route (VHP_BIN_DIRECT=0: sweep, then threshold pass) gives the same bits."""
+    rng = np.random.default_rng(23)
+    nx, ny = 150, 117
+    occ = np.stack([rect_map(nx, ny, 12, 40 + k, 3, 16) for k in range(2)])
+    n = 6
+    smap = rng.integers(0, 2, n).astype(np.int32)
+    src = np.stack([rng.integers(0, nx, n), rng.integers(0, ny, n)], 1).astype(np.int32)
+    ref = np.stack([oracle.compute_visibility(occ[m], sx, sy) for (sx, sy), m in zip(src, smap)])
+    vals = np.unique(ref[(ref > 0) & (ref < 1)])
+    assert len(vals) > 100
+    pick = rng.choice(vals, 12, replace=False)
+    thrs = []
+    for v in pick:
+        f = np.float64(np.float32(v))
+        thrs += [v, np.nextafter(v, 2.0), np.nextafter(v, -1.0), f,
+                 np.float64(np.nextafter(np.float32(v), np.float32(2))),
+                 np.float64(np.nextafter(np.float32(v), np.float32(-1)))]
+    thrs += [-1.0, 2.0, -1e300, 1e300, np.inf, 1e-310, 5e-324]
+    c = vhp.Context(0)
+    monkeypatch.setenv("VHP_BIN_DIRECT", "0")
+    c64 = vhp.Context(0)
+    monkeypatch.delenv("VHP_BIN_DIRECT")
+    for i, thr in enumerate(thrs):
+        want = ref >= thr
+        got = vhp.unpack_bits(c.visibility_batch_bin(occ, src, float(thr), src_map=smap), nx)
+        assert np.array_equal(got, want), (i, thr)
+        if i % 6 == 0:
+            assert np.array_equal(vhp.unpack_bits(c64.visibility_batch_bin(occ, src, float(thr), src_map=smap), nx), want)
+            rc, pp, tr = c.visibility_batch_runs(occ, src, float(thr), src_map=smap)
+            assert np.array_equal(vhp.unpack_bits(vhp.runs_to_bits(rc, pp, tr, nx), nx), want)
+    c.close(); c64.close()
+
+
+@pytest.mark.parametrize("n", [400, 2500])  # 4-warp and single-warp CTAs (12 pairs above: 8 warps)
+def test_binary_direct_all_warp_counts(vhp, n):
+    """The bit-writing sweep at the batch sizes that select the 4-warp and the 1-warp kernels, with
+    sources on word boundaries, corners and edges: equal to the fp64 field of the same library
+    (itself bit-exact against the oracle at these batch sizes) compared with >= threshold."""
+    rng = np.random.default_rng(n)
+    c = vhp.Context(0)
+    for nx, ny, nobs in ((101, 101, 10), (64, 50, 5), (97, 130, 0), (33, 32, 1), (160, 45, 12)):
+        occ = np.stack([rect_map(nx, ny, nobs, 90 + k, 3, 14) for k in range(4)])
+        smap = rng.integers(0, 4, n).astype(np.int32)
+        src = np.stack([rng.integers(0, nx, n), rng.integers(0, ny, n)], 1).astype(np.int32)
+        special = [(0, 0), (nx - 1, ny - 1), (0, ny - 1), (nx - 1, 0), (31, 5), (32, 5), (33, 31), (63 % nx, 32 % ny),
+                   (64 % nx, 0), (nx // 2, 0), (0, ny // 2), (nx - 1, ny // 2), (nx // 2, ny - 1)]
+        src[: len(special)] = [(min(x, nx - 1), min(y, ny - 1)) for x, y in special]
+        field = c.visibility_batch(occ, src, src_map=smap, dtype=vhp.F64)
+        for thr in (0.5, 1.0, 1e-9, 0.9999999999):
+            bits = c.visibility_batch_bin(occ, src, thr, src_map=smap)
+            got = vhp.unpack_bits(bits, nx)
+            bad = np.argwhere(got != (field >= thr))
+            assert len(bad) == 0, (nx, ny, thr, bad[:5], src[bad[0][0]])
+            assert not np.unpackbits(bits.view(np.uint8), axis=-1, bitorder="little")[..., nx:].any()
+        rc, pp, tr = c.visibility_batch_runs(occ, src, 0.5, src_map=smap)
+        assert np.array_equal(vhp.runs_to_bits(rc, pp, tr, nx), c.visibility_batch_bin(occ, src, 0.5, src_map=smap))
+    c.close()
+
+
+def test_binary_direct_large_maps(vhp):
+    """Bit-writing sweeps of 1000 x 1000 and 1333 x 777 maps with many obstacles (dark runs, every tile
+    kind) and of free maps (all lit), against the fp64 field; 3 pairs of the large map take the
+    grid-mode route (fp64 field + threshold pass) and must agree too."""
+    rng = np.random.default_rng(77)
+    c = vhp.Context(0)
+    for nx, ny, nobs, n in ((1000, 1000, 120, 24), (1333, 777, 60, 20), (1000, 1000, 0, 20), (1000, 1000, 40, 3)):
+        occ = rect_map(nx, ny, nobs, 5, 10, 60)[None]
+        src = np.stack([rng.integers(0, nx, n), rng.integers(0, ny, n)], 1).astype(np.int32)
+        src[0] = (nx // 2, ny // 2)
+        field = c.visibility_batch(occ, src, dtype=vhp.F64)
+        for thr in (0.5, 0.05):
+            bits = c.visibility_batch_bin(occ, src, thr)
+            assert np.array_equal(vhp.unpack_bits(bits, nx), field >= thr), (nx, ny, nobs, thr)
+            rc, pp, tr = c.visibility_batch_runs(occ, src, thr)
+            assert np.array_equal(vhp.runs_to_bits(rc, pp, tr, nx), bits)
+    c.close()
+
+
 def test_row_runs_bit_exact(vhp, oracle):
     """vhp_visibility_batch_runs: the thresholded visibility as transition columns per row, equal to
     the bit form and to the oracle's fp64 field compared with >= threshold; widths that fill their

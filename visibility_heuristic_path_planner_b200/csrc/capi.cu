@@ -536,21 +536,52 @@ int64_t bin_chunk_pairs(size_t cells, int64_t n) {
   return std::min<int64_t>(n, std::max<int64_t>(1, (int64_t)(((size_t)4 << 30) / (cells * 8))));
 }
 
+// Thresholded visibility of np pairs as bits (and, d_row_cnt != null, transition columns per row).
+// Batches the one-CTA tile kernel takes are swept straight into bits (kFmtBits: the field itself is
+// never stored); a non-positive threshold, a few pairs of a large map (grid mode) and the naive
+// kernel go through the fp64 field in ctx->b_bin (at most bin_chunk_pairs pairs).
+bool sweeps_into_bits(const vhp_context *ctx, int nx, int ny, int64_t np, double thr) {
+  const size_t cells = (size_t)nx * ny;
+  return ctx->sweep_impl == 0 && ctx->bin_direct && thr > 0.0 && vhp_sweep_tile_supported(nx, ny) &&
+         !(ctx->grid_sweep == 2 && vhp_sweep_grid_supported(nx, ny)) &&
+         !(ctx->grid_sweep == 1 && vhp_sweep_grid_supported(nx, ny) &&
+           np <= std::min<int64_t>(16, (int64_t)(cells / 250000)));
+}
+
+vhp_status sweep_to_bits(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx, int ny,
+                         const int32_t *d_xy, const int32_t *d_map, int64_t np, double thr,
+                         uint32_t *d_bits, uint16_t *d_row_cnt = nullptr) {
+  if (sweeps_into_bits(ctx, nx, ny, np, thr)) {
+    vhp_status st = ensure_rcp2(ctx, std::max(nx, ny) + 64);
+    if (st != VHP_OK) return st;
+    if ((st = pack_tile(ctx, d_occ, nmaps, nx, ny, false)) != VHP_OK) return st;
+    VHP_CUDA(ctx, vhp_launch_sweep_tile(ctx->tile, nx, ny, d_xy, d_map, np, VHP_F32, d_bits, ctx->rcp2_table,
+                                        ctx->d_err, ctx->stream, &ctx->launches, &thr, true));
+    if (d_row_cnt)
+      VHP_CUDA(ctx, vhp_launch_runs_row_count(d_bits, np * ny, nx, d_row_cnt, ctx->sm_count, ctx->stream,
+                                              &ctx->launches));
+    return VHP_OK;
+  }
+  vhp_status st = ensure(ctx, ctx->b_bin, (size_t)np * nx * ny * 8);
+  if (st != VHP_OK) return st;
+  if ((st = run_dev(ctx, Op::Sweep, d_occ, nmaps, nx, ny, d_xy, d_map, np, VHP_F64, ctx->b_bin.p)) != VHP_OK)
+    return st;
+  VHP_CUDA(ctx, vhp_launch_threshold_bits((const double *)ctx->b_bin.p, np * ny, nx, thr, d_bits,
+                                          ctx->sm_count, ctx->stream, &ctx->launches, d_row_cnt));
+  return VHP_OK;
+}
+
 vhp_status run_bin_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx, int ny,
                        const int32_t *d_xy, const int32_t *d_map, int64_t n, double thr,
                        uint32_t *d_bits) {
   const size_t cells = (size_t)nx * ny, wpr = (size_t)(nx + 31) / 32;
   const int64_t chunk = bin_chunk_pairs(cells, n);
-  vhp_status st = ensure(ctx, ctx->b_bin, (size_t)chunk * cells * 8);
-  if (st != VHP_OK) return st;
+  vhp_status st;
   for (int64_t p0 = 0; p0 < n; p0 += chunk) {
     const int64_t np = std::min(chunk, n - p0);
-    st = run_dev(ctx, Op::Sweep, d_occ, nmaps, nx, ny, d_xy + 2 * p0, d_map ? d_map + p0 : nullptr, np,
-                 VHP_F64, ctx->b_bin.p);
+    st = sweep_to_bits(ctx, d_occ, nmaps, nx, ny, d_xy + 2 * p0, d_map ? d_map + p0 : nullptr, np, thr,
+                       d_bits + (size_t)p0 * ny * wpr);
     if (st != VHP_OK) return st;
-    VHP_CUDA(ctx, vhp_launch_threshold_bits((const double *)ctx->b_bin.p, np * ny, nx, thr,
-                                            d_bits + (size_t)p0 * ny * wpr, ctx->sm_count, ctx->stream,
-                                            &ctx->launches));
   }
   return VHP_OK;
 }
@@ -582,7 +613,7 @@ vhp_status run_bin_host(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx,
   const int32_t *d_map = maps ? (const int32_t *)ctx->b_map.p : nullptr;
   const int64_t chunk = bin_chunk_pairs(cells, n);
   const size_t pair_words = (size_t)ny * wpr, chunk_bytes = (size_t)chunk * pair_words * 4;
-  vhp_status result = ensure(ctx, ctx->b_bin, (size_t)chunk * cells * 8);
+  vhp_status result = VHP_OK;
   for (int b = 0; b < 2 && result == VHP_OK; ++b)
     if (b == 0 || n > chunk) result = ensure(ctx, ctx->b_out[b], chunk_bytes);
   int it = 0;
@@ -592,12 +623,10 @@ vhp_status run_bin_host(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx,
     cudaError_t e = cudaSuccess;
     if (it >= 2) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0); // bit buffer b is free again
     if (e != cudaSuccess) { result = cuda_fail(ctx, e, "cudaStreamWaitEvent"); break; }
-    result = run_dev(ctx, Op::Sweep, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, d_xy + 2 * p0,
-                     d_map ? d_map + p0 : nullptr, np, VHP_F64, ctx->b_bin.p);
+    result = sweep_to_bits(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, d_xy + 2 * p0,
+                           d_map ? d_map + p0 : nullptr, np, thr, (uint32_t *)ctx->b_out[b].p);
     if (result != VHP_OK) break;
-    e = vhp_launch_threshold_bits((const double *)ctx->b_bin.p, np * ny, nx, thr, (uint32_t *)ctx->b_out[b].p,
-                                  ctx->sm_count, ctx->stream, &ctx->launches);
-    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_done[b], ctx->stream);
+    e = cudaEventRecord(ctx->ev_done[b], ctx->stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0);
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(out_bits + (size_t)p0 * pair_words, ctx->b_out[b].p, (size_t)np * pair_words * 4,
@@ -650,28 +679,28 @@ vhp_status run_runs_host(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx
   }
   const int32_t *d_xy = (const int32_t *)ctx->b_src.p;
   const int32_t *d_map = maps ? (const int32_t *)ctx->b_map.p : nullptr;
-  const int64_t chunk = bin_chunk_pairs(cells, n);
-  vhp_status result = ensure(ctx, ctx->b_bin, (size_t)chunk * cells * 8);
-  if (result == VHP_OK) result = ensure(ctx, ctx->b_out[0], (size_t)chunk * ny * wpr * 4);
-  // small per-chunk arrays: row counts, pair totals, pair offsets
-  const size_t o_cnt = 0, o_tot = ((size_t)chunk * ny * 2 + 255) & ~(size_t)255;
+  // the sweep writes bits itself: a chunk is bounded by its bits (1 GB), not by an fp64 field
+  const int64_t chunk = sweeps_into_bits(ctx, nx, ny, n, thr)
+                            ? std::min<int64_t>(n, std::max<int64_t>(1, (int64_t)(((size_t)1 << 30) / ((size_t)ny * wpr * 4))))
+                            : bin_chunk_pairs(cells, n);
+  vhp_status result = ensure(ctx, ctx->b_out[0], (size_t)chunk * ny * wpr * 4);
+  // small per-chunk arrays: row counts, row offsets, pair totals, pair offsets
+  const size_t o_cnt = 0, o_off = ((size_t)chunk * ny * 2 + 255) & ~(size_t)255;
+  const size_t o_tot = o_off + (((size_t)chunk * ny * 4 + 255) & ~(size_t)255);
   const size_t o_ptr = o_tot + (((size_t)chunk * 4 + 255) & ~(size_t)255);
   if (result == VHP_OK) result = ensure(ctx, ctx->b_misc, o_ptr + ((size_t)chunk + 1) * 8 + 256);
   unsigned long long total = 0;
   for (int64_t p0 = 0; p0 < n && result == VHP_OK; p0 += chunk) {
     const int64_t np = std::min(chunk, n - p0);
-    result = run_dev(ctx, Op::Sweep, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, d_xy + 2 * p0,
-                     d_map ? d_map + p0 : nullptr, np, VHP_F64, ctx->b_bin.p);
-    if (result != VHP_OK) break;
     char *misc = (char *)ctx->b_misc.p;
     uint16_t *d_cnt = (uint16_t *)(misc + o_cnt);
+    uint32_t *d_off = (uint32_t *)(misc + o_off);
     uint32_t *d_tot = (uint32_t *)(misc + o_tot);
+    result = sweep_to_bits(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, d_xy + 2 * p0,
+                           d_map ? d_map + p0 : nullptr, np, thr, (uint32_t *)ctx->b_out[0].p, d_cnt);
+    if (result != VHP_OK) break;
     unsigned long long *d_ptr = (unsigned long long *)(misc + o_ptr);
-    cudaError_t e = vhp_launch_threshold_bits((const double *)ctx->b_bin.p, np * ny, nx, thr, (uint32_t *)ctx->b_out[0].p,
-                                              ctx->sm_count, ctx->stream, &ctx->launches);
-    if (e == cudaSuccess)
-      e = vhp_launch_runs_count((const uint32_t *)ctx->b_out[0].p, np, ny, nx, d_cnt, d_tot, total, d_ptr,
-                                ctx->sm_count, ctx->stream, &ctx->launches);
+    cudaError_t e = vhp_launch_runs_count(d_cnt, np, ny, d_off, d_tot, total, d_ptr, ctx->stream, &ctx->launches);
     unsigned long long new_total = 0;
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(&new_total, d_ptr + np, 8, cudaMemcpyDeviceToHost, ctx->stream);
@@ -684,7 +713,7 @@ vhp_status run_runs_host(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx
     }
     const size_t chunk_elems = (size_t)(new_total - total);
     if ((result = ensure(ctx, ctx->b_out[1], std::max<size_t>(chunk_elems * 2, 256))) != VHP_OK) break;
-    e = vhp_launch_runs_write((const uint32_t *)ctx->b_out[0].p, np, ny, nx, d_cnt, d_ptr, total,
+    e = vhp_launch_runs_write((const uint32_t *)ctx->b_out[0].p, np, ny, nx, d_off, d_ptr, total,
                               (uint16_t *)ctx->b_out[1].p, ctx->sm_count, ctx->stream, &ctx->launches);
     if (e == cudaSuccess && chunk_elems)
       e = cudaMemcpyAsync(trans + total, ctx->b_out[1].p, chunk_elems * 2, cudaMemcpyDeviceToHost, ctx->stream);
@@ -931,6 +960,7 @@ vhp_status vhp_context_create(int device, void *cuda_stream, vhp_context **out) 
   if (impl && std::strcmp(impl, "naive") == 0) ctx->sweep_impl = 1;
   if (const char *e = std::getenv("VHP_GRID_SWEEP")) ctx->grid_sweep = std::atoi(e);
   if (const char *e = std::getenv("VHP_PLANNER_FIRST")) ctx->planner_first = std::atoi(e);
+  if (const char *e = std::getenv("VHP_BIN_DIRECT")) ctx->bin_direct = std::atoi(e) != 0;
   if (const char *e = std::getenv("VHP_PLANNER_ROUNDS")) ctx->planner_first_rounds = std::max(1, std::atoi(e));
   for (int i = 0; i < vhp_context::kPackSets; ++i) {
     CTX_TRY(cudaEventCreate(&ctx->ev_pack_meta[i]));

@@ -532,6 +532,7 @@ cudaError_t vhp_launch_planner(const VhpTilePlanes &pl, int nx, int ny, const in
   p.fp.g_lm = p.fp.g_prog = p.fp.g_next_row = nullptr;
   p.fp.qmask = 0xF;
   p.fp.x_edges = nullptr; p.fp.x_prog = nullptr; p.fp.x_y0 = p.fp.x_y1 = 0; p.fp.remote_mask = 0;
+  p.fp.thr = 0.0;
   p.fp.src_ctl = nullptr;
   p.se_xy = d_se_xy; p.prob_map = d_prob_map;
   p.thr = threshold; p.max_iter = max_iter; p.ls_cap = ls_cap;

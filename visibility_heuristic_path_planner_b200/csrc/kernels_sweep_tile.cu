@@ -20,7 +20,7 @@ namespace {
 // memory, so few CTAs fit an SM and each must bring its own parallelism); small maps use 4,
 // or 1 when the batch alone fills the machine (32 independent single-warp CTAs per SM: no
 // flag polling, no imbalance between the warps of a pair).
-template <typename OutT, int NW, int MINB>
+template <typename OutT, int NW, int MINB, int FMT = kFmtValues>
 __global__ void __launch_bounds__(NW * 32, MINB)
 sweep_tile_kernel(const TileArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -32,8 +32,10 @@ sweep_tile_kernel(const TileArgs p) {
     return;
   }
   const int map = p.src_map ? __ldg(p.src_map + pair) : 0;
-  OutT *out = reinterpret_cast<OutT *>(p.out) + (size_t)pair * p.nx * p.ny;
-  tile_sweep_cta<OutT, NW>(p, map, sx, sy, out, smem_raw);
+  // bit output: rows of (nx + 31) / 32 words
+  const size_t per_pair = FMT == kFmtBits ? (size_t)((p.nx + 31) >> 5) * p.ny : (size_t)p.nx * p.ny;
+  OutT *out = reinterpret_cast<OutT *>(p.out) + (size_t)pair * per_pair;
+  tile_sweep_cta<OutT, NW, kSweepCta, FMT>(p, map, sx, sy, out, smem_raw);
 }
 
 // One sweep of map 0 restricted to the grid rows [win_y0, win_y1) (strip partition):
@@ -173,10 +175,10 @@ __global__ void ratio2_selftest_kernel(const double2 *__restrict__ tab, int kmax
   if (bad) atomicAdd(mismatches, bad);
 }
 
-template <typename OutT, int NW, int MINB>
+template <typename OutT, int NW, int MINB, int FMT = kFmtValues>
 cudaError_t launch_tile_nw(const TileArgs &p, int64_t npairs, cudaStream_t st) {
   const size_t smem = tile_smem_bytes<OutT>(p.nx, p.ny, NW);
-  auto kern = sweep_tile_kernel<OutT, NW, MINB>;
+  auto kern = sweep_tile_kernel<OutT, NW, MINB, FMT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<(unsigned)npairs, NW * 32, smem, st>>>(p);
@@ -208,6 +210,16 @@ cudaError_t launch_tile(const TileArgs &p, int64_t npairs, cudaStream_t st) {
     case 10: return launch_tile_nw<OutT, 10, 3>(p, npairs, st);
     case 16: return launch_tile_nw<OutT, 16, 2>(p, npairs, st);
     default: return launch_tile_nw<OutT, 8, VHP_NW8_MINB>(p, npairs, st);
+  }
+}
+
+// bit output (TileArgs::thr, kFmtBits): the warp counts the automatic choice makes
+template <int FMT>
+cudaError_t launch_tile_fmt(const TileArgs &p, int64_t npairs, cudaStream_t st) {
+  switch (tile_warps_for(p.nx, p.ny, npairs)) {
+    case 1: return launch_tile_nw<float, 1, 32, FMT>(p, npairs, st);
+    case 2: case 4: case 6: return launch_tile_nw<float, 4, 8, FMT>(p, npairs, st);
+    default: return launch_tile_nw<float, 8, VHP_NW8_MINB, FMT>(p, npairs, st);
   }
 }
 
@@ -268,7 +280,7 @@ cudaError_t vhp_launch_ratio2_selftest(const double *d_rcp2, int kmax,
 cudaError_t vhp_launch_sweep_tile(const VhpTilePlanes &pl, int nx, int ny, const int32_t *d_src_xy,
                                   const int32_t *d_src_map, int64_t npairs, vhp_dtype dtype,
                                   void *d_out, const double *d_rcp2, int *d_err, cudaStream_t st,
-                                  int64_t *launches) {
+                                  int64_t *launches, const double *thr, bool bits) {
   TileArgs p;
   p.pl = pl;
   p.nx = nx;
@@ -288,8 +300,18 @@ cudaError_t vhp_launch_sweep_tile(const VhpTilePlanes &pl, int nx, int ny, const
   p.qmask = 0xF;
   p.src_ctl = nullptr;
   p.x_edges = nullptr; p.x_prog = nullptr; p.x_y0 = p.x_y1 = 0; p.remote_mask = 0;
-  const cudaError_t e = dtype == VHP_F32 ? launch_tile<float>(p, npairs, st)
-                                         : launch_tile<double>(p, npairs, st);
+  p.thr = 0.0;
+  cudaError_t e;
+  if (thr && bits) { // one bit per cell, (fp64 value >= thr), into a zeroed buffer
+    if (!(*thr > 0.0)) return cudaErrorInvalidValue; // cells below the threshold are never written
+    p.thr = *thr;
+    e = cudaMemsetAsync(d_out, 0, (size_t)npairs * ny * ((nx + 31) / 32) * sizeof(uint32_t), st);
+    if (e == cudaSuccess) e = launch_tile_fmt<kFmtBits>(p, npairs, st);
+  } else if (thr || bits) {
+    return cudaErrorInvalidValue;
+  } else {
+    e = dtype == VHP_F32 ? launch_tile<float>(p, npairs, st) : launch_tile<double>(p, npairs, st);
+  }
   if (launches) *launches += 1;
   return e;
 }
@@ -375,6 +397,7 @@ cudaError_t vhp_launch_sweep_window(const VhpTilePlanes &pl, int nx, int ny, int
   p.qmask = qmask;
   p.src_ctl = d_src_ctl;
   p.x_edges = nullptr; p.x_prog = nullptr; p.x_y0 = p.x_y1 = 0; p.remote_mask = 0;
+  p.thr = 0.0;
   if (peer && d_grid_ws && grid_ctas > 1) { // peer hand-over exists in grid mode only
     const int lmcap = tile_lm_cap(ny);
     if (peer->x_ws) {

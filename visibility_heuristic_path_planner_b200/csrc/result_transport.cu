@@ -153,45 +153,73 @@ cudaError_t vhp_launch_pack_results(const void *d_in, int64_t nunits, int elem_b
 // ---- thresholded binary visibility (VHP binary output) ----------------------------------------
 // bits[p][y][w], w < ceil(nx / 32): bit b of word w = (vis[p][y][32w + b] >= thr), decided on the
 // fp64 value the sweep computed (the reference's `visibility_ >= threshold`, bit-exact; an fp32
-// round trip could flip cells that sit on the threshold).  One warp per two words: 2 x 256
-// bytes of coalesced loads, two ballots.
+// round trip could flip cells that sit on the threshold).  One warp per row, U words at a time:
+// U coalesced loads in flight per lane, U ballots, one store of U words.
 namespace {
 
+__device__ __forceinline__ uint32_t transitions_of(const uint32_t w, const uint32_t prev_msb) {
+  return w ^ ((w << 1) | prev_msb); // bit b set: cell b differs from cell b - 1 (cell -1 of a row = 0)
+}
+
+// row_cnt != null: also the number of transition columns of every row (see "row runs" below)
+template <typename T, int U>
 __global__ void __launch_bounds__(256)
-threshold_bits_kernel(const double *__restrict__ vis, const int64_t nrows, const int nx, const int wpr,
-                      const double thr, uint32_t *__restrict__ bits) {
+threshold_bits_kernel(const T *__restrict__ vis, const int64_t nrows, const int nx, const int wpr,
+                      const T thr, uint32_t *__restrict__ bits, uint16_t *__restrict__ row_cnt) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int pairs_per_row = (wpr + 1) >> 1;
-  const int64_t total = nrows * pairs_per_row;
-  for (int64_t t = warp0; t < total; t += nwarps) {
-    const int64_t row = t / pairs_per_row;
-    const int w0 = 2 * (int)(t - row * pairs_per_row);
-    const double *r = vis + row * nx;
-    const int xa = 32 * w0 + lane, xb = xa + 32;
-    const double a = xa < nx ? __ldcs(r + xa) : -1.0, b = xb < nx ? __ldcs(r + xb) : -1.0;
-    const uint32_t ma = __ballot_sync(kAllLanes, xa < nx && a >= thr);
-    const uint32_t mb = __ballot_sync(kAllLanes, xb < nx && b >= thr);
-    if (lane == 0) bits[row * wpr + w0] = ma;
-    if (lane == 1 && w0 + 1 < wpr) bits[row * wpr + w0 + 1] = mb;
+  for (int64_t row = warp0; row < nrows; row += nwarps) {
+    const T *r = vis + row * nx;
+    uint32_t *o = bits + row * wpr;
+    uint32_t carry = 0, mine = 0; // carry: the top bit of the word before this group
+    int cnt = 0, w0 = 0;
+    for (; w0 < wpr; w0 += U) {
+      T v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { // U coalesced loads in flight per lane
+        const int x = 32 * (w0 + u) + lane;
+        v[u] = x < nx ? __ldcs(r + x) : (T)-1;
+      }
+      mine = 0;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t m = __ballot_sync(kAllLanes, 32 * (w0 + u) + lane < nx && v[u] >= thr);
+        if (lane == u) mine = m;
+      }
+      const bool have = lane < U && w0 + lane < wpr;
+      if (have) o[w0 + lane] = mine;
+      if (row_cnt) {
+        const uint32_t below = __shfl_up_sync(kAllLanes, mine, 1);
+        if (have) cnt += __popc(transitions_of(mine, lane ? below >> 31 : carry));
+        carry = __shfl_sync(kAllLanes, mine, U - 1) >> 31;
+      }
+    }
+    if (row_cnt) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(kAllLanes, cnt, off);
+      // a run that reaches the last cell is closed at nx: the zero padding bit of the last word does
+      // that by itself unless the row fills its last word
+      const uint32_t last = __shfl_sync(kAllLanes, mine, (wpr - 1) - (w0 - U));
+      if ((nx & 31) == 0) cnt += (int)(last >> 31);
+      if (lane == 0) row_cnt[row] = (uint16_t)cnt;
+    }
   }
 }
 
 } // namespace
 
 cudaError_t vhp_launch_threshold_bits(const double *d_vis, int64_t nrows, int nx, double thr,
-                                      uint32_t *d_bits, int sm_count, cudaStream_t st, int64_t *launches) {
+                                      uint32_t *d_bits, int sm_count, cudaStream_t st, int64_t *launches,
+    uint16_t *d_row_cnt) {
   const int wpr = (nx + 31) / 32;
-  const int64_t warps = nrows * ((wpr + 1) / 2);
-  int64_t blocks = (warps + 7) / 8;
-  if (blocks > (int64_t)sm_count * 16) blocks = (int64_t)sm_count * 16;
+  int64_t blocks = (nrows + 7) / 8;
+  if (blocks > (int64_t)sm_count * 8) blocks = (int64_t)sm_count * 8;
   if (blocks < 1) blocks = 1;
-  threshold_bits_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_vis, nrows, nx, wpr, thr, d_bits);
+  threshold_bits_kernel<double, 4><<<(unsigned)blocks, 256, 0, st>>>(d_vis, nrows, nx, wpr, thr, d_bits, d_row_cnt);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }
-
 
 // ---- thresholded binary visibility as row runs -------------------------------------------------
 // The visible set of a row, {x : vis(x, y) >= thr}, as its sorted transition columns
@@ -199,42 +227,78 @@ cudaError_t vhp_launch_threshold_bits(const double *d_vis, int64_t nrows, int nx
 // always even).  A visibility polygon crosses a row a handful of times, so this is 10-20 x smaller
 // than one bit per cell -- small enough that the host-buffer call is bound by the sweep again and
 // not by the box's PCIe / host-memory path, whatever the number of GPUs.
-//   pass 1  threshold_bits_kernel (above) -> bits[row][wpr]
-//   pass 2  runs_count_kernel: transitions per row (uint16) and per pair (uint32)
+//   pass 1  bits[row][wpr] (the sweep itself, or threshold_bits_kernel above) and transitions per
+//           row (uint16; threshold_bits_kernel or runs_row_count_kernel)
+//   pass 2  runs_rows_kernel: offset of every row inside its pair, transitions per pair (uint32)
 //   pass 3  runs_scan_kernel: exclusive scan of the pair totals (one CTA; <= a few thousand pairs)
 //   pass 4  runs_write_kernel: positions, one warp per row
 namespace {
 
-__device__ __forceinline__ uint32_t transitions_of(const uint32_t w, const uint32_t prev_msb) {
-  return w ^ ((w << 1) | prev_msb); // bit b set: cell b differs from cell b - 1 (cell -1 of a row = 0)
-}
-
-// one warp per row; lane l handles words l, l + 32, ...
+// transitions per row from the bits alone (the sweep wrote them itself): one warp per 4 rows
 __global__ void __launch_bounds__(256)
-runs_count_kernel(const uint32_t *__restrict__ bits, const int64_t nrows, const int ny, const int nx,
-                  const int wpr, uint16_t *__restrict__ row_cnt, uint32_t *__restrict__ pair_tot) {
+runs_row_count_kernel(const uint32_t *__restrict__ bits, const int64_t nrows, const int nx, const int wpr,
+                      uint16_t *__restrict__ row_cnt) {
+  constexpr int R = 4;
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t row = warp0; row < nrows; row += nwarps) {
-    const uint32_t *r = bits + row * wpr;
-    int cnt = 0;
+  for (int64_t row0 = warp0 * R; row0 < nrows; row0 += nwarps * R) {
+    int cnt[R] = {};
     for (int w0 = 0; w0 < wpr; w0 += 32) {
       const int w = w0 + lane;
-      const uint32_t cur = w < wpr ? r[w] : 0u;
-      const uint32_t prev = (w > 0 && w < wpr) ? r[w - 1] >> 31 : 0u;
-      cnt += __popc(transitions_of(cur, prev));
+      uint32_t cur[R], carry[R];
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        const bool have = row0 + u < nrows && w < wpr;
+        const uint32_t *r = bits + (row0 + u) * wpr;
+        cur[u] = have ? __ldg(r + w) : 0u;
+        carry[u] = (have && lane == 0 && w0 > 0) ? __ldg(r + w - 1) >> 31 : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        const uint32_t below = __shfl_up_sync(kAllLanes, cur[u], 1);
+        if (w < wpr) {
+          cnt[u] += __popc(transitions_of(cur[u], lane ? below >> 31 : carry[u]));
+          // a run that reaches the last cell is closed at nx: the zero padding of the last word does
+          // that by itself unless the row fills its last word
+          if (w == wpr - 1 && (nx & 31) == 0) cnt[u] += (int)(cur[u] >> 31);
+        }
+      }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(kAllLanes, cnt, off);
-    // a run that reaches the last cell is closed at nx: the zero padding bit of the last word does
-    // that by itself unless the row fills its last word
-    if ((nx & 31) == 0) cnt += (int)(r[wpr - 1] >> 31);
-    if (lane == 0) {
-      row_cnt[row] = (uint16_t)cnt;
-      atomicAdd(pair_tot + row / ny, (uint32_t)cnt);
+    for (int u = 0; u < R; ++u) {
+      int c = cnt[u];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(kAllLanes, c, off);
+      if (lane == 0 && row0 + u < nrows) row_cnt[row0 + u] = (uint16_t)c;
     }
   }
+}
+
+// one CTA per pair: row_off[row] = transitions of the pair's earlier rows, pair_tot[pair] = all of them
+__global__ void __launch_bounds__(256)
+runs_rows_kernel(const uint16_t *__restrict__ row_cnt, const int ny, uint32_t *__restrict__ row_off,
+                 uint32_t *__restrict__ pair_tot) {
+  __shared__ uint32_t s_warp[8];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const uint16_t *c = row_cnt + (size_t)blockIdx.x * ny;
+  uint32_t *o = row_off + (size_t)blockIdx.x * ny;
+  const int per = (ny + 255) / 256, i0 = min(ny, t * per), i1 = min(ny, i0 + per);
+  uint32_t sum = 0;
+  for (int i = i0; i < i1; ++i) sum += c[i];
+  uint32_t inc = sum; // inclusive scan over the CTA's 256 partial sums
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t v = __shfl_up_sync(kAllLanes, inc, d);
+    if (lane >= d) inc += v;
+  }
+  if (lane == 31) s_warp[wid] = inc;
+  __syncthreads();
+  uint32_t before = 0;
+  for (int w = 0; w < wid; ++w) before += s_warp[w];
+  uint32_t run = before + inc - sum;
+  for (int i = i0; i < i1; ++i) { o[i] = run; run += c[i]; }
+  if (t == 255) pair_tot[blockIdx.x] = before + inc;
 }
 
 // pair_ptr[p] = base + sum of pair_tot[0 .. p), pair_ptr[npairs] = base + total (one CTA)
@@ -260,7 +324,7 @@ runs_scan_kernel(const uint32_t *__restrict__ pair_tot, const int npairs, const 
 // one warp per row: write the transition columns at trans[pair_ptr[pair] - chunk_base + offset of the row]
 __global__ void __launch_bounds__(256)
 runs_write_kernel(const uint32_t *__restrict__ bits, const int64_t nrows, const int ny, const int nx,
-                  const int wpr, const uint16_t *__restrict__ row_cnt,
+                  const int wpr, const uint32_t *__restrict__ row_off,
                   const unsigned long long *__restrict__ pair_ptr, const unsigned long long chunk_base,
                   uint16_t *__restrict__ trans) {
   const int lane = threadIdx.x & 31;
@@ -268,17 +332,7 @@ runs_write_kernel(const uint32_t *__restrict__ bits, const int64_t nrows, const 
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t row = warp0; row < nrows; row += nwarps) {
     const int64_t pair = row / ny;
-    const int y = (int)(row - pair * ny);
-    // offset of the row inside its pair: sum of the counts of the pair's earlier rows
-    unsigned long long off = 0;
-    {
-      const uint16_t *c = row_cnt + pair * ny;
-      unsigned int part = 0;
-      for (int i = lane; i < y; i += 32) part += c[i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kAllLanes, part, o);
-      off = pair_ptr[pair] - chunk_base + part;
-    }
+    const unsigned long long off = pair_ptr[pair] - chunk_base + row_off[row];
     const uint32_t *r = bits + row * wpr;
     uint16_t *out = trans + off;
     int base = 0;
@@ -308,31 +362,34 @@ runs_write_kernel(const uint32_t *__restrict__ bits, const int64_t nrows, const 
 
 } // namespace
 
-// d_pair_tot: npairs uint32, zeroed here.  Leaves row_cnt and pair_ptr (npairs + 1 entries, starting
-// at `base`) on the device; the caller reads pair_ptr[npairs] to learn how many positions pass 4 writes.
-cudaError_t vhp_launch_runs_count(const uint32_t *d_bits, int64_t npairs, int ny, int nx, uint16_t *d_row_cnt,
+cudaError_t vhp_launch_runs_row_count(const uint32_t *d_bits, int64_t nrows, int nx, uint16_t *d_row_cnt,
+                                      int sm_count, cudaStream_t st, int64_t *launches) {
+  const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((nrows + 31) / 32, (int64_t)sm_count * 8));
+  runs_row_count_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_bits, nrows, nx, (nx + 31) / 32, d_row_cnt);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+// d_row_cnt: the counts threshold_bits wrote.  Leaves row_off (per row, inside its pair) and pair_ptr
+// (npairs + 1 entries, starting at `base`) on the device; the caller reads pair_ptr[npairs] to
+// learn how many positions the write pass produces.
+cudaError_t vhp_launch_runs_count(const uint16_t *d_row_cnt, int64_t npairs, int ny, uint32_t *d_row_off,
                                   uint32_t *d_pair_tot, unsigned long long base,
-                                  unsigned long long *d_pair_ptr, int sm_count, cudaStream_t st,
-                                  int64_t *launches) {
-  const int wpr = (nx + 31) / 32;
-  cudaError_t e = cudaMemsetAsync(d_pair_tot, 0, (size_t)npairs * sizeof(uint32_t), st);
-  if (e != cudaSuccess) return e;
-  const int64_t nrows = npairs * ny;
-  int64_t blocks = std::min<int64_t>((nrows + 7) / 8, (int64_t)sm_count * 16);
-  runs_count_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), 256, 0, st>>>(d_bits, nrows, ny, nx, wpr, d_row_cnt, d_pair_tot);
+                                  unsigned long long *d_pair_ptr, cudaStream_t st, int64_t *launches) {
+  runs_rows_kernel<<<(unsigned)npairs, 256, 0, st>>>(d_row_cnt, ny, d_row_off, d_pair_tot);
   runs_scan_kernel<<<1, 1024, 0, st>>>(d_pair_tot, (int)npairs, base, d_pair_ptr);
   if (launches) *launches += 2;
   return cudaGetLastError();
 }
 
 cudaError_t vhp_launch_runs_write(const uint32_t *d_bits, int64_t npairs, int ny, int nx,
-                                  const uint16_t *d_row_cnt, const unsigned long long *d_pair_ptr,
+                                  const uint32_t *d_row_off, const unsigned long long *d_pair_ptr,
                                   unsigned long long chunk_base, uint16_t *d_trans, int sm_count,
                                   cudaStream_t st, int64_t *launches) {
   const int wpr = (nx + 31) / 32;
   const int64_t nrows = npairs * ny;
   int64_t blocks = std::min<int64_t>((nrows + 7) / 8, (int64_t)sm_count * 16);
-  runs_write_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), 256, 0, st>>>(d_bits, nrows, ny, nx, wpr, d_row_cnt,
+  runs_write_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), 256, 0, st>>>(d_bits, nrows, ny, nx, wpr, d_row_off,
                                                                            d_pair_ptr, chunk_base, d_trans);
   if (launches) *launches += 1;
   return cudaGetLastError();

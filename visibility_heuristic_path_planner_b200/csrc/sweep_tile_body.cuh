@@ -159,6 +159,7 @@ struct TileArgs {
   int *x_prog;
   int x_y0, x_y1;
   int remote_mask;
+  double thr; // kFmtBits: bit = (fp64 value >= thr), thr > 0
 };
 
 // how tile_sweep_cta is used
@@ -245,6 +246,12 @@ __device__ __forceinline__ void stg16_fill(float *q, float v) {
 __device__ __forceinline__ void stg16_fill(double *q, double v) {
   __stcs(reinterpret_cast<double2 *>(q), make_double2(v, v));
 }
+
+// What a sweep stores.  kFmtValues: the field, one OutT per cell.  kFmtBits: one BIT per cell,
+// bit (x & 31) of word [y][x >> 5] = (fp64 value >= TileArgs::thr), rows of (nx + 31) / 32 words,
+// for thr > 0 and into a ZEROED buffer: cells below the threshold are not written at all, the
+// words around the source column (shared by the -x and +x quadrants) are or-ed in atomically.
+constexpr int kFmtValues = 0, kFmtBits = 2;
 
 // staging tile: element (row r, column c) of a 32 x 32 tile (odd pitch: column-wise writes
 // and the row-wise read-out are both conflict-free)
@@ -398,7 +405,7 @@ __device__ __forceinline__ int ld_acquire_sys(const int *a) {
 // (q(i0-1, j0-1)) are the left inputs; on return they hold the same for tile (I+1, J).
 // GE: the boundary rows (edges) and the progress flag are in global memory and shared with
 // warps of other CTAs (grid mode): boundary reads bypass L1, the flag is released at GPU scope.
-template <typename OutT, int NW, bool GE>
+template <typename OutT, int NW, bool GE, int FMT = kFmtValues>
 __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, const TilePre &pre,
                                              const int sx, const int sy, const int I, const int J,
                                              OutT *__restrict__ out, double *edges,
@@ -408,6 +415,8 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
   // the row above may start its tile I as soon as rowE holds this tile's top row: publish
   // before the global stores
   constexpr int kStepUnroll = NW == 1 ? VHP_STEP_UNROLL_1W : VHP_STEP_UNROLL;
+  constexpr bool BITS = FMT == kFmtBits;
+  static_assert(!BITS || sizeof(OutT) == 4, "bit output: OutT is the 32-bit word");
   auto publish = [&]() {
     if (GE) __threadfence(); // this lane's boundary-row stores, before lane 0 raises the flag
     __syncwarp();
@@ -470,6 +479,19 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
   const int r0 = max((g.diry < 0 && j0 == 0) ? 1 : 0, g.jw0 - j0);
   const int rgrid = min(wj - 1, g.Ey - j0);          // last row inside the grid
   const int rlast = min(rgrid, g.jw1 - j0);
+  // bit output: the tile's columns of one row are (part of) ONE word, since tile columns start on
+  // multiples of 32 except the first one of a quadrant, which ends on one
+  const int xw = g.dirx > 0 ? sx + i0 : sx - i0; // column of lane 0
+  const int wpr = (nx + 31) >> 5;
+  auto put_word = [&](const uint32_t m, const int rfirst, const int rend) { // m: bit l <-> column il
+    const uint32_t w = g.dirx > 0 ? m << (xw & 31) : __brev(m) >> (31 - (xw & 31));
+    if (lane >= rfirst && lane <= rend && w) { // lane <-> row j0 + lane
+      uint32_t *q = reinterpret_cast<uint32_t *>(out) + (ptrdiff_t)(sy + g.diry * (j0 + lane)) * wpr + (xw >> 5);
+      if (I == 0) atomicOr(q, w);
+      else *q = w;
+    }
+  };
+  uint32_t wb = 0; // BITS: the bits of row j0 + lane
 
   if (allocc || zero_in || (inuni && allfree)) {
     // ---- uniform tile: no arithmetic -------------------------------------------------
@@ -481,6 +503,10 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
     }
     publish();
     const int rc = min(min(wj - 1, EyC - j0), rlast); // last lit row; a border row (if any) follows
+    if constexpr (BITS) {
+      if (!zero && cor >= p.thr) put_word(__ballot_sync(kAll, lane_st && colc), r0, rc);
+      return;
+    }
     if (p.vec && nvx == 32 && (I > 0 || g.dirx > 0)) {
       // all 32 columns are stored and x0 is a multiple of 32: 128-bit stores
       constexpr int EPL = 16 / (int)sizeof(OutT), LPR = 32 / EPL; // elements per lane, lanes per row
@@ -492,13 +518,13 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
       for (int r = r0 + sub; r <= rc; r += EPL, q += EPL * rs) stg16_fill(q, v);
       if (rc < rlast && sub == 0)
         stg16_fill(out + (ptrdiff_t)(sy + g.diry * (j0 + rlast)) * nx + (xlow + (lane % LPR) * EPL),
-                   (OutT)0);
+                   to_out<OutT>(0.0));
     } else if (lane_st) {
       const OutT lv = to_out<OutT>((zero || !colc) ? 0.0 : cor);
       OutT *q = ptr + r0 * rs;
 #pragma unroll kFillUnroll
       for (int r = r0; r <= rc; ++r, q += rs) __stcs(q, lv);
-      if (rc < rlast) __stcs(ptr + rlast * rs, (OutT)0);
+      if (rc < rlast) __stcs(ptr + rlast * rs, to_out<OutT>(0.0));
     }
     return;
   }
@@ -538,7 +564,8 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
         F = (!decltype(masked)::value || ((wrow >> s) & 1u)) ? v : 0.0;
         // (storing this lane's row straight from registers, 16 bytes every few steps, was
         // measured slower than staging: 32 partial-sector requests per store instruction)
-        stage[stage_at(lane, s)] = to_out<OutT>(F);
+        if constexpr (BITS) wb |= (uint32_t)(F >= p.thr) << s;
+        else stage[stage_at(lane, s)] = to_out<OutT>(F);
         if (lane == wj - 1) rowE[s] = F;
       }
     };
@@ -569,8 +596,12 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
           const double c = __fma_rn(fd, rr.x, __dmul_rn(fd, rr.y));
           const double v = lerp_rn(F, b, c);
           F = (!decltype(masked)::value || ((wcol >> s) & 1u)) ? v : 0.0;
-          if (!decltype(masked)::value || (lane_st && s >= r0 && s <= rlast))
+          if constexpr (BITS) {
+            const uint32_t m = __ballot_sync(kAll, F >= p.thr);
+            if (lane == s) wb = m;
+          } else if (!decltype(masked)::value || (lane_st && s >= r0 && s <= rlast)) {
             __stcs(q, to_out<OutT>(F));
+          }
           if (lane == wi - 1) wnew[s] = F;
         }
       };
@@ -582,6 +613,7 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
       Lv = wnew[lane];
       cor = cor_next;
       publish();
+      if constexpr (BITS) put_word(wb & __ballot_sync(kAll, lane_st), r0, rlast);
       return;
     }
     // ---- diagonal tile: both fronts and the diagonal cell (wi == wj) ---------------------
@@ -601,8 +633,16 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
       if (lane < k) {
         C = ((wrow >> k) & 1u) ? vC : 0.0;
         R = ((wcol >> k) & 1u) ? vR : 0.0;
-        stage[stage_at(lane, k)] = to_out<OutT>(C);
-        stage[stage_at(k, lane)] = to_out<OutT>(R);
+        if constexpr (BITS) {
+          wb |= (uint32_t)(C >= p.thr) << k; // row j0 + lane, column k
+        } else {
+          stage[stage_at(lane, k)] = to_out<OutT>(C);
+          stage[stage_at(k, lane)] = to_out<OutT>(R);
+        }
+      }
+      if constexpr (BITS) { // row j0 + k, columns below k
+        const uint32_t m = __ballot_sync(kAll, lane < k && R >= p.thr);
+        if (lane == k) wb |= m;
       }
       // diagonal cell q(k,k) = q(k,k-1) * occ: q(k,k-1) is lane k-1's new C (k == 0: B[0])
       const double dsrc = __shfl_up_sync(kAll, C, 1);
@@ -610,7 +650,8 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
         const double dv = ((wrow >> k) & 1u) ? (k ? dsrc : Bv) : 0.0;
         C = dv;
         R = dv;
-        stage[stage_at(k, k)] = to_out<OutT>(dv);
+        if constexpr (BITS) wb |= (uint32_t)(dv >= p.thr) << k;
+        else stage[stage_at(k, k)] = to_out<OutT>(dv);
       }
     }
     __syncwarp();
@@ -621,7 +662,9 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
   cor = cor_next;
   // ---- write the staged tile as rows ---------------------------------------------------
   __syncwarp();
-  if (lane_st) {
+  if constexpr (BITS) {
+    put_word(wb & __ballot_sync(kAll, lane_st), r0, rlast);
+  } else if (lane_st) {
     OutT *q = ptr + r0 * rs;
 #pragma unroll kFillUnroll
     for (int r = r0; r <= rlast; ++r, q += rs) __stcs(q, stage[stage_at(r, lane)]);
@@ -638,11 +681,12 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
 // CTAs, writes the lit region (grid rows dealt over all warps of the grid) and then takes tile
 // rows from the global counter.  A row only waits for a row handed out earlier, whose warp is
 // therefore running: no co-residency of the CTAs is needed.
-template <typename OutT, int NW, int MODE = kSweepCta>
+template <typename OutT, int NW, int MODE = kSweepCta, int FMT = kFmtValues>
 __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map, const int sx,
                                                const int sy, OutT *__restrict__ out,
                                                unsigned char *smem_raw) {
   constexpr bool GE = MODE != kSweepCta;
+  constexpr bool BITS = FMT == kFmtBits;
   static_assert(!GE || NW > 1, "grid mode uses the multi-warp boundary layout");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nx = p.nx, ny = p.ny;
@@ -809,11 +853,24 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
       const int nR = upper ? lit_run(0, j) : lit_run(3, j);
       const int nL = upper ? lit_run(1, j) : lit_run(2, j);
       if (nR == 0 && nL <= 1) continue;
+      if constexpr (BITS) {
+        if ((!upper && y == 0) || !(1.0 >= p.thr)) continue; // zeros are not written
+        uint32_t *wrow = reinterpret_cast<uint32_t *>(out) + (size_t)y * ((nx + 31) >> 5);
+        const int xfirst = nL > 1 ? max(sx - (nL - 1), 1) : sx, xend = nR > 0 ? sx + nR - 1 : sx - 1;
+        for (int w = (xfirst >> 5) + lane; w <= (xend >> 5); w += 32) {
+          uint32_t m = ~0u;
+          if (w == (xfirst >> 5)) m &= ~0u << (xfirst & 31);
+          if (w == (xend >> 5)) m &= ~0u >> (31 - (xend & 31));
+          if (m == ~0u) wrow[w] = m; // a whole word inside the lit run has no other writer
+          else atomicOr(wrow + w, m);
+        }
+        continue;
+      }
       OutT *row = out + (size_t)y * nx;
-      const OutT v = (!upper && y == 0) ? (OutT)0 : (OutT)1; // y == 0 below the source: never written
+      const OutT v = to_out<OutT>((!upper && y == 0) ? 0.0 : 1.0); // y == 0 below the source: never written
       int xa = sx - (nL - 1), xb = sx + nR - 1;
       if (nL > 0 && xa == 0) { // x == 0 left of the source: never written
-        if (lane == 0) __stcs(row, (OutT)0);
+        if (lane == 0) __stcs(row, to_out<OutT>(0.0));
         xa = 1;
       }
       if (nR > 0 && nL > 1) {
@@ -873,8 +930,9 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
             const int rlast = min(min((J ? kTile : g.a) - 1, g.Ey - j0row), g.jw1 - j0row);
             const int ie = min(g.Ex, tile_start(g.a, Istop) - 1); // last local column of the run
             const int xa = g.dirx > 0 ? sx + i0 : sx - ie, xb = g.dirx > 0 ? sx + ie : sx - i0;
-            fill_block<OutT>(out, nx, sy + g.diry * (j0row + r0), g.diry, rlast - r0 + 1, xa, xb, (OutT)0, lane,
-                             p.vec != 0);
+            if constexpr (!BITS)
+              fill_block<OutT>(out, nx, sy + g.diry * (j0row + r0), g.diry, rlast - r0 + 1, xa, xb,
+                               to_out<OutT>(0.0), lane, p.vec != 0);
             if (Istop >= g.TX) return;
             pre = tile_prefetch(p, g, rowpl, colpl, bsum, sx, sy, Istop, J, lane);
             I = Istop - 1;
@@ -907,8 +965,8 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
         while ((GE ? ld_acquire_gpu(flag) : ld_acquire_shared(flag)) <= I) __nanosleep(40);
 #endif
       }
-      process_tile<OutT, NW, GE>(p, g, cur, sx, sy, I, J, out, edges, stage, wscr, lane, Lv, cor,
-                             prog + q * lmcap + J, xflag);
+      process_tile<OutT, NW, GE, FMT>(p, g, cur, sx, sy, I, J, out, edges, stage, wscr, lane, Lv, cor,
+                                  prog + q * lmcap + J, xflag);
       __syncwarp();
     }
   };

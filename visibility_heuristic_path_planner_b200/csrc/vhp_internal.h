@@ -60,16 +60,17 @@ cudaError_t vhp_launch_pack_results(const void *d_in, int64_t nunits, int elem_b
 
 // thresholded binary visibility: bits[row][ceil(nx/32)] from fp64 rows (result_transport.cu)
 cudaError_t vhp_launch_threshold_bits(const double *d_vis, int64_t nrows, int nx, double thr,
-                                      uint32_t *d_bits, int sm_count, cudaStream_t st, int64_t *launches);
-
-// thresholded binary visibility as row runs (result_transport.cu): transitions per row / pair, then
-// the transition columns themselves
-cudaError_t vhp_launch_runs_count(const uint32_t *d_bits, int64_t npairs, int ny, int nx, uint16_t *d_row_cnt,
+                                      uint32_t *d_bits, int sm_count, cudaStream_t st, int64_t *launches,
+                                      uint16_t *d_row_cnt = nullptr);
+cudaError_t vhp_launch_runs_row_count(const uint32_t *d_bits, int64_t nrows, int nx, uint16_t *d_row_cnt,
+                                      int sm_count, cudaStream_t st, int64_t *launches);
+// row runs: d_row_cnt (uint16 per row) comes from the threshold pass or from runs_row_count; runs_count leaves row_off (uint32
+// per row) and pair_ptr (npairs + 1) on the device, runs_write the transition columns
+cudaError_t vhp_launch_runs_count(const uint16_t *d_row_cnt, int64_t npairs, int ny, uint32_t *d_row_off,
                                   uint32_t *d_pair_tot, unsigned long long base,
-                                  unsigned long long *d_pair_ptr, int sm_count, cudaStream_t st,
-                                  int64_t *launches);
+                                  unsigned long long *d_pair_ptr, cudaStream_t st, int64_t *launches);
 cudaError_t vhp_launch_runs_write(const uint32_t *d_bits, int64_t npairs, int ny, int nx,
-                                  const uint16_t *d_row_cnt, const unsigned long long *d_pair_ptr,
+                                  const uint32_t *d_row_off, const unsigned long long *d_pair_ptr,
                                   unsigned long long chunk_base, uint16_t *d_trans, int sm_count,
                                   cudaStream_t st, int64_t *launches);
 
@@ -122,6 +123,7 @@ struct vhp_context {
   // planner batches: first sweep of every problem batch-wide (0 never, 1 from 4 waves of problems on
   // (default), 2 always; env VHP_PLANNER_FIRST)
   int planner_first = 1;
+  int bin_direct = 1; // binary outputs: the sweep writes bits itself (env VHP_BIN_DIRECT=0: fp64 field + threshold pass)
   int planner_first_rounds = 1; // sweeps per problem done batch-wide (env VHP_PLANNER_ROUNDS; measured: 1 is
                                 // fastest -- later rounds have too few active problems for whole-batch launches)
   // packed result transport of the host-buffer entry points: 0 plain D2H, 1 automatic
@@ -186,7 +188,9 @@ cudaError_t vhp_launch_pack_tile(const uint8_t *d_occ, int nmaps, int nx, int ny
 cudaError_t vhp_launch_sweep_tile(const VhpTilePlanes &pl, int nx, int ny, const int32_t *d_src_xy,
                                   const int32_t *d_src_map, int64_t npairs, vhp_dtype dtype,
                                   void *d_out, const double *d_rcp2, int *d_err, cudaStream_t st,
-                                  int64_t *launches);
+                                  int64_t *launches, const double *thr = nullptr, bool bits = false);
+// thr != null, bits: d_out = uint32 words, bit (x & 31) of word [pair][y][x >> 5] = (fp64 value >= thr);
+// needs thr > 0 (zeroes d_out, then writes only the cells at or above the threshold).
 
 // opt-in sweep variants (kernels_sweep_variant.cu): model 1 getAccessibilityMap.m (alpha, fac),
 // model 2 computeVisibilityUsingQueue as an order-free rule (cutoff)
