@@ -1018,6 +1018,12 @@ def main():
                                        "result_bytes_per_step": int(res2),
                                        "transport": ["plain", "packed", "packed (direct)"][packed2], "steps": 2}
             del o2
+            # the same batch as thresholded bits (the sweep writes 1 bit per cell, nothing else)
+            ob = torch.empty((n2, ny2, (nx2 + 31) // 32), dtype=torch.int32, device=dev)
+            msb = _timed_dev(stream, lambda: ctx.visibility_batch_bin_dev(occ2, src2, 0.5, ob, smap2), 5)
+            penumbra[wl]["bits_store"] = {"ms_per_step": msb, "value": n2 * nx2 * ny2 / msb / 1e6, "unit": "Gcells/s",
+                                          "threshold": 0.5}
+            del ob
             if wl in ("c2s", "c2d") and args.store == "f32":  # the same batch stored as fp64 (north_star's fp64 mode)
                 o3 = torch.empty((n2, ny2, nx2), dtype=torch.float64, device=dev)
                 ms3 = _timed_dev(stream, lambda: ctx.visibility_batch_dev(occ2, src2, o3, smap2), 5)
@@ -1039,6 +1045,12 @@ def main():
                      "roofline": {"bound": "hbm", "achieved": b3 / ms3 / 1e6, "peak": measured_peak()[0], "unit": "GB/s",
                                   "frac": b3 / ms3 / 1e6 / measured_peak()[0], "algorithmic_bytes_per_launch": b3}}
         del o3
+        ob = torch.empty((n, ny, (nx + 31) // 32), dtype=torch.int32, device=dev)
+        msb = _timed_dev(stream, lambda: ctx.visibility_batch_bin_dev(occ_t, src_t, 0.5, ob, smap_t), 10)
+        f64_store["bits_store"] = {"workload": "the headline batch as thresholded bits (vhp_visibility_batch_bin_dev: "
+                                               "the sweep compares in fp64 and writes 1 bit per cell)",
+                                   "ms_per_step": msb, "value": cells / msb / 1e6, "unit": "Gcells/s", "threshold": 0.5}
+        del ob
     if e2e is not None:
         host_ctx.close()
         del out_h

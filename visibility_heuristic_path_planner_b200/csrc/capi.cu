@@ -575,7 +575,8 @@ vhp_status run_bin_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx
                        const int32_t *d_xy, const int32_t *d_map, int64_t n, double thr,
                        uint32_t *d_bits) {
   const size_t cells = (size_t)nx * ny, wpr = (size_t)(nx + 31) / 32;
-  const int64_t chunk = bin_chunk_pairs(cells, n);
+  // no intermediate field when the sweep writes bits itself: one launch for the whole batch
+  const int64_t chunk = sweeps_into_bits(ctx, nx, ny, n, thr) ? n : bin_chunk_pairs(cells, n);
   vhp_status st;
   for (int64_t p0 = 0; p0 < n; p0 += chunk) {
     const int64_t np = std::min(chunk, n - p0);
@@ -611,7 +612,11 @@ vhp_status run_bin_host(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx,
   }
   const int32_t *d_xy = (const int32_t *)ctx->b_src.p;
   const int32_t *d_map = maps ? (const int32_t *)ctx->b_map.p : nullptr;
-  const int64_t chunk = bin_chunk_pairs(cells, n);
+  // the sweep writes bits itself: four chunks (the D2H of one under the sweeps of the next), each
+  // many waves of CTAs; else chunks bounded by the fp64 field
+  const int64_t chunk = sweeps_into_bits(ctx, nx, ny, n, thr)
+                            ? std::min<int64_t>(n, std::max<int64_t>((int64_t)ctx->sm_count * 6, (n + 3) / 4))
+                            : bin_chunk_pairs(cells, n);
   const size_t pair_words = (size_t)ny * wpr, chunk_bytes = (size_t)chunk * pair_words * 4;
   vhp_status result = VHP_OK;
   for (int b = 0; b < 2 && result == VHP_OK; ++b)

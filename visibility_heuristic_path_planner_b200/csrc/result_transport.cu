@@ -267,9 +267,7 @@ runs_row_count_kernel(const uint32_t *__restrict__ bits, const int64_t nrows, co
     }
 #pragma unroll
     for (int u = 0; u < R; ++u) {
-      int c = cnt[u];
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(kAllLanes, c, off);
+      const int c = __reduce_add_sync(kAllLanes, cnt[u]);
       if (lane == 0 && row0 + u < nrows) row_cnt[row0 + u] = (uint16_t)c;
     }
   }
@@ -321,42 +319,77 @@ runs_scan_kernel(const uint32_t *__restrict__ pair_tot, const int npairs, const 
   for (int i = t * per; i < min(npairs, (t + 1) * per); ++i) { pair_ptr[i] = run; run += pair_tot[i]; }
 }
 
-// one warp per row: write the transition columns at trans[pair_ptr[pair] - chunk_base + offset of the row]
+// one warp per 4 rows (their loads issued together): write the transition columns of row `row` at
+// trans[pair_ptr[pair] - chunk_base + row_off[row]]
 __global__ void __launch_bounds__(256)
 runs_write_kernel(const uint32_t *__restrict__ bits, const int64_t nrows, const int ny, const int nx,
                   const int wpr, const uint32_t *__restrict__ row_off,
                   const unsigned long long *__restrict__ pair_ptr, const unsigned long long chunk_base,
                   uint16_t *__restrict__ trans) {
+  constexpr int R = 4;
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t row = warp0; row < nrows; row += nwarps) {
-    const int64_t pair = row / ny;
-    const unsigned long long off = pair_ptr[pair] - chunk_base + row_off[row];
-    const uint32_t *r = bits + row * wpr;
-    uint16_t *out = trans + off;
-    int base = 0;
-    for (int w0 = 0; w0 < wpr; w0 += 32) {
-      const int w = w0 + lane;
-      const uint32_t cur = w < wpr ? r[w] : 0u;
-      const uint32_t prev = (w > 0 && w < wpr) ? r[w - 1] >> 31 : 0u;
-      uint32_t t = transitions_of(cur, prev);
-      const int n = __popc(t);
-      int pre = n; // inclusive warp scan
+  for (int64_t row0 = warp0 * R; row0 < nrows; row0 += nwarps * R) {
+    unsigned long long off[R];
+    uint32_t first[R];
+    int64_t pair = row0 / ny;
+    int y = (int)(row0 - pair * ny);
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(kAllLanes, pre, o);
-        if (lane >= o) pre += v;
-      }
-      int pos = base + pre - n;
-      while (t) {
-        const int b = __ffs(t) - 1;
-        t &= t - 1;
-        out[pos++] = (uint16_t)(32 * w + b);
-      }
-      base += __shfl_sync(kAllLanes, pre, 31);
+    for (int u = 0; u < R; ++u) {
+      const int64_t row = min(row0 + u, nrows - 1);
+      off[u] = __ldg(pair_ptr + pair) - chunk_base + __ldg(row_off + row);
+      first[u] = lane < wpr ? __ldg(bits + row * wpr + lane) : 0u;
+      if (++y == ny && row0 + u + 1 < nrows) { y = 0; ++pair; }
     }
-    if (lane == 0 && (nx & 31) == 0 && (r[wpr - 1] >> 31)) out[base] = (uint16_t)nx;
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      if (row0 + u >= nrows) break;
+      const uint32_t *r = bits + (row0 + u) * wpr;
+      uint16_t *out = trans + off[u];
+      int base = 0;
+      uint32_t last = 0;
+      for (int w0 = 0; w0 < wpr; w0 += 32) {
+        const int w = w0 + lane;
+        const uint32_t cur = w0 == 0 ? first[u] : (w < wpr ? __ldg(r + w) : 0u);
+        const uint32_t below = __shfl_up_sync(kAllLanes, cur, 1);
+        const uint32_t prev = lane ? below >> 31 : (w0 > 0 ? __ldg(r + w0 - 1) >> 31 : 0u);
+        uint32_t t = w < wpr ? transitions_of(cur, prev) : 0u;
+        const int n = __popc(t);
+        // exclusive prefix of n over the lanes: a row has a handful of transitions, so walk the
+        // lanes that hold any (a shuffle scan where they are many)
+        uint32_t holders = __ballot_sync(kAllLanes, n != 0);
+        int pre = 0, total = 0;
+        if (__popc(holders) <= 6) {
+          while (holders) {
+            const int L = __ffs(holders) - 1;
+            holders &= holders - 1;
+            const int nL = __shfl_sync(kAllLanes, n, L);
+            if (lane > L) pre += nL;
+            total += nL;
+          }
+        } else {
+          int inc = n;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(kAllLanes, inc, o);
+            if (lane >= o) inc += v;
+          }
+          pre = inc - n;
+          total = __shfl_sync(kAllLanes, inc, 31);
+        }
+        int pos = base + pre;
+        while (t) {
+          const int b = __ffs(t) - 1;
+          t &= t - 1;
+          out[pos++] = (uint16_t)(32 * w + b);
+        }
+        base += total;
+        if (w == wpr - 1) last = cur;
+      }
+      // a run that reaches the last cell of a row that fills its last word is closed at nx
+      if ((nx & 31) == 0 && lane == ((wpr - 1) & 31) && (last >> 31)) out[base] = (uint16_t)nx;
+    }
   }
 }
 
@@ -388,7 +421,7 @@ cudaError_t vhp_launch_runs_write(const uint32_t *d_bits, int64_t npairs, int ny
                                   cudaStream_t st, int64_t *launches) {
   const int wpr = (nx + 31) / 32;
   const int64_t nrows = npairs * ny;
-  int64_t blocks = std::min<int64_t>((nrows + 7) / 8, (int64_t)sm_count * 16);
+  int64_t blocks = std::min<int64_t>((nrows + 31) / 32, (int64_t)sm_count * 8);
   runs_write_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), 256, 0, st>>>(d_bits, nrows, ny, nx, wpr, d_row_off,
                                                                            d_pair_ptr, chunk_base, d_trans);
   if (launches) *launches += 1;

@@ -492,6 +492,11 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
     }
   };
   uint32_t wb = 0; // BITS: the bits of row j0 + lane
+  // value >= thr on the bit patterns: the values are never negative (or NaN) and thr > 0, where the
+  // order of IEEE doubles is the order of their bits as integers -- two integer compares per cell
+  // instead of one on the fp64 pipe, which the step loops already saturate
+  const long long thrb = __double_as_longlong(p.thr);
+  auto ge_thr = [&](const double v) -> bool { return __double_as_longlong(v) >= thrb; };
 
   if (allocc || zero_in || (inuni && allfree)) {
     // ---- uniform tile: no arithmetic -------------------------------------------------
@@ -564,7 +569,7 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
         F = (!decltype(masked)::value || ((wrow >> s) & 1u)) ? v : 0.0;
         // (storing this lane's row straight from registers, 16 bytes every few steps, was
         // measured slower than staging: 32 partial-sector requests per store instruction)
-        if constexpr (BITS) wb |= (uint32_t)(F >= p.thr) << s;
+        if constexpr (BITS) wb |= (uint32_t)ge_thr(F) << s;
         else stage[stage_at(lane, s)] = to_out<OutT>(F);
         if (lane == wj - 1) rowE[s] = F;
       }
@@ -597,7 +602,7 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
           const double v = lerp_rn(F, b, c);
           F = (!decltype(masked)::value || ((wcol >> s) & 1u)) ? v : 0.0;
           if constexpr (BITS) {
-            const uint32_t m = __ballot_sync(kAll, F >= p.thr);
+            const uint32_t m = __ballot_sync(kAll, ge_thr(F));
             if (lane == s) wb = m;
           } else if (!decltype(masked)::value || (lane_st && s >= r0 && s <= rlast)) {
             __stcs(q, to_out<OutT>(F));
@@ -634,14 +639,14 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
         C = ((wrow >> k) & 1u) ? vC : 0.0;
         R = ((wcol >> k) & 1u) ? vR : 0.0;
         if constexpr (BITS) {
-          wb |= (uint32_t)(C >= p.thr) << k; // row j0 + lane, column k
+          wb |= (uint32_t)ge_thr(C) << k; // row j0 + lane, column k
         } else {
           stage[stage_at(lane, k)] = to_out<OutT>(C);
           stage[stage_at(k, lane)] = to_out<OutT>(R);
         }
       }
       if constexpr (BITS) { // row j0 + k, columns below k
-        const uint32_t m = __ballot_sync(kAll, lane < k && R >= p.thr);
+        const uint32_t m = __ballot_sync(kAll, lane < k && ge_thr(R));
         if (lane == k) wb |= m;
       }
       // diagonal cell q(k,k) = q(k,k-1) * occ: q(k,k-1) is lane k-1's new C (k == 0: B[0])
@@ -650,7 +655,7 @@ __device__ __forceinline__ void process_tile(const TileArgs &p, const TQuad &g, 
         const double dv = ((wrow >> k) & 1u) ? (k ? dsrc : Bv) : 0.0;
         C = dv;
         R = dv;
-        if constexpr (BITS) wb |= (uint32_t)(dv >= p.thr) << k;
+        if constexpr (BITS) wb |= (uint32_t)ge_thr(dv) << k;
         else stage[stage_at(k, k)] = to_out<OutT>(dv);
       }
     }
@@ -847,25 +852,52 @@ __device__ __forceinline__ void tile_sweep_cta(const TileArgs &p, const int map,
     // rows below the source are j = 1 .. jl - 1, rows from the source upwards j = 0 .. jl - 1
     const int ylo = sy - max(max(jl[2], jl[3]) - 1, 0), yhi = sy + max(jl[0], jl[1]) - 1;
     const int wfirst = GE ? (int)blockIdx.x * NW + warp : warp, wstride = GE ? (int)gridDim.x * NW : NW;
+    if constexpr (BITS) {
+      // Bit output: a lit row is one store of its words.  The runs (nL, nR) only change where a
+      // quadrant's tile row changes, so the rows are cut into segments of constant runs (the union
+      // of the -x and +x quadrants' tile-row boundaries), dealt over the warps; a segment computes its
+      // word masks once and then stores them row after row.  (Row by row, with the staircase
+      // looked up per row, the all-lit headline batch spent 135 instructions per row.)
+      static_assert(!GE, "bit output is a one-CTA sweep");
+      const int wprl = (nx + 31) >> 5;
+      uint32_t *const wout = reinterpret_cast<uint32_t *>(out);
+      int seg = 0;
+      for (int half = 0; half < 2 && 1.0 >= p.thr; ++half) {
+        const int qR = half ? 3 : 0, qL = half ? 2 : 1, dy = half ? -1 : 1;
+        // rows j < jend; below the source they start at j = 1 and leave out y == 0 (never written)
+        const int jend = half ? min(max(jl[2], jl[3]), sy) : max(jl[0], jl[1]);
+        for (int j = half; j < jend;) {
+          const int nbR = j < qa[qR] ? qa[qR] : qa[qR] + (((j - qa[qR]) >> 5) + 1) * 32;
+          const int nbL = j < qa[qL] ? qa[qL] : qa[qL] + (((j - qa[qL]) >> 5) + 1) * 32;
+          const int jn = min(jend, min(nbR, nbL));
+          if (seg++ % NW == warp) {
+            const int nR = lit_run(qR, j), nL = lit_run(qL, j);
+            if (nR > 0 || nL > 1) {
+              const int xfirst = nL > 1 ? max(sx - (nL - 1), 1) : sx, xend = nR > 0 ? sx + nR - 1 : sx - 1;
+              for (int w = (xfirst >> 5) + lane; w <= (xend >> 5); w += 32) {
+                uint32_t m = ~0u;
+                if (w == (xfirst >> 5)) m &= ~0u << (xfirst & 31);
+                if (w == (xend >> 5)) m &= ~0u >> (31 - (xend & 31));
+                uint32_t *q = wout + (ptrdiff_t)(sy + dy * j) * wprl + w;
+                const ptrdiff_t qs = (ptrdiff_t)dy * wprl;
+                if (m == ~0u) { // a whole word inside the lit run has no other writer
+                  for (int r = j; r < jn; ++r, q += qs) *q = m;
+                } else {
+                  for (int r = j; r < jn; ++r, q += qs) atomicOr(q, m);
+                }
+              }
+            }
+          }
+          j = jn;
+        }
+      }
+    } else
     for (int y = max(ylo, p.win_y0) + wfirst; y <= min(yhi, p.win_y1 - 1); y += wstride) {
       const bool upper = y >= sy;
       const int j = upper ? y - sy : sy - y;
       const int nR = upper ? lit_run(0, j) : lit_run(3, j);
       const int nL = upper ? lit_run(1, j) : lit_run(2, j);
       if (nR == 0 && nL <= 1) continue;
-      if constexpr (BITS) {
-        if ((!upper && y == 0) || !(1.0 >= p.thr)) continue; // zeros are not written
-        uint32_t *wrow = reinterpret_cast<uint32_t *>(out) + (size_t)y * ((nx + 31) >> 5);
-        const int xfirst = nL > 1 ? max(sx - (nL - 1), 1) : sx, xend = nR > 0 ? sx + nR - 1 : sx - 1;
-        for (int w = (xfirst >> 5) + lane; w <= (xend >> 5); w += 32) {
-          uint32_t m = ~0u;
-          if (w == (xfirst >> 5)) m &= ~0u << (xfirst & 31);
-          if (w == (xend >> 5)) m &= ~0u >> (31 - (xend & 31));
-          if (m == ~0u) wrow[w] = m; // a whole word inside the lit run has no other writer
-          else atomicOr(wrow + w, m);
-        }
-        continue;
-      }
       OutT *row = out + (size_t)y * nx;
       const OutT v = to_out<OutT>((!upper && y == 0) ? 0.0 : 1.0); // y == 0 below the source: never written
       int xa = sx - (nL - 1), xb = sx + nR - 1;
