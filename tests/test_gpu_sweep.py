@@ -376,7 +376,9 @@ def test_row_runs_bit_exact(vhp, oracle):
     last word, that do not, and rows wider than 1024 cells."""
     c = vhp.Context(0)
     rng = np.random.default_rng(5)
-    for nx, ny, nobs, seed in ((101, 101, 10, 7), (64, 40, 6, 3), (96, 33, 0, 1), (1100, 37, 30, 2), (33, 31, 2, 1)):
+    # (rows of a multiple of four words take the 16-byte kernels: 1, 2, 4 and 8 lanes per row)
+    for nx, ny, nobs, seed in ((101, 101, 10, 7), (64, 40, 6, 3), (96, 33, 0, 1), (1100, 37, 30, 2), (33, 31, 2, 1),
+                               (128, 40, 5, 9), (256, 35, 6, 2), (384, 33, 8, 4), (1024, 20, 10, 6), (1000, 9, 4, 8)):
         occ = np.stack([rect_map(nx, ny, nobs, seed + k, 3, 14) for k in range(2)])
         n = 9
         smap = rng.integers(0, 2, n).astype(np.int32)

@@ -273,6 +273,103 @@ runs_row_count_kernel(const uint32_t *__restrict__ bits, const int64_t nrows, co
   }
 }
 
+// The same two passes for rows of a multiple of four words (at most 128): G lanes per row (a power of
+// two >= words / 4), ONE 16-byte load per lane, so a load instruction covers 32 / G whole rows and a
+// warp keeps 4 of them in flight.  (One word per lane and one row at a time, both passes ran at a
+// third of the HBM rate: too few bytes in flight.)
+struct RowWords {
+  uint32_t t[4]; // transitions of this lane's four words
+  int n;         // how many
+};
+__device__ __forceinline__ RowWords row_words(const uint4 v, const int l, const int w4, const int G) {
+  RowWords r;
+  const uint32_t pw = __shfl_up_sync(kAllLanes, v.w, 1, G); // the word before this lane's first one
+  const bool have = l < w4;
+  r.t[0] = have ? transitions_of(v.x, l ? pw >> 31 : 0u) : 0u;
+  r.t[1] = have ? transitions_of(v.y, v.x >> 31) : 0u;
+  r.t[2] = have ? transitions_of(v.z, v.y >> 31) : 0u;
+  r.t[3] = have ? transitions_of(v.w, v.z >> 31) : 0u;
+  r.n = __popc(r.t[0]) + __popc(r.t[1]) + __popc(r.t[2]) + __popc(r.t[3]);
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+runs_row_count_v4_kernel(const uint4 *__restrict__ bits4, const int nrows, const int nx, const int w4,
+                         const int G, uint16_t *__restrict__ row_cnt) {
+  constexpr int R = 4;
+  const int lane = threadIdx.x & 31, l = lane & (G - 1), rpi = 32 / G, sub = lane / G;
+  const int warp0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+  const bool closes = (nx & 31) == 0; // a row that fills its last word: a run reaching the end is closed at nx
+  for (int64_t row0 = (int64_t)warp0 * rpi * R; row0 < nrows; row0 += (int64_t)nwarps * rpi * R) {
+    uint4 v[R];
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int64_t row = row0 + u * rpi + sub;
+      v[u] = (row < nrows && l < w4) ? __ldg(bits4 + row * w4 + l) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int64_t row = row0 + u * rpi + sub;
+      int c = row_words(v[u], l, w4, G).n;
+      if (closes && l == w4 - 1) c += (int)(v[u].w >> 31);
+      for (int off = G >> 1; off > 0; off >>= 1) c += __shfl_xor_sync(kAllLanes, c, off, G);
+      if (l == 0 && row < nrows) row_cnt[row] = (uint16_t)c;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+runs_write_v4_kernel(const uint4 *__restrict__ bits4, const int nrows, const int ny, const int nx, const int w4,
+                     const int G, const uint32_t *__restrict__ row_off,
+                     const unsigned long long *__restrict__ pair_ptr, const unsigned long long chunk_base,
+                     uint16_t *__restrict__ trans) {
+  constexpr int R = 4;
+  const int lane = threadIdx.x & 31, l = lane & (G - 1), rpi = 32 / G, sub = lane / G;
+  const int warp0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+  const bool closes = (nx & 31) == 0;
+  for (int64_t row0 = (int64_t)warp0 * rpi * R; row0 < nrows; row0 += (int64_t)nwarps * rpi * R) {
+    uint4 v[R];
+    unsigned long long off[R];
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int64_t row = row0 + u * rpi + sub;
+      const bool live = row < nrows;
+      v[u] = (live && l < w4) ? __ldg(bits4 + row * w4 + l) : make_uint4(0u, 0u, 0u, 0u);
+      off[u] = live ? __ldg(pair_ptr + (unsigned)row / (unsigned)ny) - chunk_base + __ldg(row_off + row) : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      RowWords rw = row_words(v[u], l, w4, G);
+      int inc = rw.n; // inclusive scan over the G lanes of the row
+      for (int o = 1; o < G; o <<= 1) {
+        const int t = __shfl_up_sync(kAllLanes, inc, o, G);
+        if (l >= o) inc += t;
+      }
+      uint16_t *out = trans + off[u] + (inc - rw.n);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t t = rw.t[k];
+        while (t) {
+          const int b = __ffs(t) - 1;
+          t &= t - 1;
+          *out++ = (uint16_t)(32 * (4 * l + k) + b);
+        }
+      }
+      if (closes && l == w4 - 1 && (v[u].w >> 31)) *out = (uint16_t)nx; // (rows past nrows hold zeros)
+    }
+  }
+}
+
+// rows the 16-byte kernels take: whole 16-byte pieces, at most 32 lanes per row, 32-bit row numbers
+bool runs_v4_ok(const void *bits, int64_t nrows, int wpr, int *w4, int *G) {
+  if (wpr % 4 != 0 || wpr > 128 || nrows >= ((int64_t)1 << 31) || ((uintptr_t)bits & 15) != 0) return false;
+  *w4 = wpr / 4;
+  int g = 1;
+  while (g < *w4) g <<= 1;
+  *G = g;
+  return true;
+}
+
 // one CTA per pair: row_off[row] = transitions of the pair's earlier rows, pair_tot[pair] = all of them
 __global__ void __launch_bounds__(256)
 runs_rows_kernel(const uint16_t *__restrict__ row_cnt, const int ny, uint32_t *__restrict__ row_off,
@@ -397,6 +494,14 @@ runs_write_kernel(const uint32_t *__restrict__ bits, const int64_t nrows, const 
 
 cudaError_t vhp_launch_runs_row_count(const uint32_t *d_bits, int64_t nrows, int nx, uint16_t *d_row_cnt,
                                       int sm_count, cudaStream_t st, int64_t *launches) {
+  int w4, G;
+  if (runs_v4_ok(d_bits, nrows, (nx + 31) / 32, &w4, &G)) {
+    const int64_t per_block = (int64_t)8 * (32 / G) * 4; // rows one pass of a block covers
+    const int64_t blocks4 = std::max<int64_t>(1, std::min<int64_t>((nrows + per_block - 1) / per_block, (int64_t)sm_count * 8));
+    runs_row_count_v4_kernel<<<(unsigned)blocks4, 256, 0, st>>>((const uint4 *)d_bits, (int)nrows, nx, w4, G, d_row_cnt);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+  }
   const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((nrows + 31) / 32, (int64_t)sm_count * 8));
   runs_row_count_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_bits, nrows, nx, (nx + 31) / 32, d_row_cnt);
   if (launches) *launches += 1;
@@ -421,6 +526,15 @@ cudaError_t vhp_launch_runs_write(const uint32_t *d_bits, int64_t npairs, int ny
                                   cudaStream_t st, int64_t *launches) {
   const int wpr = (nx + 31) / 32;
   const int64_t nrows = npairs * ny;
+  int w4, G;
+  if (runs_v4_ok(d_bits, nrows, wpr, &w4, &G)) {
+    const int64_t per_block = (int64_t)8 * (32 / G) * 4;
+    const int64_t blocks4 = std::max<int64_t>(1, std::min<int64_t>((nrows + per_block - 1) / per_block, (int64_t)sm_count * 8));
+    runs_write_v4_kernel<<<(unsigned)blocks4, 256, 0, st>>>((const uint4 *)d_bits, (int)nrows, ny, nx, w4, G, d_row_off,
+                                                           d_pair_ptr, chunk_base, d_trans);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+  }
   int64_t blocks = std::min<int64_t>((nrows + 31) / 32, (int64_t)sm_count * 8);
   runs_write_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), 256, 0, st>>>(d_bits, nrows, ny, nx, wpr, d_row_off,
                                                                            d_pair_ptr, chunk_base, d_trans);
