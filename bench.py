@@ -1083,7 +1083,7 @@ def main():
     kern_ms = statistics.mean(step_ms)
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(args.workload, n),
+                "frac": achieved / peak, "traffic": ncu_traffic(args.workload, n) if args.store == "f32" else None,  # the captures are of the fp32 kernel
                 "kernel": "sweep_tile_kernel", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "traffic_source": "profiles/k1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per pair; "
