@@ -55,3 +55,18 @@ def test_all_gpus_equal_single_gpu():
     assert r["all_ranks_equal"] and all(q["equal_single_gpu"] for q in r["queries"])
     r = _run(n, 4096, 2, port=29545, p2p=False)
     assert r["all_ranks_equal"] and all(q["equal_single_gpu"] for q in r["queries"])
+
+
+def test_sharded_batch_equals_single_gpu():
+    """SURVEY 4 item iv on hardware: a (map, source) batch and a planner batch cut over the GPUs of the
+    box (sharding.py, no data-path collective) give, item for item, the bytes one GPU computes for the
+    whole batch (fp64 fields, thresholded bits, planner outputs; tools/sharded_batch_gpu.py)."""
+    n = _gpus()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", "29551", os.path.join(ROOT, "tools", "sharded_batch_gpu.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    r = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+    assert r["world"] == n and r["sweeps_equal"] and r["planner_equal"], r
