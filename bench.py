@@ -892,6 +892,42 @@ def main():
                "pageable_buffer": pageable,
                "api": "vhp_visibility_batch (host buffers; pinned output; H2D + kernel + D2H (+ host expansion) "
                       "inside the timed region; %d result pairs compared with the device-resident run)" % len(probe)}
+        # ---- the same fields as a packed handle (vhp_visibility_batch_packed): the lossless packed form
+        # stays in pinned memory owned by the handle, pairs are expanded on demand
+        ph = C.c_void_p()
+
+        def packed_step():
+            st = lib.vhp_visibility_batch_packed(host_ctx.h, maps.ctypes.data, nmaps, nx, ny, src.ctypes.data,
+                                                 None if smap is None else smap.ctypes.data, n, dt, C.byref(ph))
+            assert st == 0, host_ctx.lib.vhp_last_error(host_ctx.h)
+        packed_step()  # (allocates the handle's pinned memory; later calls reuse it)
+        barrier()
+        kp = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(kp):
+            packed_step()
+        t_ph = (time.perf_counter() - t0) / kp
+        if world > 1:
+            tt = torch.tensor([t_ph], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_ph = float(tt.item())
+        one = np.empty((ny, nx), dtype=out_np.dtype)
+        t_x = 0.0
+        for p_ in probe:  # lazy expansion of single pairs: the bytes of the device-resident run
+            tx0 = time.perf_counter()
+            st = lib.vhp_packed_expand(ph, int(p_), 1, one.ctypes.data, 1)
+            t_x += time.perf_counter() - tx0
+            assert st == 0 and np.array_equal(one, out_t[p_].cpu().numpy()), f"packed handle differs (pair {p_})"
+        e2e["packed_handle"] = {"value": cells_e2e * world / t_ph / 1e9, "unit": "Gcells/s", "ms_per_step": t_ph * 1e3,
+                                "steps": kp, "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],
+                                "d2h_bytes_per_step": int(lib.vhp_packed_bytes(ph)),
+                                "result_bytes_per_step": int(n) * nx * ny * esz,
+                                "expand_one_pair_ms": t_x / len(probe) * 1e3,
+                                "api": "vhp_visibility_batch_packed (host buffers; H2D, sweeps, packing and the D2H of "
+                                       "the packed stream into the handle's pinned memory inside the timed region; "
+                                       "nothing is expanded in the call) + vhp_packed_expand of the probe pairs "
+                                       "afterwards, bit-identical to the device-resident fields"}
+        lib.vhp_packed_destroy(ph)
         # ---- the same call with the thresholded, bit-packed result (vhp_visibility_batch_bin)
         # (checked against the fp64 fields of the probe pairs: an fp32 value can sit on the other side
         # of the threshold)

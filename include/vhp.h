@@ -112,6 +112,27 @@ vhp_status vhp_visibility_batch_dev(vhp_context *ctx, const uint8_t *d_occ,
                                     const int32_t *d_src_xy,
                                     const int32_t *d_src_map, int64_t npairs,
                                     vhp_dtype dtype, void *d_out);
+/* The same fields as a PACKED HANDLE: lossless, expanded lazily.  Visibility fields are mostly flat
+ * (lit 1.0, shadow 0.0), so the device cuts the results into 128-byte units that are either uniform
+ * (one element value) or literal, and only one element per unit plus the literal units cross PCIe --
+ * 6.5 % of the bytes on the empty 1000 x 1000 batch.  vhp_visibility_batch expands that stream into the
+ * caller's buffer inside the call (and is then bound by the host's memory bandwidth: 16 GB of stores per
+ * 4096 sweeps); this entry point keeps it, in pinned host memory owned by the handle, and
+ * vhp_packed_expand rebuilds any range of pairs on demand, bit-identical to what vhp_visibility_batch
+ * writes.  *handle = NULL creates a handle; passing an existing one reuses its memory (the steady
+ * state of a caller that processes batch after batch allocates nothing). */
+typedef struct vhp_packed vhp_packed;
+vhp_status vhp_visibility_batch_packed(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx,
+                                       int ny, const int32_t *src_xy, const int32_t *src_map,
+                                       int64_t npairs, vhp_dtype dtype, vhp_packed **handle);
+int64_t vhp_packed_pairs(const vhp_packed *h);      /* pairs held */
+int64_t vhp_packed_bytes(const vhp_packed *h);      /* bytes of packed data held (= moved over PCIe) */
+int64_t vhp_packed_pair_bytes(const vhp_packed *h); /* bytes of one expanded pair: nx * ny * element size */
+/* out[0 .. npairs * pair_bytes) = the fields of pairs [first_pair, first_pair + npairs); host threads
+ * (nthreads <= 0: one per 64 MB, at most the hardware's) */
+vhp_status vhp_packed_expand(const vhp_packed *h, int64_t first_pair, int64_t npairs, void *out,
+                             int nthreads);
+void vhp_packed_destroy(vhp_packed *h);
 /* Thresholded binary visibility, bit-packed: the part of the result that decides (which cells a
  * light source sees), 32 x smaller than fp32 fields -- 125 KB instead of 4 MB per 1000 x 1000 sweep,
  * so the host-buffer call is no longer bound by the host's memory system and scales with the

@@ -408,3 +408,31 @@ def test_row_runs_bit_exact(vhp, oracle):
                                          rc.ctypes.data, pp.ctypes.data, tr.ctypes.data, 10, C.byref(used))
     assert st == -1 and used.value == 98   # rows 1..49: visible on [1, 50); row 0 is the never-written border
     c.close()
+
+
+def test_packed_handle_expands_bit_identical(vhp):
+    """vhp_visibility_batch_packed + vhp_packed_expand: the whole batch, single pairs and ranges that
+    start / end inside 128-byte units (101 x 101 x 4 bytes is not a multiple of 128) rebuild exactly the
+    bytes vhp_visibility_batch returns; fp32 and fp64; several chunks; a reused handle."""
+    rng = np.random.default_rng(31)
+    c = vhp.Context(0)
+    h = None
+    for nx, ny, nobs, n, dt in ((101, 101, 10, 40, vhp.F32), (1000, 1000, 15, 150, vhp.F32), (333, 77, 6, 25, vhp.F64),
+                                (64, 64, 0, 9, vhp.F32), (1000, 1000, 0, 290, vhp.F64)):
+        occ = np.stack([rect_map(nx, ny, nobs, 70 + k, 8, 120 if nx > 500 else 20) for k in range(2)])
+        smap = rng.integers(0, 2, n).astype(np.int32)
+        src = np.stack([rng.integers(0, nx, n), rng.integers(0, ny, n)], 1).astype(np.int32)
+        want = c.visibility_batch(occ, src, src_map=smap, dtype=dt)
+        h = c.visibility_batch_packed(occ, src, src_map=smap, dtype=dt, handle=h)
+        assert len(h) == n and 0 < h.nbytes < want.nbytes
+        got = h.expand()
+        assert got.dtype == want.dtype and np.array_equal(got.view(np.uint8), want.view(np.uint8)), (nx, ny)
+        for first, count in ((0, 1), (n - 1, 1), (n // 3, 5), (1, n - 2)):
+            part = h.expand(first, count, threads=3 if count > 2 else 1)
+            assert np.array_equal(part.view(np.uint8), want[first:first + count].view(np.uint8)), (nx, ny, first, count)
+        if nx == 1000 and nobs == 0:
+            assert h.nbytes < 0.1 * want.nbytes  # open maps: one element per unit and a few literal units
+    with pytest.raises(vhp.VhpError):
+        h.expand(0, len(h) + 1)
+    h.close()
+    c.close()

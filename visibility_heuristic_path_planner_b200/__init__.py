@@ -106,6 +106,13 @@ def load_library(build_if_missing: bool = True):
     lib.vhp_visibility_batch_runs.argtypes = [vp, vp, i32, i32, i32, vp, vp, i64, C.c_double, vp, vp, vp, i64,
                                               C.POINTER(i64)]
     lib.vhp_runs_to_bits.argtypes = [vp, vp, vp, i64, i32, i32, vp]
+    lib.vhp_visibility_batch_packed.argtypes = [vp, vp, i32, i32, i32, vp, vp, i64, i32, C.POINTER(vp)]
+    for name in ("vhp_packed_pairs", "vhp_packed_bytes", "vhp_packed_pair_bytes"):
+        getattr(lib, name).argtypes = [vp]
+        getattr(lib, name).restype = i64
+    lib.vhp_packed_expand.argtypes = [vp, i64, i64, vp, i32]
+    lib.vhp_packed_destroy.argtypes = [vp]
+    lib.vhp_packed_destroy.restype = None
     lib.vhp_release_maps_dev.argtypes = [vp]
     lib.vhp_context_device.argtypes = [vp]
     lib.vhp_prepare_maps_dev.argtypes = [vp, vp, i32, i32, i32]
@@ -153,6 +160,42 @@ def _occ_u8(occ):
     if occ.ndim == 2:
         occ = occ[None]
     return np.ascontiguousarray(occ != 0, dtype=np.uint8)
+
+
+class PackedFields:
+    """Handle of vhp_visibility_batch_packed: the fields of a batch in packed form on the host."""
+
+    def __init__(self, lib):
+        self.lib, self.h, self.shape, self.dtype = lib, C.c_void_p(), None, None
+
+    def __len__(self):
+        return int(self.lib.vhp_packed_pairs(self.h))
+
+    @property
+    def nbytes(self):
+        """bytes of packed data held (what crossed PCIe)"""
+        return int(self.lib.vhp_packed_bytes(self.h))
+
+    def expand(self, first=0, count=None, out=None, threads=0):
+        """(count, ny, nx) fields of pairs [first, first + count), bit-identical to visibility_batch."""
+        count = len(self) - first if count is None else count
+        if out is None:
+            out = np.empty((count,) + self.shape, self.dtype)
+        st = self.lib.vhp_packed_expand(self.h, first, count, _np_ptr(out), threads)
+        if st != 0:
+            raise VhpError(st, self.lib.vhp_last_error(None).decode())
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.vhp_packed_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Context:
@@ -245,6 +288,19 @@ class Context:
         """computeVisibility for every (map, source) pair -> (npairs, ny, nx).  `out`: an
         array to fill instead of a new one (pinned host memory gets the fastest transport)."""
         return self._batch_host(self.lib.vhp_visibility_batch, occ, src_xy, src_map, dtype, out)
+
+    def visibility_batch_packed(self, occ, src_xy, src_map=None, dtype=F64, handle=None):
+        """computeVisibility for every pair, kept as a lossless packed handle
+        (vhp_visibility_batch_packed); `handle`: a PackedFields of an earlier call to refill."""
+        occ = _occ_u8(occ)
+        nmaps, ny, nx = occ.shape
+        xy = np.ascontiguousarray(src_xy, dtype=np.int32).reshape(-1, 2)
+        mp = None if src_map is None else np.ascontiguousarray(src_map, dtype=np.int32)
+        h = handle if handle is not None else PackedFields(self.lib)
+        self._check(self.lib.vhp_visibility_batch_packed(self.h, _np_ptr(occ), nmaps, nx, ny, _np_ptr(xy), _np_ptr(mp),
+                                                         xy.shape[0], dtype, C.byref(h.h)))
+        h.shape, h.dtype = (ny, nx), (np.float32 if dtype == F32 else np.float64)
+        return h
 
     def visibility_batch_bin(self, occ, src_xy, threshold, src_map=None, out=None):
         """Thresholded binary visibility, bit-packed (vhp_visibility_batch_bin): uint32

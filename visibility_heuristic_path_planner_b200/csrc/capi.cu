@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -475,6 +476,153 @@ vhp_status run_host_packed(vhp_context *ctx, Op op, int nmaps, int nx, int ny, c
                  trace_pack_ms, 1e3 * (pool.busy_seconds() - trace_busy0), pool.threads(),
                  1e3 * trace_wait_s, 1e3 * trace_ticket_s, ctx->last_d2h_bytes / 1e9,
                  (double)(launched * chunk * pair_bytes) / 1e9);
+  return VHP_OK;
+}
+
+// ---- packed handle: the lossless packed form of a batch of fields, kept on the host -------------
+// vhp_visibility_batch_packed runs the same chunks as run_host_packed in staged form, but the meta
+// blocks and literal streams stay in pinned memory owned by the handle instead of being expanded:
+// the call moves 3-7 % of the field bytes over PCIe and writes nothing else to host memory.
+// vhp_packed_expand rebuilds any range of pairs later (bit-identical to vhp_visibility_batch).
+} // namespace
+
+struct vhp_packed {
+  struct Block { char *p; size_t cap, used; };
+  struct Chunk { size_t meta_off, lit_off; int meta_blk, lit_blk; int64_t nunits, np; uint64_t nlit; };
+  int device = 0;
+  int nx = 0, ny = 0, elem = 4;
+  int64_t npairs = 0, chunk_pairs = 0;
+  size_t pair_bytes = 0;
+  std::vector<Block> blocks; // pinned host memory, reused by the next call on this handle
+  std::vector<Chunk> chunks;
+  int64_t bytes_held = 0;
+
+  // `bytes` of pinned memory, 256-byte aligned: from the first block with room, else a new block
+  bool take(size_t bytes, int *blk, size_t *off) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    for (size_t b = 0; b < blocks.size(); ++b)
+      if (blocks[b].cap - blocks[b].used >= bytes) {
+        *blk = (int)b; *off = blocks[b].used; blocks[b].used += bytes;
+        return true;
+      }
+    Block nb{nullptr, std::max<size_t>(bytes, (size_t)128 << 20), 0};
+    if (cudaHostAlloc((void **)&nb.p, nb.cap, cudaHostAllocDefault) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return false;
+    }
+    nb.used = bytes;
+    blocks.push_back(nb);
+    *blk = (int)blocks.size() - 1; *off = 0;
+    return true;
+  }
+  VhpPackedChunk view(const Chunk &c) const {
+    const char *meta = blocks[c.meta_blk].p + c.meta_off;
+    const int64_t nwords = (c.nunits + 31) / 32;
+    VhpPackedChunk v;
+    v.mask = (const uint32_t *)(meta + kVhpPackMetaHead);
+    v.word_base = v.mask + nwords;
+    v.desc = meta + kVhpPackMetaHead + (size_t)nwords * 8;
+    v.elem_bytes = elem;
+    v.literals = c.nlit ? blocks[c.lit_blk].p + c.lit_off : meta; // (never read when there are none)
+    v.nunits = c.nunits;
+    v.valid_bytes = (size_t)c.np * pair_bytes;
+    return v;
+  }
+};
+
+namespace {
+
+vhp_status run_host_to_packed(vhp_context *ctx, int nmaps, int nx, int ny, const int32_t *d_xy,
+                              const int32_t *d_map, int64_t n, vhp_dtype dtype, vhp_packed *h) {
+  constexpr int NS = vhp_context::kPackSets;
+  const size_t cells = (size_t)nx * ny, esz = dtype == VHP_F32 ? 4 : 8;
+  const size_t pair_bytes = cells * esz;
+  // chunks of 1 GB of fields (nothing is expanded here, so a chunk costs one event wait and two copies:
+  // with 256 MB chunks those fixed costs were a third of the call)
+  int64_t chunk = std::max<int64_t>(1, (int64_t)(((size_t)1 << 30) / pair_bytes));
+  chunk = std::min(chunk, n);
+  const int64_t nchunks = (n + chunk - 1) / chunk;
+  const int64_t units_max = (int64_t)(((size_t)chunk * pair_bytes + kVhpPackUnit - 1) / kVhpPackUnit);
+  const size_t meta_max = vhp_pack_meta_bytes(units_max, (int)esz), lit_max = (size_t)units_max * kVhpPackUnit;
+  h->device = ctx->device; h->nx = nx; h->ny = ny; h->elem = (int)esz;
+  h->npairs = n; h->chunk_pairs = chunk; h->pair_bytes = pair_bytes;
+  h->chunks.assign((size_t)nchunks, vhp_packed::Chunk{});
+  for (auto &b : h->blocks) b.used = 0;
+  h->bytes_held = 0;
+  vhp_status st;
+  const int nsets = (int)std::min<int64_t>(NS, nchunks);
+  for (int s = 0; s < nsets; ++s) {
+    if ((st = ensure(ctx, ctx->b_pack_out[s], lit_max)) != VHP_OK) return st;
+    if ((st = ensure(ctx, ctx->b_pack_meta[s], meta_max)) != VHP_OK) return st;
+    if ((st = ensure(ctx, ctx->b_pack_lit[s], lit_max)) != VHP_OK) return st;
+  }
+  auto chunk_units = [&](int64_t it) {
+    const int64_t np = std::min(chunk, n - it * chunk);
+    return (int64_t)(((size_t)np * pair_bytes + kVhpPackUnit - 1) / kVhpPackUnit);
+  };
+  // chunk `it`: sweeps and packing on the compute stream, the copy of the meta block on the copy stream
+  auto launch = [&](int64_t it) -> vhp_status {
+    const int s = (int)(it % NS);
+    const int64_t p0 = it * chunk, np = std::min(chunk, n - p0), nu = chunk_units(it);
+    vhp_packed::Chunk &c = h->chunks[(size_t)it];
+    c.nunits = nu; c.np = np;
+    if (!h->take(vhp_pack_meta_bytes(nu, (int)esz), &c.meta_blk, &c.meta_off))
+      return fail(ctx, VHP_ERR_CUDA, "vhp_visibility_batch_packed: out of pinned host memory");
+    if (it >= NS) VHP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_pack_t0[s], 0)); // set s copied out
+    vhp_status r = run_dev(ctx, Op::Sweep, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, d_xy + 2 * p0,
+                           d_map ? d_map + p0 : nullptr, np, dtype, ctx->b_pack_out[s].p);
+    if (r != VHP_OK) return r;
+    // (packing is an HBM-speed pass here -- nothing goes to host memory -- so it stays on the compute
+    // stream and the copy stream carries copies only)
+    VHP_CUDA(ctx, vhp_launch_pack_results(ctx->b_pack_out[s].p, nu, (int)esz, ctx->b_pack_meta[s].p,
+                                          ctx->b_pack_lit[s].p, nullptr, 0, 0, ctx->sm_count, ctx->stream,
+                                          &ctx->launches));
+    VHP_CUDA(ctx, cudaEventRecord(ctx->ev_pack_lit[s], ctx->stream));
+    VHP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pack_lit[s], 0));
+    VHP_CUDA(ctx, cudaMemcpyAsync(h->blocks[c.meta_blk].p + c.meta_off, ctx->b_pack_meta[s].p,
+                                  vhp_pack_meta_bytes(nu, (int)esz), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    VHP_CUDA(ctx, cudaEventRecord(ctx->ev_pack_meta[s], ctx->copy_stream));
+    return VHP_OK;
+  };
+  // ... once its meta block has arrived the literal count is known: copy that many units
+  auto finish = [&](int64_t it) -> vhp_status {
+    const int s = (int)(it % NS);
+    vhp_packed::Chunk &c = h->chunks[(size_t)it];
+    VHP_CUDA(ctx, cudaEventSynchronize(ctx->ev_pack_meta[s]));
+    c.nlit = *(const uint64_t *)(h->blocks[c.meta_blk].p + c.meta_off);
+    const size_t meta_bytes = vhp_pack_meta_bytes(c.nunits, (int)esz), lit_bytes = (size_t)c.nlit * kVhpPackUnit;
+    if (c.nlit) {
+      if (!h->take(lit_bytes, &c.lit_blk, &c.lit_off))
+        return fail(ctx, VHP_ERR_CUDA, "vhp_visibility_batch_packed: out of pinned host memory");
+      VHP_CUDA(ctx, cudaMemcpyAsync(h->blocks[c.lit_blk].p + c.lit_off, ctx->b_pack_lit[s].p, lit_bytes,
+                                    cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+    VHP_CUDA(ctx, cudaEventRecord(ctx->ev_pack_t0[s], ctx->copy_stream)); // the set's device buffers are free
+    ctx->last_d2h_bytes += (int64_t)(meta_bytes + lit_bytes);
+    h->bytes_held += (int64_t)(meta_bytes + lit_bytes);
+    return VHP_OK;
+  };
+  vhp_status result = VHP_OK;
+  int64_t launched = 0, finished = 0;
+  for (int64_t it = 0; it < nchunks && result == VHP_OK; ++it) {
+    if ((result = launch(it)) != VHP_OK) break;
+    ++launched;
+    if (it >= 1) {
+      if ((result = finish(it - 1)) != VHP_OK) break;
+      ++finished;
+    }
+  }
+  while (result == VHP_OK && finished < launched) {
+    result = finish(finished);
+    if (result == VHP_OK) ++finished;
+  }
+  cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream);
+  cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+  if (e2 == cudaSuccess) e2 = e1;
+  if (result != VHP_OK) return result;
+  if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "sync stream");
+  ctx->last_result_bytes = (int64_t)((size_t)n * pair_bytes);
+  ctx->last_transport_packed = 1;
   return VHP_OK;
 }
 
@@ -1058,6 +1206,118 @@ vhp_status vhp_visibility_batch(vhp_context *ctx, const uint8_t *occ, int nmaps,
                                 const int32_t *src_xy, const int32_t *src_map, int64_t npairs,
                                 vhp_dtype dtype, void *out) {
   return run_host(ctx, Op::Sweep, occ, nmaps, nx, ny, src_xy, src_map, npairs, dtype, out);
+}
+
+vhp_status vhp_visibility_batch_packed(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx, int ny,
+                                       const int32_t *src_xy, const int32_t *src_map, int64_t npairs,
+                                       vhp_dtype dtype, vhp_packed **handle) {
+  if (!handle) return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_visibility_batch_packed: null handle pointer");
+  vhp_status st = check_common(ctx, occ, nmaps, nx, ny, src_xy, npairs, dtype, handle);
+  if (st != VHP_OK) return st;
+  if ((st = check_points(ctx, src_xy, 2, src_map, npairs, nmaps, nx, ny, "vhp_visibility_batch_packed")) != VHP_OK)
+    return st;
+  ctx->last_d2h_bytes = ctx->last_result_bytes = 0;
+  ctx->last_transport_packed = 0;
+  VHP_ON_DEVICE(ctx);
+  vhp_packed *h = *handle;
+  const bool fresh = h == nullptr;
+  if (fresh) {
+    h = new (std::nothrow) vhp_packed();
+    if (!h) return fail(ctx, VHP_ERR_CUDA, "vhp_visibility_batch_packed: out of memory");
+  } else if (h->device != ctx->device && !h->blocks.empty()) {
+    return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_visibility_batch_packed: the handle belongs to another device");
+  }
+  h->device = ctx->device;
+  h->npairs = 0;
+  h->chunks.clear();
+  auto run = [&]() -> vhp_status {
+    if (npairs == 0) return VHP_OK;
+    const size_t cells = (size_t)nx * ny, occ_bytes = (size_t)nmaps * cells;
+    vhp_status r;
+    if ((r = ensure(ctx, ctx->b_occ, occ_bytes)) != VHP_OK) return r;
+    if ((r = ensure(ctx, ctx->b_src, (size_t)npairs * 8)) != VHP_OK) return r;
+    if (src_map && (r = ensure(ctx, ctx->b_map, (size_t)npairs * 4)) != VHP_OK) return r;
+    VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_occ.p, occ, occ_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_src.p, src_xy, (size_t)npairs * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (src_map)
+      VHP_CUDA(ctx, cudaMemcpyAsync(ctx->b_map.p, src_map, (size_t)npairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->planes_sticky = false;
+    ctx->tile_src = nullptr;
+    if (ctx->sweep_impl == 0 && (vhp_sweep_tile_supported(nx, ny) || vhp_sweep_grid_supported(nx, ny))) {
+      if ((r = pack_tile(ctx, (const uint8_t *)ctx->b_occ.p, nmaps, nx, ny, true)) != VHP_OK) return r;
+      ctx->planes_sticky = true;
+    }
+    r = run_host_to_packed(ctx, nmaps, nx, ny, (const int32_t *)ctx->b_src.p,
+                           src_map ? (const int32_t *)ctx->b_map.p : nullptr, npairs, dtype, h);
+    ctx->planes_sticky = false;
+    ctx->tile_src = nullptr;
+    if (r != VHP_OK) return r;
+    return check_device_error(ctx);
+  };
+  st = run();
+  if (st != VHP_OK) {
+    h->npairs = 0;
+    h->chunks.clear();
+    if (fresh) vhp_packed_destroy(h);
+    return st;
+  }
+  *handle = h;
+  return VHP_OK;
+}
+
+int64_t vhp_packed_pairs(const vhp_packed *h) { return h ? h->npairs : 0; }
+int64_t vhp_packed_bytes(const vhp_packed *h) { return h ? h->bytes_held : 0; }
+int64_t vhp_packed_pair_bytes(const vhp_packed *h) { return h ? (int64_t)h->pair_bytes : 0; }
+
+vhp_status vhp_packed_expand(const vhp_packed *h, int64_t first_pair, int64_t npairs, void *out, int nthreads) {
+  if (!h || first_pair < 0 || npairs < 0 || first_pair + npairs > h->npairs || (npairs > 0 && !out))
+    return vhp_i_fail(nullptr, VHP_ERR_INVALID_ARG, "vhp_packed_expand: null handle / buffer or pairs out of range");
+  if (npairs == 0) return VHP_OK;
+  const size_t b_begin = (size_t)first_pair * h->pair_bytes, b_end = (size_t)(first_pair + npairs) * h->pair_bytes;
+  const size_t chunk_bytes = (size_t)h->chunk_pairs * h->pair_bytes;
+  // slices of about equal size, cut at 128-byte units of the batch's first chunk (any cut is valid)
+  const size_t total = b_end - b_begin;
+  int nt = nthreads > 0 ? nthreads : (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()),
+                                                           (total + ((size_t)64 << 20) - 1) / ((size_t)64 << 20));
+  nt = std::max(1, std::min(nt, 64));
+  auto work = [&](size_t lo, size_t hi) { // bytes [lo, hi) of the whole batch
+    while (lo < hi) {
+      const size_t ci = lo / chunk_bytes, c0 = ci * chunk_bytes;
+      const size_t upto = std::min(hi, c0 + chunk_bytes);
+      vhp_expand_bytes(h->view(h->chunks[ci]), lo - c0, upto - c0, (char *)out + (lo - b_begin));
+      lo = upto;
+    }
+  };
+  if (nt == 1) {
+    work(b_begin, b_end);
+    return VHP_OK;
+  }
+  const size_t per = ((total / nt) + 127) & ~(size_t)127;
+  std::vector<std::thread> th;
+  try {
+    for (int t = 0; t < nt; ++t) {
+      const size_t lo = b_begin + std::min(total, (size_t)t * per), hi = t == nt - 1 ? b_end : b_begin + std::min(total, (size_t)(t + 1) * per);
+      if (lo < hi) th.emplace_back(work, lo, hi);
+    }
+  } catch (...) { // no more threads to be had: the caller's thread does the rest
+    const size_t done = th.size();
+    for (auto &t : th) t.join();
+    work(b_begin + std::min(total, done * per), b_end);
+    return VHP_OK;
+  }
+  for (auto &t : th) t.join();
+  return VHP_OK;
+}
+
+void vhp_packed_destroy(vhp_packed *h) {
+  if (!h) return;
+  int cur = 0;
+  const bool have = cudaGetDevice(&cur) == cudaSuccess;
+  if (!h->blocks.empty()) cudaSetDevice(h->device);
+  for (auto &b : h->blocks) cudaFreeHost(b.p);
+  if (have) cudaSetDevice(cur);
+  (void)cudaGetLastError();
+  delete h;
 }
 
 vhp_status vhp_visibility_variant_batch_dev(vhp_context *ctx, const uint8_t *d_occ, int nmaps, int nx,

@@ -83,6 +83,47 @@ void expand_words(const VhpPackedChunk &c, int64_t w0, int64_t w1) {
 
 } // namespace
 
+// Bytes [b0, b1) of a packed chunk (staged form: the literal units are in c.literals) -> out[0 .. b1 - b0).
+// Any byte range: the lazy side of the packed handle (vhp_packed_expand) asks for single pairs, which
+// start and end inside units.  A uniform unit's pattern has the period of one element and units start on
+// multiples of 128 bytes of the chunk, so a range that starts on an element boundary stays in phase.
+void vhp_expand_bytes(const VhpPackedChunk &c, size_t b0, size_t b1, char *out) {
+  b1 = std::min(b1, c.valid_bytes);
+  if (b0 >= b1) return;
+  const int64_t u0 = (int64_t)(b0 / kVhpPackUnit), u1 = (int64_t)((b1 - 1) / kVhpPackUnit);
+  for (int64_t u = u0; u <= u1; ++u) {
+    const size_t ub = (size_t)u * kVhpPackUnit;
+    const size_t lo = std::max(b0, ub), hi = std::min(b1, ub + kVhpPackUnit);
+    char *dst = out + (lo - b0);
+    const uint32_t m = c.mask[u >> 5];
+    if ((m >> (u & 31)) & 1u) {
+      // the literal units of one mask word are consecutive in the stream, from word_base on (the words
+      // themselves took their slots in no particular order)
+      const size_t lit = (size_t)c.word_base[u >> 5] + __builtin_popcount(m & (uint32_t)((1ull << (u & 31)) - 1ull));
+      std::memcpy(dst, c.literals + lit * kVhpPackUnit + (lo - ub), hi - lo);
+    } else if (c.elem_bytes == 4) {
+      const uint32_t e = static_cast<const uint32_t *>(c.desc)[u];
+      if (hi - lo == (size_t)kVhpPackUnit && (((uintptr_t)dst) & 15u) == 0) {
+        fill_unit(dst, ((uint64_t)e << 32) | e, kVhpPackUnit);
+      } else {
+        uint32_t blk[kVhpPackUnit / 4];
+        for (uint32_t &b : blk) b = e;
+        std::memcpy(dst, reinterpret_cast<const char *>(blk) + ((lo - ub) & 3u), hi - lo);
+      }
+    } else {
+      const uint64_t e = static_cast<const uint64_t *>(c.desc)[u];
+      if (hi - lo == (size_t)kVhpPackUnit && (((uintptr_t)dst) & 15u) == 0) {
+        fill_unit(dst, e, kVhpPackUnit);
+      } else {
+        uint64_t blk[kVhpPackUnit / 8 + 1];
+        for (uint64_t &b : blk) b = e;
+        std::memcpy(dst, reinterpret_cast<const char *>(blk) + ((lo - ub) & 7u), hi - lo);
+      }
+    }
+  }
+  _mm_sfence();
+}
+
 struct VhpExpandPool::Impl {
   struct Job {
     VhpPackedChunk chunk;

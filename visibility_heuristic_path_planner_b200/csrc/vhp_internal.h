@@ -74,6 +74,9 @@ cudaError_t vhp_launch_runs_write(const uint32_t *d_bits, int64_t npairs, int ny
                                   unsigned long long chunk_base, uint16_t *d_trans, int sm_count,
                                   cudaStream_t st, int64_t *launches);
 
+// bytes [b0, b1) of a packed chunk in staged form (literals != null) -> out (host_expand.cpp)
+void vhp_expand_bytes(const VhpPackedChunk &c, size_t b0, size_t b1, char *out);
+
 // host threads that expand packed chunks into the caller's buffer (FIFO, each job is spread
 // over all threads)
 class VhpExpandPool {
