@@ -10,6 +10,16 @@
 
 #include "sweep_tile_body.cuh"
 
+// Single-warp CTAs: 32 per SM would need 64 registers per thread, which the tile body only reaches with
+// spills, and shared memory keeps fewer than 32 resident from about 64 x 64 maps on.  Compiled for 20
+// per SM (80 registers, no spills): 256 x 256 maps (c4) 616 -> 647 Gcells/s (a bound of 24: 638; 16 and
+// 12, 90 registers: 609), 101 x 101 and 64 x 64 maps +3 % (tools/small_batch_probe.py).
+#ifndef VHP_NW1_MINB
+#define VHP_NW1_MINB 20
+#endif
+#ifndef VHP_NW4_MINB
+#define VHP_NW4_MINB 5 // 4-warp CTAs (mid-size batches of small maps): 96 registers, no spills; 2000 pairs of
+#endif                 // 256 x 256: 370 (bound 8, 64 registers, spills) -> 436 (6) -> 444 Gcells/s (5)
 #ifndef VHP_NW8_MINB
 #define VHP_NW8_MINB 3 // resident 8-warp CTAs per SM the register allocation aims at
 #endif
@@ -203,9 +213,9 @@ int tile_warps_for(int nx, int ny, int64_t npairs) {
 template <typename OutT>
 cudaError_t launch_tile(const TileArgs &p, int64_t npairs, cudaStream_t st) {
   switch (tile_warps_for(p.nx, p.ny, npairs)) {
-    case 1: return launch_tile_nw<OutT, 1, 32>(p, npairs, st);
+    case 1: return launch_tile_nw<OutT, 1, VHP_NW1_MINB>(p, npairs, st);
     case 2: return launch_tile_nw<OutT, 2, 12>(p, npairs, st);
-    case 4: return launch_tile_nw<OutT, 4, 8>(p, npairs, st);
+    case 4: return launch_tile_nw<OutT, 4, VHP_NW4_MINB>(p, npairs, st);
     case 6: return launch_tile_nw<OutT, 6, 4>(p, npairs, st);
     case 10: return launch_tile_nw<OutT, 10, 3>(p, npairs, st);
     case 16: return launch_tile_nw<OutT, 16, 2>(p, npairs, st);
@@ -217,8 +227,8 @@ cudaError_t launch_tile(const TileArgs &p, int64_t npairs, cudaStream_t st) {
 template <int FMT>
 cudaError_t launch_tile_fmt(const TileArgs &p, int64_t npairs, cudaStream_t st) {
   switch (tile_warps_for(p.nx, p.ny, npairs)) {
-    case 1: return launch_tile_nw<float, 1, 32, FMT>(p, npairs, st);
-    case 2: case 4: case 6: return launch_tile_nw<float, 4, 8, FMT>(p, npairs, st);
+    case 1: return launch_tile_nw<float, 1, VHP_NW1_MINB, FMT>(p, npairs, st);
+    case 2: case 4: case 6: return launch_tile_nw<float, 4, VHP_NW4_MINB, FMT>(p, npairs, st);
     default: return launch_tile_nw<float, 8, VHP_NW8_MINB, FMT>(p, npairs, st);
   }
 }
