@@ -239,12 +239,13 @@ vhp_status vhp_context_last_transport(const vhp_context *ctx, int64_t *d2h_bytes
 /* The host half of the packed transport on its own (no GPU needed; tests): expand one packed
  * chunk into dst[0 .. valid_bytes) with `threads` host threads.  Unit u (128 bytes; the last
  * one may be partial) is literal iff bit u % 32 of mask[u / 32]; the literal units of mask
- * word w lie back to back from literals + 128 * word_base[w]; a uniform unit repeats the
- * element desc[u] (elem_bytes = 4 or 8 bytes each).  literals == NULL is the direct mode: the
+ * word w lie back to back from literals + 128 * word_base[w]; a uniform unit is all 0.0 or,
+ * where bit u % 32 of vmask[u / 32] is set, all 1.0 (elements of elem_bytes = 4 or 8 bytes: fp32 /
+ * fp64; units of equal elements of any other value are literal).  literals == NULL is the direct mode: the
  * literal units are taken to be in dst already (the device stored them there) and are left
  * untouched; only the uniform units are written. */
 vhp_status vhp_expand_packed_chunk(const uint32_t *mask, const uint32_t *word_base,
-                                   const void *desc, int elem_bytes, const void *literals,
+                                   const uint32_t *vmask, int elem_bytes, const void *literals,
                                    int64_t nunits, int64_t valid_bytes, void *dst, int threads);
 
 /* ---- a5: batched ray casting (raycasting + the all-targets loop) -------------

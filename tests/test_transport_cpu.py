@@ -16,7 +16,8 @@ def lib():
 
 
 def pack_numpy(raw: bytes, elem: int):
-    """uniform / literal classification of 128-byte units, as pack_results_kernel does it"""
+    """uniform (all 0.0 or all 1.0) / literal classification of 128-byte units, as
+    pack_results_kernel does it; returns (mask, word_base, vmask, literals, nunits, nlit)"""
     valid = len(raw)
     nunits = (valid + UNIT - 1) // UNIT
     nwords = (nunits + 31) // 32
@@ -26,23 +27,26 @@ def pack_numpy(raw: bytes, elem: int):
     units = buf.reshape(nunits, UNIT)
     mask = np.zeros(nwords, np.uint32)
     base = np.zeros(nwords, np.uint32)
-    desc = np.zeros(nwords * 32, np.uint32 if elem == 4 else np.uint64)
+    vmask = np.zeros(nwords, np.uint32)
+    one = np.array([1.0], np.float32 if elem == 4 else np.float64).view(np.uint32 if elem == 4 else np.uint64)[0]
     lits, cursor = [], 0
     # words in a scrambled order, like warps racing for the cursor
     order = np.random.default_rng(7).permutation(nwords)
     slots = {}
     for w in order:
-        m, mine = 0, []
+        m, vm, mine = 0, 0, []
         for u in range(32):
             k = w * 32 + u
             if k >= nunits:
                 break
             e = units[k].view(np.uint32 if elem == 4 else np.uint64)
-            desc[k] = e[0]
-            if not (e == e[0]).all():
+            if (e == e[0]).all() and e[0] in (0, one):
+                vm |= (1 << u) if e[0] == one else 0
+            else:
                 m |= 1 << u
                 mine.append(units[k])
         mask[w] = m
+        vmask[w] = vm
         base[w] = cursor
         slots[int(w)] = (cursor, mine)
         cursor += len(mine)
@@ -50,7 +54,7 @@ def pack_numpy(raw: bytes, elem: int):
     for w, (b0, mine) in slots.items():
         for i, u in enumerate(mine):
             lit[(b0 + i) * UNIT:(b0 + i + 1) * UNIT] = u
-    return mask, base, desc, lit, nunits, cursor
+    return mask, base, vmask, lit, nunits, cursor
 
 
 @pytest.mark.parametrize("elem,dtype", [(4, np.float32), (8, np.float64)])
@@ -65,12 +69,12 @@ def test_expand_restores_the_bytes(lib, elem, dtype, n, offset, threads):
         kind = int(g.integers(0, 3))
         a[i:i + l] = 0 if kind == 0 else (1 if kind == 1 else g.random(len(a[i:i + l])))
     raw = a.tobytes()
-    mask, base, desc, lit, nunits, nlit = pack_numpy(raw, elem)
+    mask, base, vmask, lit, nunits, nlit = pack_numpy(raw, elem)
     # destination with a chosen misalignment (offset 0: the non-temporal path)
     backing = np.full(len(raw) + 64 + 16, 0xEE, np.uint8)
     start = (-backing.ctypes.data) % 16 + offset
     dst = backing[start:start + len(raw)]
-    st = lib.vhp_expand_packed_chunk(mask.ctypes.data, base.ctypes.data, desc.ctypes.data, elem,
+    st = lib.vhp_expand_packed_chunk(mask.ctypes.data, base.ctypes.data, vmask.ctypes.data, elem,
                                      lit.ctypes.data, nunits, len(raw), dst.ctypes.data, threads)
     assert st == 0
     assert dst.tobytes() == raw
@@ -100,7 +104,7 @@ def test_direct_mode_leaves_literal_units_alone(lib, elem, dtype):
         a[i:i + l] = g.random(len(a[i:i + l])) if g.random() < 0.5 else 0
     raw = a.tobytes()
     assert len(raw) % UNIT == 0
-    mask, base, desc, lit, nunits, nlit = pack_numpy(raw, elem)
+    mask, base, vmask, lit, nunits, nlit = pack_numpy(raw, elem)
     dst = np.full(len(raw), 0xEE, np.uint8)
     litmask = np.zeros(nunits, bool)
     for w in range(len(mask)):
@@ -110,7 +114,7 @@ def test_direct_mode_leaves_literal_units_alone(lib, elem, dtype):
     src = np.frombuffer(raw, np.uint8).reshape(nunits, UNIT)
     view = dst.reshape(nunits, UNIT)
     view[litmask] = src[litmask]          # what the device's stores leave behind
-    st = lib.vhp_expand_packed_chunk(mask.ctypes.data, base.ctypes.data, desc.ctypes.data, elem,
+    st = lib.vhp_expand_packed_chunk(mask.ctypes.data, base.ctypes.data, vmask.ctypes.data, elem,
                                      None, nunits, len(raw), dst.ctypes.data, 3)
     assert st == 0
     assert dst.tobytes() == raw
@@ -133,11 +137,11 @@ def test_expand_fuzz(lib):
         else:
             a = np.repeat(g.integers(0, 3, nelem // 40 + 1), 40)[:nelem].astype(dt)  # flat runs
         raw = a.tobytes()
-        mask, base, desc, lit, nunits, _ = pack_numpy(raw, elem)
+        mask, base, vmask, lit, nunits, _ = pack_numpy(raw, elem)
         dst = np.full(len(raw) + 32, 0xEE, np.uint8)
         off = (-dst.ctypes.data) % 16
         d = dst[off:off + len(raw)]
-        assert lib.vhp_expand_packed_chunk(mask.ctypes.data, base.ctypes.data, desc.ctypes.data, elem,
+        assert lib.vhp_expand_packed_chunk(mask.ctypes.data, base.ctypes.data, vmask.ctypes.data, elem,
                                            lit.ctypes.data, nunits, len(raw), d.ctypes.data, 2) == 0
         assert d.tobytes() == raw
         assert (dst[off + len(raw):] == 0xEE).all()

@@ -425,7 +425,7 @@ vhp_status run_host_packed(vhp_context *ctx, Op op, int nmaps, int nx, int ny, c
     VhpPackedChunk c;
     c.mask = (const uint32_t *)(meta + kVhpPackMetaHead);
     c.word_base = c.mask + nwords;
-    c.desc = meta + kVhpPackMetaHead + (size_t)nwords * 8;
+    c.vmask = c.word_base + nwords;
     c.elem_bytes = (int)esz;
     c.literals = direct ? nullptr : (const char *)ctx->h_pack_lit[s];
     c.tail = meta + 16;
@@ -521,7 +521,7 @@ struct vhp_packed {
     VhpPackedChunk v;
     v.mask = (const uint32_t *)(meta + kVhpPackMetaHead);
     v.word_base = v.mask + nwords;
-    v.desc = meta + kVhpPackMetaHead + (size_t)nwords * 8;
+    v.vmask = v.word_base + nwords;
     v.elem_bytes = elem;
     v.literals = c.nlit ? blocks[c.lit_blk].p + c.lit_off : meta; // (never read when there are none)
     v.nunits = c.nunits;
@@ -1493,7 +1493,7 @@ vhp_status vhp_context_last_transport(const vhp_context *ctx, int64_t *d2h_bytes
 }
 
 vhp_status vhp_expand_packed_chunk(const uint32_t *mask, const uint32_t *word_base,
-                                   const void *desc, int elem_bytes, const void *literals,
+                                   const uint32_t *vmask, int elem_bytes, const void *literals,
                                    int64_t nunits, int64_t valid_bytes, void *dst, int threads) {
   if (elem_bytes != 4 && elem_bytes != 8)
     return fail(nullptr, VHP_ERR_INVALID_ARG, "vhp_expand_packed_chunk: elem_bytes is 4 or 8");
@@ -1501,12 +1501,12 @@ vhp_status vhp_expand_packed_chunk(const uint32_t *mask, const uint32_t *word_ba
       valid_bytes <= (nunits - 1) * (int64_t)kVhpPackUnit)
     return fail(nullptr, VHP_ERR_INVALID_ARG, "vhp_expand_packed_chunk: nunits does not match valid_bytes");
   if (nunits == 0) return VHP_OK;
-  if (!mask || !word_base || !desc || !dst)
+  if (!mask || !word_base || !vmask || !dst)
     return fail(nullptr, VHP_ERR_INVALID_ARG, "vhp_expand_packed_chunk: null argument");
   VhpPackedChunk c;
   c.mask = mask;
   c.word_base = word_base;
-  c.desc = desc;
+  c.vmask = vmask;
   c.elem_bytes = elem_bytes;
   c.literals = (const char *)literals;
   c.dst = (char *)dst;

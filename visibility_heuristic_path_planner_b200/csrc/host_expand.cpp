@@ -48,11 +48,17 @@ inline void copy_unit(char *dst, const char *src, size_t bytes) {
   }
 }
 
+// eight bytes of a uniform unit of ones (the pattern has the period of one element)
+inline uint64_t ones_pattern(int elem_bytes) {
+  return elem_bytes == 4 ? 0x3f8000003f800000ull : 0x3ff0000000000000ull;
+}
+
 void expand_words(const VhpPackedChunk &c, int64_t w0, int64_t w1) {
   const int64_t last_word = (c.nunits + 31) / 32 - 1;
+  const uint64_t one = ones_pattern(c.elem_bytes);
   for (int64_t w = w0; w < w1; ++w) {
     if (!c.literals && (int)(w & 15) < c.gpu_share && w != last_word) continue; // the device's word
-    const uint32_t m = c.mask[w];
+    const uint32_t m = c.mask[w], vm = c.vmask[w];
     const char *lit = c.literals ? c.literals + (size_t)c.word_base[w] * kVhpPackUnit : nullptr;
     const int64_t u0 = w * 32;
     const int nu = (int)std::min<int64_t>(32, c.nunits - u0);
@@ -67,14 +73,7 @@ void expand_words(const VhpPackedChunk &c, int64_t w0, int64_t w1) {
           std::memcpy(c.dst + off, c.tail, bytes);            // unit is ours (from the meta block)
         }
       } else {
-        uint64_t pat;
-        if (c.elem_bytes == 4) {
-          const uint32_t e = static_cast<const uint32_t *>(c.desc)[u0 + u];
-          pat = ((uint64_t)e << 32) | e;
-        } else {
-          pat = static_cast<const uint64_t *>(c.desc)[u0 + u];
-        }
-        fill_unit(c.dst + off, pat, bytes);
+        fill_unit(c.dst + off, ((vm >> u) & 1u) ? one : 0ull, bytes);
       }
     }
   }
@@ -101,22 +100,13 @@ void vhp_expand_bytes(const VhpPackedChunk &c, size_t b0, size_t b1, char *out) 
       // themselves took their slots in no particular order)
       const size_t lit = (size_t)c.word_base[u >> 5] + __builtin_popcount(m & (uint32_t)((1ull << (u & 31)) - 1ull));
       std::memcpy(dst, c.literals + lit * kVhpPackUnit + (lo - ub), hi - lo);
-    } else if (c.elem_bytes == 4) {
-      const uint32_t e = static_cast<const uint32_t *>(c.desc)[u];
-      if (hi - lo == (size_t)kVhpPackUnit && (((uintptr_t)dst) & 15u) == 0) {
-        fill_unit(dst, ((uint64_t)e << 32) | e, kVhpPackUnit);
-      } else {
-        uint32_t blk[kVhpPackUnit / 4];
-        for (uint32_t &b : blk) b = e;
-        std::memcpy(dst, reinterpret_cast<const char *>(blk) + ((lo - ub) & 3u), hi - lo);
-      }
     } else {
-      const uint64_t e = static_cast<const uint64_t *>(c.desc)[u];
+      const uint64_t pat = ((c.vmask[u >> 5] >> (u & 31)) & 1u) ? ones_pattern(c.elem_bytes) : 0ull;
       if (hi - lo == (size_t)kVhpPackUnit && (((uintptr_t)dst) & 15u) == 0) {
-        fill_unit(dst, e, kVhpPackUnit);
-      } else {
+        fill_unit(dst, pat, kVhpPackUnit);
+      } else { // a partial unit starts on an element boundary: keep the phase inside the 8-byte pattern
         uint64_t blk[kVhpPackUnit / 8 + 1];
-        for (uint64_t &b : blk) b = e;
+        for (uint64_t &b : blk) b = pat;
         std::memcpy(dst, reinterpret_cast<const char *>(blk) + ((lo - ub) & 7u), hi - lo);
       }
     }

@@ -3,14 +3,15 @@
 // The host-buffer entry points are PCIe-bound: 4096 sweeps of a 1000 x 1000 grid are 16.4 GB
 // of fp32 results per call against a kernel that produces them in 2.5 ms.  Visibility fields
 // are mostly flat (lit 1.0, shadow 0.0), so before a chunk of results leaves the device this
-// kernel classifies every 128-byte unit of it as uniform (all elements equal, bit for bit) or
-// literal, and compacts the literal units into one stream.  Only the stream and one element
-// plus a bit of meta data per unit cross PCIe; host threads rebuild the exact bytes
-// (host_expand.cpp).
+// kernel classifies every 128-byte unit of it as uniform (all elements 0.0 or all elements 1.0,
+// bit for bit) or literal, and compacts the literal units into one stream.  Only the stream and
+// two bits of meta data per unit cross PCIe; host threads rebuild the exact bytes
+// (host_expand.cpp).  (A unit of equal elements of any other value is literal: they are rare, and
+// shipping one element per unit to cover them doubled the bytes of the empty-grid batch.)
 //
 // Units are 128 bytes (32 fp32 / 16 fp64 cells): one warp-wide 16-byte load covers four units,
 // eight loads make a mask word (32 units = 4 KB), kept in registers.  A unit is uniform when
-// the eight lanes that hold it see one element value, bit for bit.  The literal units of a word
+// the eight lanes that hold it see one element value, 0.0 or 1.0, bit for bit.  The literal units of a word
 // get consecutive slots of the stream from one atomicAdd on the chunk's cursor.
 //
 // Direct mode (the caller's buffer is pinned, mapped and 16-byte aligned): the literal units
@@ -34,7 +35,7 @@ constexpr int kUnitsPerLoad = 32 / kLanesPerUnit; // 4
 constexpr int kLoadsPerWord = 32 / kUnitsPerLoad; // 8
 
 // meta block: [cursor u64, pad to 16][tail unit][mask u32 x nwords][word_base u32 x nwords]
-//             [desc ELEM bytes x 32*nwords]
+//             [vmask u32 x nwords]   (vmask bit u: the uniform unit u of the word is 1.0, else 0.0)
 template <int ELEM> // element size in bytes: 4 or 8
 __global__ void __launch_bounds__(256)
 pack_results_kernel(const uint4 *__restrict__ in, const int64_t nunits, unsigned char *__restrict__ meta,
@@ -45,7 +46,7 @@ pack_results_kernel(const uint4 *__restrict__ in, const int64_t nunits, unsigned
   uint4 *tail = reinterpret_cast<uint4 *>(meta + 16);
   uint32_t *mask = reinterpret_cast<uint32_t *>(meta + kVhpPackMetaHead);
   uint32_t *word_base = mask + nwords;
-  unsigned char *desc = meta + kVhpPackMetaHead + (size_t)nwords * 8;
+  uint32_t *vmask = word_base + nwords;
   const int lane = threadIdx.x & 31;
   const int grp = lane / kLanesPerUnit;        // which of the four units of a load this lane holds
   const int lead = grp * kLanesPerUnit;        // first lane of that unit
@@ -57,7 +58,7 @@ pack_results_kernel(const uint4 *__restrict__ in, const int64_t nunits, unsigned
     const int64_t q0 = u0 * kLanesPerUnit + lane; // this lane's 16-byte piece of load 0
     uint4 v[kLoadsPerWord];
     uint32_t lit_bits = 0;                       // bit k: this lane's unit of load k is literal
-    uint32_t d0 = 0, d1 = 0;                     // first element of unit u0 + lane
+    uint32_t one_bits = 0;                       // bit k: ... is uniform 1.0
 #pragma unroll
     for (int k = 0; k < kLoadsPerWord; ++k) {
       const int64_t q = q0 + 32 * k;
@@ -66,26 +67,28 @@ pack_results_kernel(const uint4 *__restrict__ in, const int64_t nunits, unsigned
       const bool same = ELEM == 4 ? (v[k].x == f0 && v[k].y == f0 && v[k].z == f0 && v[k].w == f0)
                                   : (v[k].x == f0 && v[k].y == f1 && v[k].z == f0 && v[k].w == f1);
       const uint32_t b = __ballot_sync(kAllLanes, same);
-      const bool uni = ((b >> lead) & 0xffu) == 0xffu;
+      const bool zero = ELEM == 4 ? f0 == 0u : (f0 | f1) == 0u;
+      const bool one = ELEM == 4 ? f0 == 0x3f800000u : (f0 == 0u && f1 == 0x3ff00000u);
+      const bool uni = ((b >> lead) & 0xffu) == 0xffu && (zero || one);
       lit_bits |= (uni ? 0u : 1u) << k;
-      // lane j describes unit u0 + j = unit (j % 4) of load j / 4
-      const uint32_t e0 = __shfl_sync(kAllLanes, v[k].x, (lane % kUnitsPerLoad) * kLanesPerUnit);
-      const uint32_t e1 = __shfl_sync(kAllLanes, v[k].y, (lane % kUnitsPerLoad) * kLanesPerUnit);
-      if (lane / kUnitsPerLoad == k) {
-        d0 = e0;
-        d1 = e1;
-      }
+      one_bits |= ((uni && one) ? 1u : 0u) << k;
     }
-    // mask bit of unit u0 + 4k + g  <-  lit_bits bit k of any lane of group g
-    uint32_t m = 0;
+    // mask bit of unit u0 + 4k + g  <-  lit_bits bit k of any lane of group g (vm, one_bits likewise)
+    uint32_t m = 0, vm = 0;
 #pragma unroll
     for (int k = 0; k < kLoadsPerWord; ++k) {
       const uint32_t b = __ballot_sync(kAllLanes, (lit_bits >> k) & 1u);
+      const uint32_t bo = __ballot_sync(kAllLanes, (one_bits >> k) & 1u);
 #pragma unroll
-      for (int g = 0; g < kUnitsPerLoad; ++g)
+      for (int g = 0; g < kUnitsPerLoad; ++g) {
         m |= ((b >> (g * kLanesPerUnit)) & 1u) << (k * kUnitsPerLoad + g);
+        vm |= ((bo >> (g * kLanesPerUnit)) & 1u) << (k * kUnitsPerLoad + g);
+      }
     }
-    if (u0 + 32 > nunits) m &= (1u << (int)(nunits - u0)) - 1u; // units past the end of the chunk
+    if (u0 + 32 > nunits) { // units past the end of the chunk
+      m &= (1u << (int)(nunits - u0)) - 1u;
+      vm &= (1u << (int)(nunits - u0)) - 1u;
+    }
     if (host_dst && (int)(w & 15) < gpu_share && w != nwords - 1) {
       // a word the device delivers completely (mask 0: nothing left for the host to copy)
 #pragma unroll
@@ -93,6 +96,7 @@ pack_results_kernel(const uint4 *__restrict__ in, const int64_t nunits, unsigned
       if (lane == 0) {
         mask[w] = 0u;
         word_base[w] = 0u;
+        vmask[w] = 0u;
       }
       continue;
     }
@@ -102,9 +106,8 @@ pack_results_kernel(const uint4 *__restrict__ in, const int64_t nunits, unsigned
     if (lane == 0) {
       mask[w] = m;
       word_base[w] = base;
+      vmask[w] = vm;
     }
-    if (ELEM == 4) reinterpret_cast<uint32_t *>(desc)[u0 + lane] = d0; // padded to whole words
-    else reinterpret_cast<uint2 *>(desc)[u0 + lane] = make_uint2(d0, d1);
 #pragma unroll
     for (int k = 0; k < kLoadsPerWord; ++k) {
       const int u = k * kUnitsPerLoad + grp; // this lane's unit of load k

@@ -28,14 +28,14 @@ struct VhpDevBuf {
 // ---- packed result transport (result_transport.cu, host_expand.cpp) -------------
 // A chunk of results (flat bytes) is cut into 128-byte units; 32 consecutive units make a
 // mask word.  Unit u of word w is literal iff bit u of mask[w]; the literal units of a word
-// are stored back to back from unit slot word_base[w] of the literal stream; every unit has
-// its first element in desc[] (the fill value of a uniform unit).
+// are stored back to back from unit slot word_base[w] of the literal stream; a uniform unit is
+// all 0.0 or, where bit u of vmask[w] is set, all 1.0 (elements of elem_bytes).
 constexpr int kVhpPackUnit = 128;
 constexpr int kVhpPackMetaHead = 16 + kVhpPackUnit; // cursor (padded) + the tail unit
 struct VhpPackedChunk {
   const uint32_t *mask = nullptr;
   const uint32_t *word_base = nullptr;
-  const void *desc = nullptr;     // elem_bytes per unit
+  const uint32_t *vmask = nullptr; // bit u of word w: the uniform unit 32 w + u is 1.0 (else 0.0)
   int elem_bytes = 4;             // 4 or 8
   const char *literals = nullptr; // null: direct mode, the device stored the literal units in dst
   const char *tail = nullptr;     // direct mode: a partial, literal last unit
@@ -45,10 +45,11 @@ struct VhpPackedChunk {
   int64_t nunits = 0;
   size_t valid_bytes = 0;         // bytes of the chunk (the last unit may be partial)
 };
-// device-side meta block of one packed chunk: [cursor u64, pad to 16][tail unit][mask][word_base][desc]
+// device-side meta block of one packed chunk: [cursor u64, pad to 16][tail unit][mask][word_base][vmask]
 inline size_t vhp_pack_meta_bytes(int64_t nunits, int elem_bytes) {
   const int64_t nwords = (nunits + 31) / 32;
-  return kVhpPackMetaHead + (size_t)nwords * 8 + (size_t)nwords * 32 * elem_bytes;
+  (void)elem_bytes;
+  return kVhpPackMetaHead + (size_t)nwords * 12;
 }
 // in: nunits * 128 readable bytes.  Writes the meta block and either the literal stream
 // (host_dst null) or the literal units themselves to host_dst + 128 * unit (a device-accessible
