@@ -114,8 +114,8 @@ vhp_status vhp_visibility_batch_dev(vhp_context *ctx, const uint8_t *d_occ,
                                     vhp_dtype dtype, void *d_out);
 /* The same fields as a PACKED HANDLE: lossless, expanded lazily.  Visibility fields are mostly flat
  * (lit 1.0, shadow 0.0), so the device cuts the results into 128-byte units that are either uniform
- * (one element value) or literal, and only one element per unit plus the literal units cross PCIe --
- * 6.5 % of the bytes on the empty 1000 x 1000 batch.  vhp_visibility_batch expands that stream into the
+ * (all 0.0 or all 1.0) or literal, and only two bits per unit plus the literal units cross PCIe --
+ * 3.5 % of the bytes on the empty 1000 x 1000 batch.  vhp_visibility_batch expands that stream into the
  * caller's buffer inside the call (and is then bound by the host's memory bandwidth: 16 GB of stores per
  * 4096 sweeps); this entry point keeps it, in pinned host memory owned by the handle, and
  * vhp_packed_expand rebuilds any range of pairs on demand, bit-identical to what vhp_visibility_batch
@@ -215,7 +215,7 @@ vhp_status vhp_release_maps_dev(vhp_context *ctx);
  * Their results are far larger than what PCIe moves in the time the kernels need (16.4 GB per
  * 4096 sweeps of a 1000 x 1000 grid), and visibility fields are mostly flat (lit 1.0, shadow
  * 0.0).  In the packed transport the device classifies every 128-byte unit of a chunk of
- * results as uniform or literal; only the literal units and one element plus one bit of meta
+ * results as uniform (all 0.0 / all 1.0) or literal; only the literal units and two bits of meta
  * data per unit cross PCIe (into pinned, 16-byte aligned memory the GPU stores the literal
  * units straight to their place), and host threads (env VHP_HOST_THREADS, default: all cores, at most 32) rebuild
  * the exact bytes in `out`.  `out` is bit-identical either way.

@@ -3,7 +3,7 @@
 // The host-buffer entry points (vhp_visibility_batch, vhp_raycast_batch) return fields in
 // which long runs of cells carry one value (lit: 1.0, shadow: 0.0).  Instead of moving
 // every byte over PCIe, the device packs each chunk of results into 128-byte units that
-// are either "uniform" (one element value) or "literal" (copied verbatim); this file
+// are either "uniform" (all 0.0 or all 1.0) or "literal" (copied verbatim); this file
 // expands a packed chunk into the caller's buffer with a small pool of host threads using
 // non-temporal stores.  The expansion is lossless: the caller's buffer ends up bit-identical
 // to the device buffer.
