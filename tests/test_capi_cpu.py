@@ -69,3 +69,12 @@ def test_headers_compile_standalone(tmp_path):
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
                     "-I", inc, str(c)], check=True)
     subprocess.run(["g++", "-std=c++20", "-Wall", "-fsyntax-only", "-I", inc, str(cpp)], check=True)
+
+
+def test_packed_handle_api_without_a_handle(lib):
+    """The accessors of the packed handle take NULL; expanding without a handle is an argument error."""
+    import numpy as np
+    assert lib.vhp_packed_pairs(None) == 0 and lib.vhp_packed_bytes(None) == 0 and lib.vhp_packed_pair_bytes(None) == 0
+    out = np.zeros(4, np.float32)
+    assert lib.vhp_packed_expand(None, 0, 1, out.ctypes.data, 1) == -1
+    lib.vhp_packed_destroy(None)
