@@ -248,6 +248,13 @@ vhp_status vhp_expand_packed_chunk(const uint32_t *mask, const uint32_t *word_ba
                                    const uint32_t *vmask, int elem_bytes, const void *literals,
                                    int64_t nunits, int64_t valid_bytes, void *dst, int threads);
 
+/* The lazy form of the same expansion (what vhp_packed_expand runs per chunk): bytes [b0, b1) of the
+ * chunk -> out[0 .. b1 - b0), single-threaded; b0 a multiple of elem_bytes, literals not NULL. */
+vhp_status vhp_expand_packed_range(const uint32_t *mask, const uint32_t *word_base,
+                                   const uint32_t *vmask, int elem_bytes, const void *literals,
+                                   int64_t nunits, int64_t valid_bytes, int64_t b0, int64_t b1,
+                                   void *out);
+
 /* ---- a5: batched ray casting (raycasting + the all-targets loop) -------------
  * out[p][y][x] = visibilityRayCasting_ after the loop of benchmark() :228-232 on
  * a field initialised to 1.0 (reset() :45). */

@@ -147,3 +147,44 @@ def test_expand_fuzz(lib):
         assert (dst[off + len(raw):] == 0xEE).all()
 
     run()
+
+
+def test_expand_range_fuzz(lib):
+    """vhp_expand_packed_range (the lazy expansion behind vhp_packed_expand): any byte range that starts
+    on an element boundary -- inside units, across mask words, up to a partial last unit -- equals that
+    slice of the original bytes, and nothing outside the destination is touched."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=80, deadline=None)
+    @given(st.integers(1, 12000), st.sampled_from([4, 8]), st.integers(0, 2), st.integers(0, 2 ** 31))
+    def run(nelem, elem, kind, seed):
+        g = np.random.default_rng(seed)
+        dt = np.float32 if elem == 4 else np.float64
+        a = np.ones(nelem, dt)
+        if kind == 0:
+            a = g.random(nelem).astype(dt)                                        # nothing compresses
+        elif kind == 1:
+            for _ in range(max(1, nelem // 300)):                                # flat runs and ramps
+                i, l = int(g.integers(0, nelem)), int(g.integers(1, 500))
+                k = int(g.integers(0, 4))
+                a[i:i + l] = (0, 1, 0.25)[k] if k < 3 else g.random(len(a[i:i + l]))
+        raw = a.tobytes()
+        mask, base, vmask, lit, nunits, _ = pack_numpy(raw, elem)
+        for _ in range(6):
+            e0 = int(g.integers(0, nelem))
+            e1 = int(g.integers(e0, nelem + 1))
+            b0, b1 = e0 * elem, e1 * elem
+            dst = np.full(b1 - b0 + 48, 0xEE, np.uint8)
+            off = 16 + int(g.integers(0, 2)) * 4
+            assert lib.vhp_expand_packed_range(mask.ctypes.data, base.ctypes.data, vmask.ctypes.data, elem,
+                                               lit.ctypes.data, nunits, len(raw), b0, b1,
+                                               dst[off:].ctypes.data) == 0
+            assert dst[off:off + b1 - b0].tobytes() == raw[b0:b1]
+            assert (dst[:off] == 0xEE).all() and (dst[off + b1 - b0:] == 0xEE).all()
+
+    run()
+    z = np.zeros(64, np.uint32)
+    assert lib.vhp_expand_packed_range(z.ctypes.data, z.ctypes.data, z.ctypes.data, 4, z.ctypes.data, 1, 100, 2, 50,
+                                       z.ctypes.data) != 0   # not on an element boundary
+    assert lib.vhp_expand_packed_range(z.ctypes.data, z.ctypes.data, z.ctypes.data, 4, z.ctypes.data, 1, 100, 0, 104,
+                                       z.ctypes.data) != 0   # past the end

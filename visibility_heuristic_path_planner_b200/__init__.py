@@ -126,6 +126,7 @@ def load_library(build_if_missing: bool = True):
     lib.vhp_context_set_result_transport.argtypes = [vp, i32]
     lib.vhp_context_set_result_gpu_share.argtypes = [vp, i32]
     lib.vhp_expand_packed_chunk.argtypes = [vp, vp, vp, i32, vp, i64, i64, vp, i32]
+    lib.vhp_expand_packed_range.argtypes = [vp, vp, vp, i32, vp, i64, i64, i64, i64, vp]
     lib.vhp_context_last_transport.argtypes = [vp, C.POINTER(i64), C.POINTER(i64),
                                                C.POINTER(C.c_int32)]
     lib.vhp_environment_draw.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]

@@ -1517,6 +1517,31 @@ vhp_status vhp_expand_packed_chunk(const uint32_t *mask, const uint32_t *word_ba
   return VHP_OK;
 }
 
+vhp_status vhp_expand_packed_range(const uint32_t *mask, const uint32_t *word_base,
+                                   const uint32_t *vmask, int elem_bytes, const void *literals,
+                                   int64_t nunits, int64_t valid_bytes, int64_t b0, int64_t b1, void *out) {
+  if (elem_bytes != 4 && elem_bytes != 8)
+    return fail(nullptr, VHP_ERR_INVALID_ARG, "vhp_expand_packed_range: elem_bytes is 4 or 8");
+  if (nunits < 0 || valid_bytes < 0 || valid_bytes > nunits * (int64_t)kVhpPackUnit ||
+      valid_bytes <= (nunits - 1) * (int64_t)kVhpPackUnit)
+    return fail(nullptr, VHP_ERR_INVALID_ARG, "vhp_expand_packed_range: nunits does not match valid_bytes");
+  if (b0 < 0 || b1 < b0 || b1 > valid_bytes || b0 % elem_bytes != 0)
+    return fail(nullptr, VHP_ERR_INVALID_ARG, "vhp_expand_packed_range: bad byte range");
+  if (b0 == b1) return VHP_OK;
+  if (!mask || !word_base || !vmask || !literals || !out)
+    return fail(nullptr, VHP_ERR_INVALID_ARG, "vhp_expand_packed_range: null argument");
+  VhpPackedChunk c;
+  c.mask = mask;
+  c.word_base = word_base;
+  c.vmask = vmask;
+  c.elem_bytes = elem_bytes;
+  c.literals = (const char *)literals;
+  c.nunits = nunits;
+  c.valid_bytes = (size_t)valid_bytes;
+  vhp_expand_bytes(c, (size_t)b0, (size_t)b1, (char *)out);
+  return VHP_OK;
+}
+
 vhp_status vhp_context_set_planner_loop(vhp_context *ctx, int mode) {
   if (!ctx || mode < 0 || mode > 3) return fail(ctx, VHP_ERR_INVALID_ARG, "vhp_context_set_planner_loop: bad argument");
   ctx->grid_loop_mode = mode;
