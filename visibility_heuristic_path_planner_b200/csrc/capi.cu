@@ -855,6 +855,13 @@ vhp_status run_runs_host(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx
     unsigned long long *d_ptr = (unsigned long long *)(misc + o_ptr);
     cudaError_t e = vhp_launch_runs_count(d_cnt, np, ny, d_off, d_tot, total, d_ptr, ctx->stream, &ctx->launches);
     unsigned long long new_total = 0;
+    // the row counts and pair offsets are final here: they leave on the copy stream, under the write pass
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_done[0], ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[0], 0);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(row_count + (size_t)p0 * ny, d_cnt, (size_t)np * ny * 2, cudaMemcpyDeviceToHost, ctx->copy_stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(pair_ptr + p0, d_ptr, ((size_t)np + 1) * 8, cudaMemcpyDeviceToHost, ctx->copy_stream);
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(&new_total, d_ptr + np, 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -870,15 +877,13 @@ vhp_status run_runs_host(vhp_context *ctx, const uint8_t *occ, int nmaps, int nx
                               (uint16_t *)ctx->b_out[1].p, ctx->sm_count, ctx->stream, &ctx->launches);
     if (e == cudaSuccess && chunk_elems)
       e = cudaMemcpyAsync(trans + total, ctx->b_out[1].p, chunk_elems * 2, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(row_count + (size_t)p0 * ny, d_cnt, (size_t)np * ny * 2, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(pair_ptr + p0, d_ptr, ((size_t)np + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); // the device buffers are reused by the next chunk
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->copy_stream);
     if (e != cudaSuccess) { result = cuda_fail(ctx, e, "row runs: write"); break; }
     ctx->last_d2h_bytes += (int64_t)(chunk_elems * 2 + (size_t)np * ny * 2 + ((size_t)np + 1) * 8 + 8);
     total = new_total;
   }
+  (void)cudaStreamSynchronize(ctx->copy_stream); // (a failed chunk may have left its copies in flight)
   ctx->planes_sticky = false;
   ctx->tile_src = nullptr;
   ctx->last_result_bytes = ctx->last_d2h_bytes;
